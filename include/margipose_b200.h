@@ -1,0 +1,100 @@
+/* margipose_b200 -- C ABI of the B200-native MargiPose hot path.
+ *
+ * The reference (anibali/margipose) is pure Python/PyTorch and has no FFI; its extension
+ * point is the Python model registry (src/margipose/models/__init__.py:10-27).  This header
+ * is the drop-in boundary underneath the Python mirror of that registry
+ * (margipose_b200/models): every entry point replaces a group of PyTorch op sites on the
+ * reference's hot path (cited per function; paths relative to /root/reference/src/margipose/).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated;
+ *  - the caller owns and allocates every buffer, including workspaces; no hidden allocation;
+ *  - work is enqueued on `stream` (a cudaStream_t passed as void*); no implicit sync;
+ *  - returns 0 on success, a negative MP_ERR_* code otherwise; never throws;
+ *    mp_last_error() returns a thread-local description of the last failure;
+ *  - tensors: heatmaps / logits are fp32 NCHW-contiguous (B, J, H, W) as in the reference;
+ *    network activations are bf16 NHWC (see DESIGN.md "Data layout").
+ */
+#ifndef MARGIPOSE_B200_H
+#define MARGIPOSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MP_API __attribute__((visibility("default")))
+#else
+#define MP_API
+#endif
+
+#define MP_OK 0
+#define MP_ERR_ARG (-1)
+#define MP_ERR_CUDA (-2)
+#define MP_ERR_UNSUPPORTED (-3)
+
+/* ABI version of this header; bumped on any signature change. */
+MP_API int mp_abi_version(void);
+/* Thread-local message for the last non-zero return code. Host pointer, never NULL. */
+MP_API const char* mp_last_error(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused tail.
+ *
+ * mp_tail_fwd: for each (b, j) and each non-NULL plane k in {xy, zy, xz}:
+ *   p_k = softmax(in_k) over H*W if from_logits else in_k          dsntnn.py:124-130
+ *   (a_k, b_k) = (E[col coord], E[row coord]) of p_k               dsntnn.py:39-62,84-96
+ *   js_k = JS(p_k || normalised Gaussian(mu_k, sigma px))          dsntnn.py:154-232
+ *   coords = (a_xy, b_xy, (a_zy + b_xz)/2)                         models/margipose_model.py:254-261
+ *   loss  = js_xy + js_zy + js_xz + |coords - target|              models/margipose_model.py:236-252
+ *          (2D samples, valid_depth[b]==0: js_xy + |coords.xy - target.xy|, :223-234)
+ * Outputs are all optional (NULL skips): prob[k] (B,J,H,W); ab[k] (B,J,2); js[k] (B,J);
+ * coords (B,J,3); loss (B,J) (added to the existing value when accumulate != 0, which is how
+ * the per-stage sum of the reference's loss loop is formed).
+ * Targets: `target` (B,J,3) xyz drives the fused loss (per-plane means are derived as
+ * xy->(x,y), zy->(z,y), xz->(x,z)); alternatively mu[k] (B,J,2) gives an explicit (col,row)
+ * mean for plane k (generic js_reg_losses).  valid_depth: (B) int32 or NULL (= all 3D).
+ * pixelwise: 1 = 'jsd', 0 = None (models/margipose_model.py:215-221).
+ */
+MP_API int mp_tail_fwd(const float* const in[3], int from_logits, float* const prob[3],
+                float* const ab[3], float* const js[3], const float* const mu[3],
+                const float* target, const int* valid_depth, float* coords, float* loss,
+                int accumulate, int pixelwise, double sigma, int B, int J, int H, int W,
+                void* stream);
+
+/* mp_tail_bwd: gradient of the tail w.r.t. its input planes (replaces the ~440-node autograd
+ * graph of one stage's tail).  For each plane k with out[k] != NULL:
+ *   D = gup_k + w_js * dJS/dp + c_col * col_coord + c_row * row_coord
+ *   out_k = project ? p_k * (D - sum(p_k * D)) : D        (project = softmax backward)
+ * Fused mode (target != NULL): coefficients come from saved `coords` (B,J,3), `target` and
+ * w (B,J) = dL/dloss[b,j].  Generic mode: coef[k] (B,J,3) = (w_js, c_col, c_row), with mu[k]
+ * (B,J,2) required when w_js is used.  gup[k] (upstream gradient on p_k) may be NULL. */
+MP_API int mp_tail_bwd(const float* const prob[3], const float* const gup[3], float* const out[3],
+                const float* target, const float* coords, const float* w,
+                const int* valid_depth, const float* const mu[3], const float* const coef[3],
+                int project, int pixelwise, double sigma, int B, int J, int H, int W,
+                void* stream);
+
+/* average_loss (dsntnn.py:99-121): out2[0] = sum(l*mask)/max(sum(mask),1), out2[1] = denominator.
+ * mask may be NULL (= ones). */
+MP_API int mp_masked_mean_fwd(const float* losses, const float* mask, int n, float* out2, void* stream);
+MP_API int mp_masked_mean_bwd(const float* grad_out, const float* mask, const float* mean_den, int n,
+                       float* grad_losses, void* stream);
+
+/* euclidean_losses (dsntnn.py:133-151) over n points of d dims, and its gradient. */
+MP_API int mp_euclid_fwd(const float* actual, const float* target, int n, int d, float* out, void* stream);
+MP_API int mp_euclid_bwd(const float* grad_out, const float* actual, const float* target,
+                  const float* dist, int n, int d, float* grad_actual, void* stream);
+
+/* make_gauss (dsntnn.py:154-195), 2D: mu (BJ,2) = (col,row) means in normalised units,
+ * out (BJ,H,W); sigma in pixels. */
+MP_API int mp_make_gauss(const float* mu, float* out, int normalize, double sigma, int BJ, int H, int W,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARGIPOSE_B200_H */

@@ -1,0 +1,92 @@
+"""ctypes binding of the C ABI declared in include/margipose_b200.h.
+
+The product path has NO fallback: if the shared library is missing or a call fails, we raise.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'libmargipose_b200.so')
+
+c_float_p = ctypes.c_void_p   # device pointers travel as integers
+c_int = ctypes.c_int
+c_double = ctypes.c_double
+c_void_p = ctypes.c_void_p
+c_size_t = ctypes.c_size_t
+PlaneTable = ctypes.c_void_p * 3
+
+_lib = None
+
+
+class MargiposeB200Error(RuntimeError):
+    pass
+
+
+def _signatures():
+    P, I, D, PT = c_void_p, c_int, c_double, ctypes.POINTER(PlaneTable)
+    return {
+        'mp_abi_version': (I, []),
+        'mp_last_error': (ctypes.c_char_p, []),
+        'mp_tail_fwd': (I, [PT, I, PT, PT, PT, PT, P, P, P, P, I, I, D, I, I, I, I, P]),
+        'mp_tail_bwd': (I, [PT, PT, PT, P, P, P, P, PT, PT, I, I, D, I, I, I, I, P]),
+        'mp_masked_mean_fwd': (I, [P, P, I, P, P]),
+        'mp_masked_mean_bwd': (I, [P, P, P, I, P, P]),
+        'mp_euclid_fwd': (I, [P, P, I, I, P, P]),
+        'mp_euclid_bwd': (I, [P, P, P, P, I, I, P, P]),
+        'mp_make_gauss': (I, [P, P, I, D, I, I, I, P]),
+    }
+
+
+def lib():
+    """Loads (once) and returns the C-ABI library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MargiposeB200Error(
+                'margipose_b200: %s not found. Build it with `python -m margipose_b200.build` '
+                '(or __graft_entry__.build()); there is no CPU / PyTorch fallback.' % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _signatures().items():
+            fn = getattr(handle, name)     # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_signatures().keys())
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().mp_last_error().decode('utf-8', 'replace')
+        raise MargiposeB200Error('%s failed (code %d): %s' % (what or 'margipose_b200 call', rc, msg))
+
+
+def ptr(t):
+    """Device pointer of a tensor (or NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def planes(ts):
+    """A 3-entry pointer table (host array of device pointers) for the plane-wise entry points."""
+    if ts is None:
+        return None
+    return ctypes.byref(PlaneTable(*[(t.data_ptr() if t is not None else None) for t in ts]))
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise MargiposeB200Error(
+                'margipose_b200 runs on CUDA tensors only (got a %s tensor); there is no CPU path'
+                % t.device)

@@ -1,0 +1,63 @@
+// Shared helpers for the margipose_b200 CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define MP_OK 0
+#define MP_ERR_ARG (-1)       // invalid argument (shape / alignment / null pointer)
+#define MP_ERR_CUDA (-2)      // a CUDA runtime call failed; see mp_last_error()
+#define MP_ERR_UNSUPPORTED (-3)
+
+void mp_set_error(const char* fmt, ...);
+
+#define MP_CHECK_ARG(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      mp_set_error(__VA_ARGS__);           \
+      return MP_ERR_ARG;                   \
+    }                                      \
+  } while (0)
+
+#define MP_CHECK_LAUNCH(name)                                              \
+  do {                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                  \
+    if (e__ != cudaSuccess) {                                              \
+      mp_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return MP_ERR_CUDA;                                                  \
+    }                                                                      \
+  } while (0)
+
+#define MP_CUDA(call)                                                          \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      mp_set_error("%s failed: %s", #call, cudaGetErrorString(e__));           \
+      return MP_ERR_CUDA;                                                      \
+    }                                                                          \
+  } while (0)
+
+static inline bool mp_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}

@@ -1,0 +1,653 @@
+// Fused differentiable tail of MargiPose for sm_100a: spatial softmax, soft-argmax (DSNT)
+// expectations, xy/zy/xz marginal combination, Gaussian target rendering, Jensen-Shannon
+// regulariser and Euclidean loss -- one forward kernel and one backward kernel.
+//
+// Replaces (reference, /root/reference/src/margipose/): dsntnn.py:124-130 (flat_softmax),
+// :84-96 (dsnt), :154-195 (make_gauss), :198-232 (js_reg_losses), :133-151
+// (euclidean_losses); models/margipose_model.py:223-261 (loss assembly, heatmaps_to_coords).
+// Maths: SURVEY.md Appendix B.
+//
+// Bandwidth-bound: one CTA per (sample, joint) walks the three H x W planes; every heatmap
+// element is read once (128-bit loads) and written once (128-bit stores); all reductions are
+// warp shuffles + one shared-memory hop; no atomics, so results are run-to-run deterministic.
+// Algorithmic HBM bytes per element: forward 8 (read logit, write prob), backward 12
+// (read prob, read upstream grad, write dlogit).
+#include "common.cuh"
+#include "../../include/margipose_b200.h"
+
+namespace {
+
+constexpr int NT = 256;        // threads per CTA
+constexpr int NW = NT / 32;
+constexpr int MAX_DIM = 1024;  // max H or W
+constexpr float KL_EPS = 1e-24f;
+
+struct Geom {
+  int H, W, HW;
+  float cw_step, cw_first, ch_step, ch_first;  // pixel centre c_i = i * step + first
+  float kw, kh;                                // Gaussian exponent scale per axis
+};
+
+struct FwdArgs {
+  const float* in[3];
+  float* prob[3];        // nullable
+  float* ab[3];          // nullable: (BJ, 2) per-plane (col, row) expectations
+  float* js[3];          // nullable: (BJ) per-plane JS divergence
+  const float* target;   // nullable: (BJ, 3) xyz targets  (fused mode)
+  const float* mu[3];    // nullable: (BJ, 2) per-plane (col,row) targets (generic mode)
+  const int* valid_depth;  // nullable: (B) 1 = 3D sample, 0 = 2D sample
+  float* coords;         // nullable: (BJ, 3)
+  float* loss;           // nullable: (BJ)
+  int J;
+  int accumulate;        // loss[bj] += instead of =
+  int pixelwise;         // 1 = JSD term on, 0 = off
+  Geom g;
+};
+
+struct BwdArgs {
+  const float* prob[3];
+  const float* gup[3];    // nullable upstream grad on probs
+  float* out[3];          // nullable -> plane skipped
+  const float* target;    // fused mode: (BJ,3)
+  const float* coords;    // fused mode: (BJ,3) saved by forward
+  const float* w;         // fused mode: (BJ) dL/dloss[b,j]
+  const int* valid_depth;
+  const float* mu[3];     // generic mode: (BJ,2) per plane (needed when coef w_js != 0)
+  const float* coef[3];   // generic mode: (BJ,3) = (w_js, c_col, c_row) per plane
+  int J;
+  int pixelwise;
+  Geom g;
+};
+
+__device__ __forceinline__ float centre(int i, float step, float first) {
+  return __fadd_rn(__fmul_rn((float)i, step), first);   // same op order as dsntnn.py:35-36
+}
+
+template <int N>
+__device__ __forceinline__ void block_sum(float (&x)[N], float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < N; ++k) x[k] = warp_sum(x[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) red[wid * N + k] = x[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += red[w * N + k];   // fixed order -> deterministic
+    x[k] = s;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_max(v);
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float m = red[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  return m;
+}
+
+template <int VEC, int V>
+__device__ __forceinline__ void plane_load(const float* __restrict__ src, int HW, float fill,
+                                           float (&x)[V * VEC]) {
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int e = (threadIdx.x + i * NT) * VEC;
+    if (VEC == 4) {
+      if (e < HW) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src + e));
+        x[i * VEC + 0] = t.x; x[i * VEC + 1] = t.y; x[i * VEC + 2] = t.z; x[i * VEC + 3] = t.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) x[i * VEC + k] = fill;
+      }
+    } else {
+      x[i] = (e < HW) ? __ldg(src + e) : fill;
+    }
+  }
+}
+
+template <int VEC, int V>
+__device__ __forceinline__ void plane_store(float* __restrict__ dst, int HW,
+                                            const float (&x)[V * VEC]) {
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int e = (threadIdx.x + i * NT) * VEC;
+    if (e < HW) {
+      if (VEC == 4) {
+        *reinterpret_cast<float4*>(dst + e) =
+            make_float4(x[i * VEC + 0], x[i * VEC + 1], x[i * VEC + 2], x[i * VEC + 3]);
+      } else {
+        dst[e] = x[i];
+      }
+    }
+  }
+}
+
+// Renders the separable Gaussian factors for one plane into shared memory and returns
+// 1 / (sum + eps) (dsntnn.py:169-195).
+__device__ __forceinline__ float gauss_factors(const Geom& g, float mu_col, float mu_row,
+                                               float* s_ecol, float* s_erow, float* red) {
+  float part[2] = {0.f, 0.f};
+  for (int i = threadIdx.x; i < g.W; i += NT) {
+    const float d = centre(i, g.cw_step, g.cw_first) - mu_col;
+    const float e = expf(__fmul_rn(__fmul_rn(d, d), g.kw));
+    s_ecol[i] = e;
+    part[0] += e;
+  }
+  for (int i = threadIdx.x; i < g.H; i += NT) {
+    const float d = centre(i, g.ch_step, g.ch_first) - mu_row;
+    const float e = expf(__fmul_rn(__fmul_rn(d, d), g.kh));
+    s_erow[i] = e;
+    part[1] += e;
+  }
+  block_sum<2>(part, red);   // also publishes s_ecol / s_erow (it syncs)
+  return 1.0f / (part[0] * part[1] + KL_EPS);
+}
+
+// One plane, forward. x: logits (FROM_LOGITS) or probabilities in; probabilities out.
+// Results (a = col expectation, b = row expectation, js) are returned to every thread.
+template <int VEC, int V, bool FROM_LOGITS>
+__device__ __forceinline__ void plane_forward(float (&x)[V * VEC], const Geom& g, bool want_js,
+                                              float mu_col, float mu_row, float* s_ecol,
+                                              float* s_erow, float* red, float& a, float& b,
+                                              float& js) {
+  float ginv = 0.f;
+  if (want_js) ginv = gauss_factors(g, mu_col, mu_row, s_ecol, s_erow, red);
+
+  if (FROM_LOGITS) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < V * VEC; ++i) m = fmaxf(m, x[i]);
+    m = block_max(m, red);
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int e = (threadIdx.x + i * NT) * VEC;
+      const int h = e / g.W, w0 = e - h * g.W;
+      const float ch = centre(h, g.ch_step, g.ch_first);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float ex = expf(x[i * VEC + k] - m);   // fill = -inf -> 0
+        x[i * VEC + k] = ex;
+        acc[0] += ex;
+        acc[1] += ex * centre(w0 + k, g.cw_step, g.cw_first);
+        acc[2] += ex * ch;
+      }
+    }
+    block_sum<3>(acc, red);
+    const float inv = 1.0f / acc[0];
+#pragma unroll
+    for (int i = 0; i < V * VEC; ++i) x[i] *= inv;
+    a = acc[1] * inv;
+    b = acc[2] * inv;
+    js = 0.f;
+    if (want_js) {
+      float part[1] = {0.f};
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int e = (threadIdx.x + i * NT) * VEC;
+        if (e < g.HW) {
+          const int h = e / g.W, w0 = e - h * g.W;
+          const float er = s_erow[h] * ginv;
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const float p = x[i * VEC + k];
+            const float q = s_ecol[w0 + k] * er;
+            const float lm = logf(0.5f * (p + q) + KL_EPS);
+            part[0] += p * (logf(p + KL_EPS) - lm) + q * (logf(q + KL_EPS) - lm);
+          }
+        }
+      }
+      block_sum<1>(part, red);
+      js = 0.5f * part[0];
+    }
+  } else {
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int e = (threadIdx.x + i * NT) * VEC;
+      if (e < g.HW) {
+        const int h = e / g.W, w0 = e - h * g.W;
+        const float ch = centre(h, g.ch_step, g.ch_first);
+        const float er = want_js ? s_erow[h] * ginv : 0.f;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const float p = x[i * VEC + k];
+          acc[0] += p * centre(w0 + k, g.cw_step, g.cw_first);
+          acc[1] += p * ch;
+          if (want_js) {
+            const float q = s_ecol[w0 + k] * er;
+            const float lm = logf(0.5f * (p + q) + KL_EPS);
+            acc[2] += p * (logf(p + KL_EPS) - lm) + q * (logf(q + KL_EPS) - lm);
+          }
+        }
+      }
+    }
+    block_sum<3>(acc, red);
+    a = acc[0];
+    b = acc[1];
+    js = 0.5f * acc[2];
+  }
+}
+
+template <int VEC, int V, bool FROM_LOGITS>
+__global__ void __launch_bounds__(NT) tail_fwd_kernel(const FwdArgs A) {
+  __shared__ float s_ecol[MAX_DIM];
+  __shared__ float s_erow[MAX_DIM];
+  __shared__ float red[NW * 3];
+  constexpr bool PRELOAD = (V * VEC <= 16);
+  constexpr int NP = PRELOAD ? 3 : 1;
+  float x[NP][V * VEC];
+
+  const int bj = blockIdx.x;
+  const int b = bj / A.J;
+  const size_t off = (size_t)bj * A.g.HW;
+  const float fill = FROM_LOGITS ? -INFINITY : 0.f;
+  const bool is3d = A.valid_depth ? (A.valid_depth[b] != 0) : true;
+
+  float tx = 0.f, ty = 0.f, tz = 0.f;
+  if (A.target) {
+    tx = A.target[bj * 3 + 0];
+    ty = A.target[bj * 3 + 1];
+    tz = A.target[bj * 3 + 2];
+  }
+
+  if (PRELOAD) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (A.in[k]) plane_load<VEC, V>(A.in[k] + off, A.g.HW, fill, x[PRELOAD ? k : 0]);
+  }
+
+  float ea[3] = {0.f, 0.f, 0.f}, eb[3] = {0.f, 0.f, 0.f}, js[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (!A.in[k]) continue;
+    float(&xk)[V * VEC] = x[PRELOAD ? k : 0];
+    if (!PRELOAD) plane_load<VEC, V>(A.in[k] + off, A.g.HW, fill, xk);
+    // per-plane target (col, row): xy -> (x, y); zy -> (z, y); xz -> (x, z)
+    float mc, mr;
+    bool want_js;
+    if (A.mu[k]) {
+      mc = A.mu[k][bj * 2 + 0];
+      mr = A.mu[k][bj * 2 + 1];
+      want_js = A.js[k] != nullptr;
+    } else {
+      mc = (k == 1) ? tz : tx;
+      mr = (k == 2) ? tz : ty;
+      want_js = A.target && A.pixelwise && (A.loss || A.js[k]) && (k == 0 || is3d);
+    }
+    plane_forward<VEC, V, FROM_LOGITS>(xk, A.g, want_js, mc, mr, s_ecol, s_erow, red, ea[k], eb[k],
+                                       js[k]);
+    if (A.prob[k]) plane_store<VEC, V>(A.prob[k] + off, A.g.HW, xk);
+    if (threadIdx.x == 0) {
+      if (A.ab[k]) {
+        A.ab[k][bj * 2 + 0] = ea[k];
+        A.ab[k][bj * 2 + 1] = eb[k];
+      }
+      if (A.js[k]) A.js[k][bj] = js[k];
+    }
+  }
+
+  if (threadIdx.x == 0) {
+    // margipose_model.py:254-261
+    const float px = ea[0], py = eb[0], pz = 0.5f * (ea[1] + eb[2]);
+    if (A.coords) {
+      A.coords[bj * 3 + 0] = px;
+      A.coords[bj * 3 + 1] = py;
+      A.coords[bj * 3 + 2] = pz;
+    }
+    if (A.loss && A.target) {
+      const float dx = px - tx, dy = py - ty, dz = pz - tz;
+      float l;
+      if (is3d) l = js[0] + js[1] + js[2] + sqrtf(dx * dx + dy * dy + dz * dz);
+      else l = js[0] + sqrtf(dx * dx + dy * dy);
+      A.loss[bj] = A.accumulate ? A.loss[bj] + l : l;
+    }
+  }
+}
+
+// Backward of one (sample, joint): for each plane
+//   D = G + w_js * dJS/dp + c_col * c_w + c_row * c_h ;  out = PROJECT ? p * (D - sum(p*D)) : D
+template <int VEC, int V, bool PROJECT>
+__global__ void __launch_bounds__(NT) tail_bwd_kernel(const BwdArgs A) {
+  __shared__ float s_ecol[MAX_DIM];
+  __shared__ float s_erow[MAX_DIM];
+  __shared__ float red[NW * 3];
+  float p[V * VEC], d[V * VEC];
+
+  const int bj = blockIdx.x;
+  const int b = bj / A.J;
+  const size_t off = (size_t)bj * A.g.HW;
+  const bool is3d = A.valid_depth ? (A.valid_depth[b] != 0) : true;
+
+  float tx = 0.f, ty = 0.f, tz = 0.f, w = 0.f, ddx = 0.f, ddy = 0.f, ddz = 0.f;
+  if (A.target) {   // fused mode: derive the coefficients from saved coords / targets
+    tx = A.target[bj * 3 + 0];
+    ty = A.target[bj * 3 + 1];
+    tz = A.target[bj * 3 + 2];
+    w = A.w[bj];
+    const float dx = A.coords[bj * 3 + 0] - tx, dy = A.coords[bj * 3 + 1] - ty;
+    const float dz = is3d ? A.coords[bj * 3 + 2] - tz : 0.f;
+    // d dist / d coord = diff / dist; infinite at dist == 0, like the reference (dsntnn.py:149-150)
+    const float inv = w / sqrtf(dx * dx + dy * dy + dz * dz);
+    ddx = dx * inv;
+    ddy = dy * inv;
+    ddz = dz * inv;
+  }
+
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (!A.out[k]) continue;
+    float wjs, cc, cr, mc, mr;
+    if (A.coef[k]) {
+      wjs = A.coef[k][bj * 3 + 0];
+      cc = A.coef[k][bj * 3 + 1];
+      cr = A.coef[k][bj * 3 + 2];
+      mc = A.mu[k] ? A.mu[k][bj * 2 + 0] : 0.f;
+      mr = A.mu[k] ? A.mu[k][bj * 2 + 1] : 0.f;
+    } else if (A.target) {
+      mc = (k == 1) ? tz : tx;
+      mr = (k == 2) ? tz : ty;
+      wjs = (A.pixelwise && (k == 0 || is3d)) ? w : 0.f;
+      cc = (k == 0) ? ddx : (k == 1 ? 0.5f * ddz : 0.f);
+      cr = (k == 0) ? ddy : (k == 2 ? 0.5f * ddz : 0.f);
+    } else {
+      wjs = cc = cr = mc = mr = 0.f;
+    }
+    const bool want_js = (A.coef[k] ? (A.mu[k] != nullptr) : (wjs != 0.f));
+    float ginv = 0.f;
+    if (want_js) ginv = gauss_factors(A.g, mc, mr, s_ecol, s_erow, red);
+
+    plane_load<VEC, V>(A.prob[k] + off, A.g.HW, 0.f, p);
+    if (A.gup[k]) {
+      plane_load<VEC, V>(A.gup[k] + off, A.g.HW, 0.f, d);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V * VEC; ++i) d[i] = 0.f;
+    }
+    float part[1] = {0.f};
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int e = (threadIdx.x + i * NT) * VEC;
+      if (e < A.g.HW) {
+        const int h = e / A.g.W, w0 = e - h * A.g.W;
+        const float lin_r = cr * centre(h, A.g.ch_step, A.g.ch_first);
+        const float er = want_js ? s_erow[h] * ginv : 0.f;
+#pragma unroll
+        for (int kk = 0; kk < VEC; ++kk) {
+          const float pv = p[i * VEC + kk];
+          float dv = d[i * VEC + kk] + cc * centre(w0 + kk, A.g.cw_step, A.g.cw_first) + lin_r;
+          if (want_js) {
+            const float q = s_ecol[w0 + kk] * er;
+            const float m = 0.5f * (pv + q);
+            const float djs = 0.5f * (logf(pv + KL_EPS) - logf(m + KL_EPS) + pv / (pv + KL_EPS) -
+                                      m / (m + KL_EPS));
+            dv += wjs * djs;
+          }
+          d[i * VEC + kk] = dv;
+          part[0] += pv * dv;
+        }
+      }
+    }
+    if (PROJECT) {
+      block_sum<1>(part, red);
+#pragma unroll
+      for (int i = 0; i < V * VEC; ++i) d[i] = p[i] * (d[i] - part[0]);
+    }
+    plane_store<VEC, V>(A.out[k] + off, A.g.HW, d);
+    if (!PROJECT && want_js) __syncthreads();   // s_ecol / s_erow are rewritten by the next plane
+  }
+}
+
+// ---- masked mean (dsntnn.py:99-121): out[0] = sum(l*m)/max(sum(m),1), out[1] = that denominator
+__global__ void __launch_bounds__(NT) masked_mean_kernel(const float* __restrict__ l,
+                                                         const float* __restrict__ m, int n,
+                                                         float* __restrict__ out) {
+  __shared__ float red[NW * 2];
+  float acc[2] = {0.f, 0.f};
+  for (int i = threadIdx.x; i < n; i += NT) {
+    const float mv = m ? m[i] : 1.f;
+    acc[0] += l[i] * mv;
+    acc[1] += mv;
+  }
+  block_sum<2>(acc, red);
+  if (threadIdx.x == 0) {
+    const float den = fmaxf(acc[1], 1.f);
+    out[0] = acc[0] / den;
+    out[1] = den;
+  }
+}
+
+// grad_l[i] = g[0] * m[i] / den
+__global__ void masked_mean_bwd_kernel(const float* __restrict__ g, const float* __restrict__ m,
+                                       const float* __restrict__ mean_den, int n,
+                                       float* __restrict__ gl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) gl[i] = g[0] * (m ? m[i] : 1.f) / mean_den[1];
+}
+
+// euclidean_losses (dsntnn.py:133-151): out[i] = |a[i,:] - t[i,:]|_2
+__global__ void euclid_fwd_kernel(const float* __restrict__ a, const float* __restrict__ t, int n,
+                                  int d, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < d; ++k) {
+    const float v = a[i * d + k] - t[i * d + k];
+    s += v * v;
+  }
+  out[i] = sqrtf(s);
+}
+
+// grad_a[i,k] = g[i] * (a - t)[i,k] / dist[i]   (infinite at dist == 0, as in the reference)
+__global__ void euclid_bwd_kernel(const float* __restrict__ g, const float* __restrict__ a,
+                                  const float* __restrict__ t, const float* __restrict__ dist,
+                                  int n, int d, float* __restrict__ ga) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float s = g[i] / dist[i];
+  for (int k = 0; k < d; ++k) ga[i * d + k] = (a[i * d + k] - t[i * d + k]) * s;
+}
+
+// make_gauss (dsntnn.py:154-195), 2D: out[bj, h, w]
+__global__ void __launch_bounds__(NT) make_gauss_kernel(const float* __restrict__ mu,
+                                                        float* __restrict__ out, Geom g,
+                                                        int normalize) {
+  __shared__ float s_ecol[MAX_DIM];
+  __shared__ float s_erow[MAX_DIM];
+  __shared__ float red[NW * 3];
+  const int bj = blockIdx.x;
+  float ginv = gauss_factors(g, mu[bj * 2 + 0], mu[bj * 2 + 1], s_ecol, s_erow, red);
+  if (!normalize) ginv = 1.f;
+  float* dst = out + (size_t)bj * g.HW;
+  for (int e = threadIdx.x; e < g.HW; e += NT) {
+    const int h = e / g.W, w = e - h * g.W;
+    dst[e] = s_ecol[w] * (s_erow[h] * ginv);
+  }
+}
+
+Geom make_geom(int H, int W, double sigma) {
+  Geom g;
+  g.H = H; g.W = W; g.HW = H * W;
+  g.cw_step = (float)(2.0 / W);
+  g.cw_first = (float)(-(W - 1.0) / W);
+  g.ch_step = (float)(2.0 / H);
+  g.ch_first = (float)(-(H - 1.0) / H);
+  const double sw = 2.0 * sigma / W, sh = 2.0 * sigma / H;
+  g.kw = (float)(-0.5 * (1.0 / sw) * (1.0 / sw));
+  g.kh = (float)(-0.5 * (1.0 / sh) * (1.0 / sh));
+  return g;
+}
+
+template <bool FROM_LOGITS>
+int launch_fwd(const FwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
+  const int HW = A.g.HW;
+#define MP_FWD(VEC, V) tail_fwd_kernel<VEC, V, FROM_LOGITS><<<BJ, NT, 0, st>>>(A)
+  if (vec4) {
+    const int v = (HW / 4 + NT - 1) / NT;
+    if (v <= 1) MP_FWD(4, 1);
+    else if (v <= 2) MP_FWD(4, 2);
+    else if (v <= 4) MP_FWD(4, 4);
+    else if (v <= 8) MP_FWD(4, 8);
+    else if (v <= 16) MP_FWD(4, 16);
+    else return MP_ERR_UNSUPPORTED;
+  } else {
+    const int v = (HW + NT - 1) / NT;
+    if (v <= 4) MP_FWD(1, 4);
+    else if (v <= 16) MP_FWD(1, 16);
+    else if (v <= 64) MP_FWD(1, 64);
+    else return MP_ERR_UNSUPPORTED;
+  }
+#undef MP_FWD
+  return MP_OK;
+}
+
+template <bool PROJECT>
+int launch_bwd(const BwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
+  const int HW = A.g.HW;
+#define MP_BWD(VEC, V) tail_bwd_kernel<VEC, V, PROJECT><<<BJ, NT, 0, st>>>(A)
+  if (vec4) {
+    const int v = (HW / 4 + NT - 1) / NT;
+    if (v <= 1) MP_BWD(4, 1);
+    else if (v <= 2) MP_BWD(4, 2);
+    else if (v <= 4) MP_BWD(4, 4);
+    else if (v <= 8) MP_BWD(4, 8);
+    else if (v <= 16) MP_BWD(4, 16);
+    else return MP_ERR_UNSUPPORTED;
+  } else {
+    const int v = (HW + NT - 1) / NT;
+    if (v <= 4) MP_BWD(1, 4);
+    else if (v <= 16) MP_BWD(1, 16);
+    else if (v <= 64) MP_BWD(1, 64);
+    else return MP_ERR_UNSUPPORTED;
+  }
+#undef MP_BWD
+  return MP_OK;
+}
+
+bool all_aligned16(const float* const* p, int n) {
+  for (int i = 0; i < n; ++i)
+    if (p[i] && !mp_aligned16(p[i])) return false;
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mp_tail_fwd(const float* const in[3], int from_logits, float* const prob[3],
+                float* const ab[3], float* const js[3], const float* const mu[3],
+                const float* target, const int* valid_depth, float* coords, float* loss,
+                int accumulate, int pixelwise, double sigma, int B, int J, int H, int W,
+                void* stream) {
+  MP_CHECK_ARG(in && (in[0] || in[1] || in[2]), "mp_tail_fwd: no input plane");
+  MP_CHECK_ARG(B > 0 && J > 0 && H > 0 && W > 0, "mp_tail_fwd: bad shape %dx%dx%dx%d", B, J, H, W);
+  MP_CHECK_ARG(H <= MAX_DIM && W <= MAX_DIM, "mp_tail_fwd: H, W must be <= %d", MAX_DIM);
+  MP_CHECK_ARG((size_t)H * W <= 16384, "mp_tail_fwd: H*W must be <= 16384");
+  MP_CHECK_ARG(!(loss && !target), "mp_tail_fwd: loss output needs targets");
+  FwdArgs A;
+  for (int k = 0; k < 3; ++k) {
+    A.in[k] = in[k];
+    A.prob[k] = prob ? prob[k] : nullptr;
+    A.ab[k] = ab ? ab[k] : nullptr;
+    A.js[k] = js ? js[k] : nullptr;
+    A.mu[k] = mu ? mu[k] : nullptr;
+    MP_CHECK_ARG(!(A.js[k] && !A.mu[k] && !target), "mp_tail_fwd: js output needs a target");
+  }
+  A.target = target; A.valid_depth = valid_depth; A.coords = coords; A.loss = loss;
+  A.J = J; A.accumulate = accumulate; A.pixelwise = pixelwise;
+  A.g = make_geom(H, W, sigma);
+  const bool vec4 = (W % 4 == 0) && all_aligned16(A.in, 3) &&
+                    all_aligned16((const float* const*)A.prob, 3);
+  int rc = from_logits ? launch_fwd<true>(A, B * J, vec4, (cudaStream_t)stream)
+                       : launch_fwd<false>(A, B * J, vec4, (cudaStream_t)stream);
+  if (rc != MP_OK) { mp_set_error("mp_tail_fwd: unsupported plane size %dx%d", H, W); return rc; }
+  MP_CHECK_LAUNCH("mp_tail_fwd");
+  return MP_OK;
+}
+
+int mp_tail_bwd(const float* const prob[3], const float* const gup[3], float* const out[3],
+                const float* target, const float* coords, const float* w,
+                const int* valid_depth, const float* const mu[3], const float* const coef[3],
+                int project, int pixelwise, double sigma, int B, int J, int H, int W,
+                void* stream) {
+  MP_CHECK_ARG(prob && out, "mp_tail_bwd: null plane table");
+  MP_CHECK_ARG(B > 0 && J > 0 && H > 0 && W > 0, "mp_tail_bwd: bad shape");
+  MP_CHECK_ARG(H <= MAX_DIM && W <= MAX_DIM && (size_t)H * W <= 16384, "mp_tail_bwd: plane too large");
+  MP_CHECK_ARG(!(target && (!coords || !w)), "mp_tail_bwd: fused mode needs coords and w");
+  BwdArgs A;
+  for (int k = 0; k < 3; ++k) {
+    A.prob[k] = prob[k];
+    A.gup[k] = gup ? gup[k] : nullptr;
+    A.out[k] = out[k];
+    A.mu[k] = mu ? mu[k] : nullptr;
+    A.coef[k] = coef ? coef[k] : nullptr;
+    MP_CHECK_ARG(!(A.out[k] && !A.prob[k]), "mp_tail_bwd: output plane %d without probabilities", k);
+  }
+  A.target = target; A.coords = coords; A.w = w; A.valid_depth = valid_depth;
+  A.J = J; A.pixelwise = pixelwise;
+  A.g = make_geom(H, W, sigma);
+  const bool vec4 = (W % 4 == 0) && all_aligned16(A.prob, 3) && all_aligned16(A.gup, 3) &&
+                    all_aligned16((const float* const*)A.out, 3);
+  int rc = project ? launch_bwd<true>(A, B * J, vec4, (cudaStream_t)stream)
+                   : launch_bwd<false>(A, B * J, vec4, (cudaStream_t)stream);
+  if (rc != MP_OK) { mp_set_error("mp_tail_bwd: unsupported plane size %dx%d", H, W); return rc; }
+  MP_CHECK_LAUNCH("mp_tail_bwd");
+  return MP_OK;
+}
+
+int mp_euclid_fwd(const float* actual, const float* target, int n, int d, float* out, void* stream) {
+  MP_CHECK_ARG(actual && target && out && n >= 0 && d > 0, "mp_euclid_fwd: bad arguments");
+  if (n == 0) return MP_OK;
+  euclid_fwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(actual, target, n, d, out);
+  MP_CHECK_LAUNCH("mp_euclid_fwd");
+  return MP_OK;
+}
+
+int mp_euclid_bwd(const float* grad_out, const float* actual, const float* target,
+                  const float* dist, int n, int d, float* grad_actual, void* stream) {
+  MP_CHECK_ARG(grad_out && actual && target && dist && grad_actual && n >= 0 && d > 0,
+               "mp_euclid_bwd: bad arguments");
+  if (n == 0) return MP_OK;
+  euclid_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(grad_out, actual, target, dist,
+                                                                      n, d, grad_actual);
+  MP_CHECK_LAUNCH("mp_euclid_bwd");
+  return MP_OK;
+}
+
+int mp_make_gauss(const float* mu, float* out, int normalize, double sigma, int BJ, int H, int W,
+                  void* stream) {
+  MP_CHECK_ARG(mu && out && BJ > 0 && H > 0 && W > 0 && H <= MAX_DIM && W <= MAX_DIM,
+               "mp_make_gauss: bad arguments");
+  make_gauss_kernel<<<BJ, NT, 0, (cudaStream_t)stream>>>(mu, out, make_geom(H, W, sigma), normalize);
+  MP_CHECK_LAUNCH("mp_make_gauss");
+  return MP_OK;
+}
+
+int mp_masked_mean_fwd(const float* losses, const float* mask, int n, float* out2, void* stream) {
+  MP_CHECK_ARG(losses && out2 && n >= 0, "mp_masked_mean_fwd: bad arguments");
+  masked_mean_kernel<<<1, NT, 0, (cudaStream_t)stream>>>(losses, mask, n, out2);
+  MP_CHECK_LAUNCH("mp_masked_mean_fwd");
+  return MP_OK;
+}
+
+int mp_masked_mean_bwd(const float* grad_out, const float* mask, const float* mean_den, int n,
+                       float* grad_losses, void* stream) {
+  MP_CHECK_ARG(grad_out && mean_den && grad_losses && n >= 0, "mp_masked_mean_bwd: bad arguments");
+  if (n == 0) return MP_OK;
+  masked_mean_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(grad_out, mask, mean_den,
+                                                                           n, grad_losses);
+  MP_CHECK_LAUNCH("mp_masked_mean_bwd");
+  return MP_OK;
+}
+
+}  // extern "C"
