@@ -161,7 +161,7 @@ class _MaskedMean(torch.autograd.Function):
                                        stream_ptr(losses.device)), 'mp_masked_mean_fwd')
         ctx.save_for_backward(mask, out2)
         ctx.shape = losses.shape
-        return out2[0]
+        return out2[0].clone()
 
     @staticmethod
     def backward(ctx, g):
