@@ -94,6 +94,85 @@ MP_API int mp_euclid_bwd(const float* grad_out, const float* actual, const float
 MP_API int mp_make_gauss(const float* mu, float* out, int normalize, double sigma, int BJ, int H, int W,
                   void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Convolutions as implicit GEMM on the 5th-gen tensor cores.
+ *
+ * Replaces every nn.Conv2d / nn.ConvTranspose2d op site of models/margipose_model.py:33,67-68,
+ * 73-74,79-82,125,145 and of the truncated torchvision ResNet (:130-135), forward and backward.
+ *
+ * Activations are bf16 NHWC with the channel count padded to a multiple of 64.  A source tensor
+ * is handed over as a 5-D view (innermost first: C, W, P, H, N) so that one TMA box
+ * {64 channels, tile_w, 1, tile_rows, 1} fetches the operand tile of a filter tap already
+ * shifted (zero padding = TMA out-of-bounds fill) and, for stride-2 taps, already decimated:
+ *   stride 1:  dims (C, W, 1, H, N)
+ *   stride 2:  dims (2C, W/2, 2, H/2, N) over the same memory; a tap picks the column parity
+ *              through c0 (0 or C) and the row parity through p.
+ */
+#define MP_MAX_TAPS 10
+
+typedef struct mp_view5 {
+  const void* ptr;       /* bf16 */
+  int64_t dim[5];        /* elements, innermost first */
+  int64_t stride[5];     /* elements; stride[0] == 1; (stride * 2 bytes) % 16 == 0 */
+} mp_view5;
+
+typedef struct mp_tap {
+  int32_t src;           /* source view index (0 or 1) */
+  int32_t c0;            /* coordinate offset in dim 0 */
+  int32_t dw;            /* added to the tile's w origin (dim 1) */
+  int32_t p;             /* coordinate in dim 2 */
+  int32_t dh;            /* added to the tile's h origin (dim 3) */
+  int32_t koff;          /* igemm: first K column of this tap in wmat; wgrad: tap slot in dw */
+} mp_tap;
+
+/* out[n,h,w,:] (+= res[n,h,w,:]) = sum_taps sum_c src[tap](n, h+dh, w+dw, c) * wmat[:, koff + c]
+ * over an (n_img, out_h, out_w) output pixel grid.  wmat is bf16 [w_rows][w_k] row-major with
+ * w_rows % 32 == 0 (zero rows beyond the real Cout).  The output pixel (n,h,w) lives at
+ * out + n*out_sn + h*out_sh + w*out_sw (elements; lets a transposed conv scatter one output
+ * parity class per launch); out_c channels are stored (multiple of 8).  When stat_sum/stat_sq are
+ * given, the per-channel sum and sum of squares of the stored (bf16-rounded) values are
+ * atomically added to them -- the BatchNorm batch statistics of nn.BatchNorm2d in train mode. */
+typedef struct mp_igemm_args {
+  mp_view5 src[2];
+  const void* wmat;
+  int64_t w_rows, w_k;
+  int32_t n_taps;
+  mp_tap taps[MP_MAX_TAPS];
+  int32_t cblocks;                 /* 64-channel blocks per tap */
+  int32_t n_img, out_h, out_w;
+  void* out;                       /* bf16 */
+  const void* res;                 /* bf16, same addressing as out, or NULL */
+  int64_t out_sn, out_sh, out_sw;
+  int32_t out_c;
+  float* stat_sum;
+  float* stat_sq;
+} mp_igemm_args;
+
+MP_API int mp_conv_igemm(const mp_igemm_args* args, void* stream);
+
+/* Weight gradient: dw[m][slot][n] += sum over the (n_img, grid_h, grid_w) pixel grid of
+ *   a(pix, m) * b[tap](pix + shift, n)
+ * a: natural view (C, W, 1, H, N) of the tensor indexed by the GEMM row m (dY for nn.Conv2d,
+ * x for nn.ConvTranspose2d); b: view addressed through the taps like in mp_conv_igemm.
+ * dw is fp32 [m_real][n_slots][n_real] (the channels-last memory of the torch parameter);
+ * n_cols = channel count of b padded to 64. */
+typedef struct mp_wgrad_args {
+  mp_view5 a;
+  mp_view5 b;
+  int32_t n_taps;
+  mp_tap taps[MP_MAX_TAPS];
+  int32_t m_real, n_real, n_cols, n_slots;
+  int32_t n_img, grid_h, grid_w;
+  float* dw;
+} mp_wgrad_args;
+
+MP_API int mp_conv_wgrad(const mp_wgrad_args* args, void* stream);
+
+/* Tunables for experiments (name -> value); returns MP_ERR_ARG for unknown names.
+ *   "igemm_smem"  : shared-memory budget per CTA of mp_conv_igemm in bytes (default 101376)
+ *   "wgrad_ctas"  : target CTA count of mp_conv_wgrad (default 296) */
+MP_API int mp_set_tunable(const char* name, int64_t value);
+
 #ifdef __cplusplus
 }
 #endif

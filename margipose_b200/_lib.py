@@ -17,6 +17,34 @@ c_void_p = ctypes.c_void_p
 c_size_t = ctypes.c_size_t
 PlaneTable = ctypes.c_void_p * 3
 
+MP_MAX_TAPS = 10
+
+
+class View5(ctypes.Structure):
+    _fields_ = [('ptr', c_void_p), ('dim', ctypes.c_int64 * 5), ('stride', ctypes.c_int64 * 5)]
+
+
+class Tap(ctypes.Structure):
+    _fields_ = [('src', ctypes.c_int32), ('c0', ctypes.c_int32), ('dw', ctypes.c_int32),
+                ('p', ctypes.c_int32), ('dh', ctypes.c_int32), ('koff', ctypes.c_int32)]
+
+
+class IgemmArgs(ctypes.Structure):
+    _fields_ = [('src', View5 * 2), ('wmat', c_void_p), ('w_rows', ctypes.c_int64),
+                ('w_k', ctypes.c_int64), ('n_taps', ctypes.c_int32), ('taps', Tap * MP_MAX_TAPS),
+                ('cblocks', ctypes.c_int32), ('n_img', ctypes.c_int32), ('out_h', ctypes.c_int32),
+                ('out_w', ctypes.c_int32), ('out', c_void_p), ('res', c_void_p),
+                ('out_sn', ctypes.c_int64), ('out_sh', ctypes.c_int64), ('out_sw', ctypes.c_int64),
+                ('out_c', ctypes.c_int32), ('stat_sum', c_void_p), ('stat_sq', c_void_p)]
+
+
+class WgradArgs(ctypes.Structure):
+    _fields_ = [('a', View5), ('b', View5), ('n_taps', ctypes.c_int32), ('taps', Tap * MP_MAX_TAPS),
+                ('m_real', ctypes.c_int32), ('n_real', ctypes.c_int32), ('n_cols', ctypes.c_int32),
+                ('n_slots', ctypes.c_int32), ('n_img', ctypes.c_int32), ('grid_h', ctypes.c_int32),
+                ('grid_w', ctypes.c_int32), ('dw', c_void_p)]
+
+
 _lib = None
 
 
@@ -36,6 +64,9 @@ def _signatures():
         'mp_euclid_fwd': (I, [P, P, I, I, P, P]),
         'mp_euclid_bwd': (I, [P, P, P, P, I, I, P, P]),
         'mp_make_gauss': (I, [P, P, I, D, I, I, I, P]),
+        'mp_conv_igemm': (I, [ctypes.POINTER(IgemmArgs), P]),
+        'mp_conv_wgrad': (I, [ctypes.POINTER(WgradArgs), P]),
+        'mp_set_tunable': (I, [ctypes.c_char_p, ctypes.c_int64]),
     }
 
 

@@ -1,0 +1,274 @@
+"""Host-side geometry of the convolution layers on the MargiPose hot path.
+
+Turns one nn.Conv2d / nn.ConvTranspose2d op site of the reference
+(/root/reference/src/margipose/models/margipose_model.py:33,67-68,73-74,79-82 and the torchvision
+ResNet blocks behind :130-135) into launches of the tcgen05 implicit-GEMM kernels behind the C
+ABI (include/margipose_b200.h: mp_conv_igemm, mp_conv_wgrad): which 5-D view of the NHWC
+activation each filter tap reads, with which shift / parity, and which K-slice of the packed
+weight matrix it multiplies.
+
+Conventions
+  activations : bf16 (N, H, W, Cp) contiguous, Cp = channels padded to a multiple of 64
+  weights     : fp32 master in channels-last memory -- Conv2d (Co, Ci, kh, kw) stored as
+                [Co][kh*kw][Ci], ConvTranspose2d (Ci, Co, kh, kw) stored as [Ci][kh*kw][Co] --
+                and two bf16 packs per layer (forward and data-gradient orientation), each
+                [rows padded to 64][taps][K padded to 64]
+Supported: kernel 1 or 3 (padding k // 2), stride 1 or 2; transposed only with stride 2 and
+output_padding 1 -- everything the reference's columns and ResNet blocks use.
+"""
+import ctypes
+
+import torch
+
+from ._lib import (IgemmArgs, WgradArgs, View5, MP_MAX_TAPS, lib, check, stream_ptr)
+
+
+def pad64(c):
+    return (c + 63) // 64 * 64
+
+
+def _view(t, parity=False):
+    """5-D TMA view (C, W, P, H, N) of an (N, H, W, Cp) bf16 tensor; parity=True exposes the
+    even/odd rows and columns as separate coordinates (stride-2 taps)."""
+    n, h, w, c = t.shape
+    assert t.dtype == torch.bfloat16 and t.is_contiguous() and c % 64 == 0
+    v = View5()
+    v.ptr = t.data_ptr()
+    if not parity:
+        dims, strides = (c, w, 1, h, n), (1, c, w * c, w * c, h * w * c)
+    else:
+        assert h % 2 == 0 and w % 2 == 0
+        dims, strides = (2 * c, w // 2, 2, h // 2, n), (1, 2 * c, w * c, 2 * w * c, h * w * c)
+    for i in range(5):
+        v.dim[i] = dims[i]
+        v.stride[i] = strides[i]
+    return v
+
+
+def _axis_taps_s1(k):
+    """(kernel index, shift) pairs along one axis of a stride-1 conv: in = out + r - k//2."""
+    return [(r, r - k // 2) for r in range(k)]
+
+
+def _axis_taps_s2(k):
+    """(kernel index, parity, shift in the decimated axis) for in = 2*out + r - k//2."""
+    out = []
+    for r in range(k):
+        off = r - k // 2
+        out.append((r, off % 2, (off - off % 2) // 2))
+    return out
+
+
+def _axis_taps_up(k, parity):
+    """Taps that reach output parity `parity` of a stride-2 transposed relation
+    out = 2*in + r - k//2 : (kernel index, shift of `in` relative to out // 2)."""
+    out = []
+    for r in range(k):
+        off = r - k // 2            # out = 2*in + off  ->  in = (out - off) / 2
+        if (parity - off) % 2 == 0:
+            out.append((r, (parity - off) // 2))
+    return out
+
+
+class ConvGeom:
+    """Geometry of one conv layer (shared by forward, dgrad and wgrad launches)."""
+
+    def __init__(self, cin, cout, k, stride=1, transposed=False):
+        assert k in (1, 3) and stride in (1, 2)
+        assert not transposed or stride == 2
+        self.cin, self.cout, self.k, self.stride, self.transposed = cin, cout, k, stride, transposed
+        self.cin_p, self.cout_p = pad64(cin), pad64(cout)
+        self.taps = k * k
+
+    # master weight memory: [rows][taps][cols] fp32 (channels-last of the torch parameter)
+    @property
+    def master_shape(self):
+        return (self.cin, self.taps, self.cout) if self.transposed else (self.cout, self.taps, self.cin)
+
+    @property
+    def torch_weight_shape(self):
+        return (self.cin, self.cout, self.k, self.k) if self.transposed else \
+            (self.cout, self.cin, self.k, self.k)
+
+    def out_hw(self, h, w):
+        if self.transposed:
+            return 2 * h, 2 * w
+        return (h // 2, w // 2) if self.stride == 2 else (h, w)
+
+    # ---- packs: fwd multiplies x (K = cin) giving cout rows; bwd multiplies dy (K = cout)
+    def fwd_pack_shape(self):
+        return (self.cout_p, self.taps * self.cin_p)
+
+    def bwd_pack_shape(self):
+        return (self.cin_p, self.taps * self.cout_p)
+
+
+def _fill_taps(args, taps):
+    assert 1 <= len(taps) <= MP_MAX_TAPS
+    args.n_taps = len(taps)
+    for i, (src, c0, dw, p, dh, koff) in enumerate(taps):
+        t = args.taps[i]
+        t.src, t.c0, t.dw, t.p, t.dh, t.koff = src, c0, dw, p, dh, koff
+
+
+def _igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_c, res=None,
+           stats=None, out_offset=0):
+    """srcs: list of (tensor, parity) pairs; see mp_conv_igemm in include/margipose_b200.h."""
+    a = IgemmArgs()
+    for i, (t, parity) in enumerate(srcs):
+        a.src[i] = _view(t, parity)
+    a.wmat = wmat.data_ptr()
+    a.w_rows, a.w_k = wmat.shape
+    _fill_taps(a, taps)
+    a.cblocks = cblocks
+    a.n_img, a.out_h, a.out_w = n_img, out_h, out_w
+    a.out = out.data_ptr() + 2 * out_offset
+    a.res = (res.data_ptr() + 2 * out_offset) if res is not None else None
+    a.out_sn, a.out_sh, a.out_sw = out_strides
+    a.out_c = out_c
+    if stats is not None:
+        a.stat_sum, a.stat_sq = stats[0].data_ptr(), stats[1].data_ptr()
+    check(lib().mp_conv_igemm(ctypes.byref(a), stream_ptr(out.device)), 'mp_conv_igemm')
+
+
+def _wgrad(a_t, b_t, b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, grid_h, grid_w, dw):
+    """See mp_conv_wgrad in include/margipose_b200.h."""
+    a = WgradArgs()
+    a.a = _view(a_t)
+    a.b = _view(b_t, b_parity)
+    _fill_taps(a, taps)
+    a.m_real, a.n_real, a.n_cols, a.n_slots = m_real, n_real, n_cols, n_slots
+    a.n_img, a.grid_h, a.grid_w = n_img, grid_h, grid_w
+    a.dw = dw.data_ptr()
+    check(lib().mp_conv_wgrad(ctypes.byref(a), stream_ptr(dw.device)), 'mp_conv_wgrad')
+
+
+def _down_taps(k, c_in_p, k_stride, src=0, koff0=0):
+    """Taps of a stride-2 gather (conv forward s2 / transposed-conv dgrad) over a parity view."""
+    taps = []
+    for r, ph, dh in _axis_taps_s2(k):
+        for s, pw, dw in _axis_taps_s2(k):
+            taps.append((src, pw * c_in_p, dw, ph, dh, koff0 + (r * k + s) * k_stride))
+    return taps
+
+
+def _s1_taps(k, k_stride, sign, src=0, koff0=0):
+    taps = []
+    for r, dh in _axis_taps_s1(k):
+        for s, dw in _axis_taps_s1(k):
+            taps.append((src, 0, sign * dw, 0, sign * dh, koff0 + (r * k + s) * k_stride))
+    return taps
+
+
+def conv_forward(g, x, wpack, out, stats=None, res=None):
+    """y = conv(x) (or conv_transpose(x)); x (N,H,W,cin_p), out (N,Ho,Wo,cout_p), both bf16 NHWC.
+    stats = (sum, sumsq) fp32 (cout_p) accumulators for the BatchNorm batch statistics."""
+    n, h, w, _ = x.shape
+    ho, wo = g.out_hw(h, w)
+    assert tuple(out.shape) == (n, ho, wo, g.cout_p) and tuple(wpack.shape) == g.fwd_pack_shape()
+    cb = g.cin_p // 64
+    if not g.transposed:
+        if g.stride == 1:
+            taps, src = _s1_taps(g.k, g.cin_p, +1), (x, False)
+        else:
+            taps, src = _down_taps(g.k, g.cin_p, g.cin_p), (x, True)
+        _igemm([src], wpack, taps, cb, n, ho, wo, out, (ho * wo * g.cout_p, wo * g.cout_p, g.cout_p),
+               g.cout_p, res=res, stats=stats)
+    else:
+        _scatter_up(g.k, (x, False), wpack, g.cin_p, cb, n, h, w, out, g.cout_p, stats, res)
+
+
+def _scatter_up(k, src, wpack, k_stride, cb, n, h, w, out, c_out_p, stats, res, extra=None):
+    """The stride-2 'up' relation out[2a+ph, 2b+pw] = sum of taps over in[a+dh, b+dw]: one launch
+    per output parity class, scattered into the (N, 2h, 2w, C) output.  Classes no tap reaches
+    (1x1 kernels) stay zero in `out` (the buffer is zero-initialised once by its owner).
+    extra = (k2, src2, k_stride2, koff0): a second source fused into the same accumulation."""
+    wo = 2 * w
+    strides = (4 * h * w * c_out_p, 2 * wo * c_out_p, 2 * c_out_p)
+    for ph in (0, 1):
+        for pw in (0, 1):
+            taps = [(0, 0, dw, 0, dh, (r * k + s) * k_stride)
+                    for r, dh in _axis_taps_up(k, ph) for s, dw in _axis_taps_up(k, pw)]
+            srcs = [src]
+            if extra is not None:
+                k2, src2, ks2, koff0 = extra
+                srcs.append(src2)
+                taps += [(1, 0, dw, 0, dh, koff0 + (r * k2 + s) * ks2)
+                         for r, dh in _axis_taps_up(k2, ph) for s, dw in _axis_taps_up(k2, pw)]
+            if not taps:
+                continue
+            _igemm(srcs, wpack, taps, cb, n, h, w, out, strides, c_out_p, res=res, stats=stats,
+                   out_offset=(ph * wo + pw) * c_out_p)
+
+
+def conv_dgrad(g, dy, wpack_bwd, dx, res=None, second=None):
+    """dx = d/dx of conv_forward (optionally + res).  `second` = (g2, dy2, koff0) fuses the data
+    gradient of another conv that read the same x with the same stride (the residual block's
+    shortcut); wpack_bwd then holds both layers' bwd packs side by side along K."""
+    n, ho, wo, _ = dy.shape
+    cb = g.cout_p // 64
+    if second is not None:
+        g2, dy2, koff0 = second
+        assert g2.cout_p == g.cout_p and g2.cin_p == g.cin_p and g2.stride == g.stride and \
+            g2.transposed == g.transposed
+    if not g.transposed:
+        if g.stride == 1:
+            taps, srcs = _s1_taps(g.k, g.cout_p, -1), [(dy, False)]
+            if second is not None:
+                taps += _s1_taps(g2.k, g2.cout_p, -1, src=1, koff0=koff0)
+                srcs.append((dy2, False))
+            _igemm(srcs, wpack_bwd, taps, cb, n, ho, wo, dx, (ho * wo * g.cin_p, wo * g.cin_p, g.cin_p),
+                   g.cin_p, res=res)
+        else:
+            extra = None
+            if second is not None:
+                extra = (g2.k, (dy2, False), g2.cout_p, koff0)
+            _scatter_up(g.k, (dy, False), wpack_bwd, g.cout_p, cb, n, ho, wo, dx, g.cin_p, None, res,
+                        extra=extra)
+    else:
+        h, w = ho // 2, wo // 2
+        taps, srcs = _down_taps(g.k, g.cout_p, g.cout_p), [(dy, True)]
+        if second is not None:
+            taps += _down_taps(g2.k, g2.cout_p, g2.cout_p, src=1, koff0=koff0)
+            srcs.append((dy2, True))
+        _igemm(srcs, wpack_bwd, taps, cb, n, h, w, dx, (h * w * g.cin_p, w * g.cin_p, g.cin_p),
+               g.cin_p, res=res)
+
+
+def conv_wgrad(g, x, dy, dw):
+    """dw += d/dW of conv_forward; dw is the fp32 master-layout gradient [rows][taps][cols]."""
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and tuple(dw.shape) == g.master_shape
+    if not g.transposed:
+        n, ho, wo, _ = dy.shape
+        if g.stride == 1:
+            taps, parity = _s1_taps(g.k, 1, +1), False
+        else:
+            taps, parity = _down_taps(g.k, g.cin_p, 1), True
+        _wgrad(dy, x, parity, taps, g.cout, g.cin, g.cin_p, g.taps, n, ho, wo, dw)
+    else:
+        n, h, w, _ = x.shape
+        _wgrad(x, dy, True, _down_taps(g.k, g.cout_p, 1), g.cin, g.cout, g.cout_p, g.taps, n, h, w, dw)
+
+
+# ---- reference packing in torch (used by tests and by model materialisation until the CUDA pack
+# kernel takes over); master is the fp32 [rows][taps][cols] tensor.
+def pack_fwd(g, master):
+    """bf16 [cout_p][taps*cin_p]: rows = output channels, K = (tap, input channel)."""
+    m = master.permute(2, 1, 0) if g.transposed else master          # -> [cout][taps][cin]
+    out = torch.zeros(g.cout_p, g.taps, g.cin_p, dtype=torch.bfloat16, device=master.device)
+    out[:g.cout, :, :g.cin] = m.to(torch.bfloat16)
+    return out.reshape(g.cout_p, g.taps * g.cin_p)
+
+
+def pack_bwd(g, master):
+    """bf16 [cin_p][taps*cout_p]: rows = input channels, K = (tap, output channel)."""
+    m = master if g.transposed else master.permute(2, 1, 0)          # -> [cin][taps][cout]
+    out = torch.zeros(g.cin_p, g.taps, g.cout_p, dtype=torch.bfloat16, device=master.device)
+    out[:g.cin, :, :g.cout] = m.to(torch.bfloat16)
+    return out.reshape(g.cin_p, g.taps * g.cout_p)
+
+
+def master_from_torch(g, weight):
+    """torch parameter (Co,Ci,kh,kw) / (Ci,Co,kh,kw) -> master [rows][taps][cols] fp32."""
+    a, b, kh, kw = weight.shape
+    return weight.permute(0, 2, 3, 1).reshape(a, kh * kw, b).contiguous().float()

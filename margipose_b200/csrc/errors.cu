@@ -16,3 +16,17 @@ extern "C" {
 int mp_abi_version(void) { return 1; }
 const char* mp_last_error(void) { return g_err; }
 }
+
+// ---- tunables (experiments only; defaults are what the benchmarks use)
+#include <string.h>
+void mp_set_igemm_smem(long long v);
+void mp_set_wgrad_tunable(int which, long long v);
+
+extern "C" int mp_set_tunable(const char* name, int64_t value) {
+  if (!name) { mp_set_error("mp_set_tunable: null name"); return MP_ERR_ARG; }
+  if (!strcmp(name, "igemm_smem")) { mp_set_igemm_smem(value); return MP_OK; }
+  if (!strcmp(name, "wgrad_ctas")) { mp_set_wgrad_tunable(0, value); return MP_OK; }
+  if (!strcmp(name, "wgrad_taps")) { mp_set_wgrad_tunable(1, value); return MP_OK; }
+  mp_set_error("mp_set_tunable: unknown tunable '%s'", name);
+  return MP_ERR_ARG;
+}

@@ -1,0 +1,26 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution kernels through the C ABI (see
+tests/conv_cases.py for the checks and tolerances)."""
+import pytest
+
+from tests import conv_cases as K
+
+pytestmark = pytest.mark.gpu
+IDS = lambda c: 'x'.join(map(str, c))   # noqa: E731
+
+
+@pytest.mark.parametrize('case', K.CASES, ids=IDS)
+def test_conv_forward_and_stats(case):
+    K.DEV = 'cuda'
+    K.check_conv_forward_and_stats(case)
+
+
+@pytest.mark.parametrize('case', K.CASES, ids=IDS)
+def test_conv_dgrad_and_wgrad(case):
+    K.DEV = 'cuda'
+    K.check_conv_dgrad_and_wgrad(case)
+
+
+@pytest.mark.parametrize('stride,tr', [(1, False), (2, False), (2, True)])
+def test_fused_block_dgrad(stride, tr):
+    K.DEV = 'cuda'
+    K.check_fused_block_dgrad(stride, tr)
