@@ -154,8 +154,8 @@ MP_API int mp_conv_igemm(const mp_igemm_args* args, void* stream);
  *   a(pix, m) * b[tap](pix + shift, n)
  * a: natural view (C, W, 1, H, N) of the tensor indexed by the GEMM row m (dY for nn.Conv2d,
  * x for nn.ConvTranspose2d); b: view addressed through the taps like in mp_conv_igemm.
- * dw is fp32 [m_real][n_slots][n_real] (the channels-last memory of the torch parameter);
- * n_cols = channel count of b padded to 64. */
+ * dw is fp32 [m_real][n_slots][n_real] (the channels-last memory of the torch parameter).
+ * One launch covers the n_cols (64..256, multiple of 64) channels of b starting at n_off. */
 typedef struct mp_wgrad_args {
   mp_view5 a;
   mp_view5 b;
@@ -163,10 +163,116 @@ typedef struct mp_wgrad_args {
   mp_tap taps[MP_MAX_TAPS];
   int32_t m_real, n_real, n_cols, n_slots;
   int32_t n_img, grid_h, grid_w;
+  int32_t n_off;
   float* dw;
 } mp_wgrad_args;
 
 MP_API int mp_conv_wgrad(const mp_wgrad_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * BatchNorm + activation + residual, forward and backward (nn.BatchNorm2d / nn.ReLU / `+` in
+ * ResidualBlock, models/margipose_model.py:31-40, and in the torchvision ResNet blocks).
+ *
+ * One conv output `y` (bf16 (M, Cp), M = N*H*W pixels) with its BatchNorm is a "branch".  The
+ * forward computes, per pixel and channel,
+ *     out = post( pre(bn_a(y_a)) + [ bn_b(y_b) | res | 0 ] ),   pre/post = ReLU or identity
+ * which covers relu(bn(y)) (first half of a block), relu(bn(y2)) + bn(ys) (MargiPose
+ * ResidualBlock output), relu(bn(y2) + x) and relu(bn(y2) + bn(yd)) (ResNet blocks).
+ * In training mode the batch statistics come from the per-channel sums the conv epilogue
+ * accumulated (sum, sq), running statistics are updated with `momentum` (unbiased variance),
+ * and mean / 1/std are saved for the backward; in eval mode the running statistics are used.
+ */
+typedef struct mp_bn_branch {
+  const void* y;            /* bf16 (M, Cp); NULL = branch absent */
+  const float* sum;         /* (Cp) batch sum of y        (training forward) */
+  const float* sq;          /* (Cp) batch sum of y*y      (training forward) */
+  const float* gamma;       /* (C) */
+  const float* beta;        /* (C) */
+  float* running_mean;      /* (C) */
+  float* running_var;       /* (C) */
+  float* save_mean;         /* (Cp) written by forward, read by backward */
+  float* save_invstd;       /* (Cp) */
+  const float* conv_bias;   /* (C) bias of the producing conv or NULL (only shifts the mean) */
+  void* dy;                 /* backward: bf16 (M, Cp) gradient w.r.t. y */
+  float* dgamma;            /* backward: (C), accumulated (+=) */
+  float* dbeta;             /* backward: (C), accumulated (+=) */
+} mp_bn_branch;
+
+typedef struct mp_bn_args {
+  mp_bn_branch a, b;
+  const void* res;          /* bf16 (M, Cp) identity residual or NULL */
+  int32_t relu_a, relu_out;
+  void* out;                /* forward output bf16 (M, Cp) (also read by backward when relu_out) */
+  float* out_nchw;          /* forward: fp32 (N, C, HW) copy of the output (logits) or NULL */
+  const void* dout;         /* backward: bf16 (M, Cp) gradient w.r.t. out, or NULL */
+  const float* dout_nchw;   /* backward: fp32 (N, C, HW) gradient w.r.t. out_nchw, or NULL */
+  void* dres;               /* backward: bf16 (M, Cp) gradient w.r.t. res, or NULL */
+  float* sums;              /* backward workspace (4, Cp): zero before mp_bn_bwd_reduce */
+  int64_t M;
+  int32_t C, Cp, HW;
+  int32_t training;
+  float momentum, eps;
+} mp_bn_args;
+
+MP_API int mp_bn_fwd(const mp_bn_args* args, void* stream);
+/* backward = two launches: per-channel reductions, then the elementwise gradient. */
+MP_API int mp_bn_bwd_reduce(const mp_bn_args* args, void* stream);
+MP_API int mp_bn_bwd_apply(const mp_bn_args* args, void* stream);
+
+/* nn.MaxPool2d(3, 2, 1) of the ResNet stem on bf16 NHWC; idx (N, H/2, W/2, C) uint8 records the
+ * arg-max tap (first maximum in row-major window order, as ATen does) for the backward. */
+MP_API int mp_maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, void* stream);
+MP_API int mp_maxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int N, int H, int W, int C,
+                          void* stream);
+
+/* HeatmapColumn axis permutation (models/margipose_model.py:86-99) on bf16 NHWC (N, S, S, C),
+ * C = G*S real channels inside Cp: mode 1 ('zy') out[n,h,c',g*S+w] = in[n,h,w,g*S+c'];
+ * mode 2 ('xz') out[n,c',w,g*S+h] = in[n,h,w,g*S+c'].  Both are involutions (backward = same call). */
+MP_API int mp_axis_permute(const void* in, void* out, int mode, int N, int S, int C, int Cp, void* stream);
+
+/* HeatmapCombiner (models/margipose_model.py:142-150) fused with the stage-input update (:195):
+ * out[pix, c] = inp[pix, c] + sum_k sum_j w[c, k*J + j] * p_k[n, j, pix]; p_k fp32 (N, J, HW). */
+MP_API int mp_combiner_fwd(const float* const p[3], const float* w, const void* inp, void* out,
+                           int N, int J, int HW, int C, void* stream);
+/* d p_k (fp32 (N, J, HW); overwritten, or += when accumulate != 0) and d w (+=) from
+ * d out (bf16 (N*HW, C)). */
+MP_API int mp_combiner_bwd(const void* dout, const float* const p[3], const float* w,
+                           float* const dp[3], float* dw, int accumulate, int N, int J, int HW,
+                           int C, void* stream);
+
+/* ResNet stem conv1 (7x7, stride 2, padding 3, 3 input channels): gathers the fp32 NCHW image
+ * into bf16 patch rows (N, H/2, W/2, 192) with k = (r*7 + s)*3 + c (147 real + zero padding), so
+ * the conv and its weight gradient run as 1x1 cases of mp_conv_igemm / mp_conv_wgrad. */
+MP_API int mp_stem_im2col(const float* x, void* patches, int N, int H, int W, void* stream);
+
+/* out = sum of n (<= 4) bf16 tensors of `count` elements (gradient fan-in). */
+MP_API int mp_add_bf16(const void* const in[4], int n, void* out, int64_t count, void* stream);
+
+/* fp32 master weights -> bf16 GEMM operands, one launch for the whole network.  `table` is a
+ * DEVICE array of n_entries records sorted by work_off; dst elements beyond the source extent are
+ * zero-filled.  Entry e fills the [rows_p][taps][cols_p] block
+ *   packed[dst_off + r*dst_row_stride + t*cols_p + c] = transpose ? src[c][t][r] : src[r][t][c]
+ * (src = master + src_off, fp32 [A][taps][B]); a row stride larger than taps*cols_p lets two layers
+ * share one matrix along K (fused data gradient of a residual block). */
+typedef struct mp_pack_entry {
+  int64_t src_off;         /* elements into `master` */
+  int64_t dst_off;         /* elements into `packed` */
+  int64_t dst_row_stride;  /* elements */
+  int64_t work_off;        /* cumulative rows_p*taps*cols_p of the entries before this one */
+  int64_t work_end;        /* work_off + rows_p*taps*cols_p */
+  int32_t A, B, taps;      /* source extents */
+  int32_t transpose;
+  int32_t rows_p, cols_p;  /* padded destination extents (cols_p % 8 == 0) */
+} mp_pack_entry;
+MP_API int mp_pack_weights(const float* master, void* packed, const mp_pack_entry* table,
+                           int n_entries, int64_t total_work, void* stream);
+
+/* torch.optim.SGD step over flat fp32 buffers (momentum buffer initialised on first_step):
+ *   g = grad*grad_scale + wd*p;  buf = first ? g : mom*buf + (1-dampening)*g;
+ *   p -= lr * (nesterov ? g + mom*buf : buf) */
+MP_API int mp_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr,
+                       float momentum, float dampening, float weight_decay, int nesterov,
+                       int first_step, float grad_scale, void* stream);
 
 /* Tunables for experiments (name -> value); returns MP_ERR_ARG for unknown names.
  *   "igemm_smem"  : shared-memory budget per CTA of mp_conv_igemm in bytes (default 101376)

@@ -42,7 +42,30 @@ class WgradArgs(ctypes.Structure):
     _fields_ = [('a', View5), ('b', View5), ('n_taps', ctypes.c_int32), ('taps', Tap * MP_MAX_TAPS),
                 ('m_real', ctypes.c_int32), ('n_real', ctypes.c_int32), ('n_cols', ctypes.c_int32),
                 ('n_slots', ctypes.c_int32), ('n_img', ctypes.c_int32), ('grid_h', ctypes.c_int32),
-                ('grid_w', ctypes.c_int32), ('dw', c_void_p)]
+                ('grid_w', ctypes.c_int32), ('n_off', ctypes.c_int32), ('dw', c_void_p)]
+
+
+class BnBranch(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ('y', 'sum', 'sq', 'gamma', 'beta', 'running_mean',
+                                        'running_var', 'save_mean', 'save_invstd', 'conv_bias',
+                                        'dy', 'dgamma', 'dbeta')]
+
+
+class BnArgs(ctypes.Structure):
+    _fields_ = [('a', BnBranch), ('b', BnBranch), ('res', c_void_p), ('relu_a', ctypes.c_int32),
+                ('relu_out', ctypes.c_int32), ('out', c_void_p), ('out_nchw', c_void_p),
+                ('dout', c_void_p), ('dout_nchw', c_void_p), ('dres', c_void_p), ('sums', c_void_p),
+                ('M', ctypes.c_int64), ('C', ctypes.c_int32), ('Cp', ctypes.c_int32),
+                ('HW', ctypes.c_int32), ('training', ctypes.c_int32), ('momentum', ctypes.c_float),
+                ('eps', ctypes.c_float)]
+
+
+class PackEntry(ctypes.Structure):
+    _fields_ = [('src_off', ctypes.c_int64), ('dst_off', ctypes.c_int64),
+                ('dst_row_stride', ctypes.c_int64), ('work_off', ctypes.c_int64),
+                ('work_end', ctypes.c_int64), ('A', ctypes.c_int32), ('B', ctypes.c_int32),
+                ('taps', ctypes.c_int32), ('transpose', ctypes.c_int32), ('rows_p', ctypes.c_int32),
+                ('cols_p', ctypes.c_int32)]
 
 
 _lib = None
@@ -67,6 +90,19 @@ def _signatures():
         'mp_conv_igemm': (I, [ctypes.POINTER(IgemmArgs), P]),
         'mp_conv_wgrad': (I, [ctypes.POINTER(WgradArgs), P]),
         'mp_set_tunable': (I, [ctypes.c_char_p, ctypes.c_int64]),
+        'mp_bn_fwd': (I, [ctypes.POINTER(BnArgs), P]),
+        'mp_bn_bwd_reduce': (I, [ctypes.POINTER(BnArgs), P]),
+        'mp_bn_bwd_apply': (I, [ctypes.POINTER(BnArgs), P]),
+        'mp_maxpool_fwd': (I, [P, P, P, I, I, I, I, P]),
+        'mp_maxpool_bwd': (I, [P, P, P, I, I, I, I, P]),
+        'mp_axis_permute': (I, [P, P, I, I, I, I, I, P]),
+        'mp_combiner_fwd': (I, [PT, P, P, P, I, I, I, I, P]),
+        'mp_combiner_bwd': (I, [P, PT, P, PT, P, I, I, I, I, I, P]),
+        'mp_stem_im2col': (I, [P, P, I, I, I, P]),
+        'mp_add_bf16': (I, [ctypes.POINTER(c_void_p * 4), I, P, ctypes.c_int64, P]),
+        'mp_pack_weights': (I, [P, P, P, I, ctypes.c_int64, P]),
+        'mp_sgd_step': (I, [P, P, P, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                            ctypes.c_float, I, I, ctypes.c_float, P]),
     }
 
 

@@ -128,19 +128,31 @@ def _igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out
     a.out_c = out_c
     if stats is not None:
         a.stat_sum, a.stat_sq = stats[0].data_ptr(), stats[1].data_ptr()
-    check(lib().mp_conv_igemm(ctypes.byref(a), stream_ptr(out.device)), 'mp_conv_igemm')
+    _igemm_launch(a, out.device)
+
+
+def _igemm_launch(a, device):
+    """Enqueues one mp_conv_igemm; the engine swaps this hook to record launches instead."""
+    check(lib().mp_conv_igemm(ctypes.byref(a), stream_ptr(device)), 'mp_conv_igemm')
+
+
+def _wgrad_launch(a, device):
+    check(lib().mp_conv_wgrad(ctypes.byref(a), stream_ptr(device)), 'mp_conv_wgrad')
 
 
 def _wgrad(a_t, b_t, b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, grid_h, grid_w, dw):
-    """See mp_conv_wgrad in include/margipose_b200.h."""
-    a = WgradArgs()
-    a.a = _view(a_t)
-    a.b = _view(b_t, b_parity)
-    _fill_taps(a, taps)
-    a.m_real, a.n_real, a.n_cols, a.n_slots = m_real, n_real, n_cols, n_slots
-    a.n_img, a.grid_h, a.grid_w = n_img, grid_h, grid_w
-    a.dw = dw.data_ptr()
-    check(lib().mp_conv_wgrad(ctypes.byref(a), stream_ptr(dw.device)), 'mp_conv_wgrad')
+    """See mp_conv_wgrad in include/margipose_b200.h; wide b operands go in 256-channel slices."""
+    for n_off in range(0, n_cols, 256):
+        a = WgradArgs()
+        a.a = _view(a_t)
+        a.b = _view(b_t, b_parity)
+        _fill_taps(a, taps)
+        a.m_real, a.n_real, a.n_slots = m_real, n_real, n_slots
+        a.n_cols, a.n_off = min(256, n_cols - n_off), n_off
+        a.n_img, a.grid_h, a.grid_w = n_img, grid_h, grid_w
+        a.dw = dw.data_ptr()
+        if n_off < n_real:
+            _wgrad_launch(a, dw.device)
 
 
 def _down_taps(k, c_in_p, k_stride, src=0, koff0=0):

@@ -1,0 +1,411 @@
+// Small HBM-bound kernels around the tensor-core path (sm_100a): stem max-pool, the HeatmapColumn
+// axis permutation, the HeatmapCombiner 1x1 conv on fp32 NCHW probabilities, the stem im2col
+// gather, gradient fan-in sums, fp32->bf16 weight packing and the flat SGD step.
+//
+// Reference op sites (/root/reference/src/margipose/): models/margipose_model.py:133 (maxpool),
+// :86-99 (axis permutation), :142-150,195 (combiner + stage input update), :130 (stem conv1,
+// via torchvision), bin/train_3d.py:338-340 (SGD with momentum).
+#include "common.cuh"
+#include "../../include/margipose_b200.h"
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                    pack_bf16x2(v[6], v[7]));
+}
+
+// ------------------------------------------------------------------ maxpool 3x3 / stride 2 / pad 1
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                   uint8_t* __restrict__ idx, int N, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, G = C / 8;
+  const long long total = (long long)N * Ho * Wo * G;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int g = (int)(i % G);
+  long long t = i / G;
+  const int wo = (int)(t % Wo); t /= Wo;
+  const int ho = (int)(t % Ho);
+  const int n = (int)(t / Ho);
+  float best[8];
+  int arg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+  for (int r = 0; r < 3; ++r) {
+    const int h = 2 * ho + r - 1;
+    if (h < 0 || h >= H) continue;
+    for (int s = 0; s < 3; ++s) {
+      const int w = 2 * wo + s - 1;
+      if (w < 0 || w >= W) continue;
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + g * 8)), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (v[j] > best[j] || v[j] != v[j]) { best[j] = v[j]; arg[j] = r * 3 + s; }
+    }
+  }
+  const long long o = (((long long)n * Ho + ho) * Wo + wo) * C + g * 8;
+  *reinterpret_cast<uint4*>(y + o) = pack8(best);
+  uint2 a;
+  a.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+  a.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+  *reinterpret_cast<uint2*>(idx + o) = a;
+}
+
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                   __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, G = C / 8;
+  const long long total = (long long)N * H * W * G;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int g = (int)(i % G);
+  long long t = i / G;
+  const int w = (int)(t % W); t /= W;
+  const int h = (int)(t % H);
+  const int n = (int)(t / H);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  // output windows (ho, wo) that contain (h, w): 2*ho + r - 1 == h
+  for (int r = 0; r < 3; ++r) {
+    const int hh = h + 1 - r;
+    if (hh < 0 || (hh & 1) || hh / 2 >= Ho) continue;
+    for (int s = 0; s < 3; ++s) {
+      const int ww = w + 1 - s;
+      if (ww < 0 || (ww & 1) || ww / 2 >= Wo) continue;
+      const long long o = (((long long)n * Ho + hh / 2) * Wo + ww / 2) * C + g * 8;
+      const uint2 a = __ldg(reinterpret_cast<const uint2*>(idx + o));
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o)), v);
+      const int tap = r * 3 + s;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int aj = ((j < 4 ? a.x : a.y) >> ((j & 3) * 8)) & 0xff;
+        if (aj == tap) acc[j] += v[j];
+      }
+    }
+  }
+  *reinterpret_cast<uint4*>(dx + (((long long)n * H + h) * W + w) * C + g * 8) = pack8(acc);
+}
+
+// ------------------------------------------------------------------------------ axis permutation
+// out[n, h, c', g*S + w] = in[n, h, w, g*S + c']  (mode 1)
+// out[n, c', w, g*S + h] = in[n, h, w, g*S + c']  (mode 2)
+__global__ void axis_permute_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                    int mode, int N, int S, int C, int Cp) {
+  const long long total = (long long)N * S * S * Cp;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = (int)(i % Cp);
+  long long t = i / Cp;
+  const int col = (int)(t % S); t /= S;
+  const int row = (int)(t % S);
+  const int n = (int)(t / S);
+  __nv_bfloat16 v = __float2bfloat16(0.f);
+  if (ch < C) {
+    const int g = ch / S, k = ch - g * S;
+    // out(row, col, g*S + k):  mode 1: h = row, c' = col, w = k ;  mode 2: c' = row, w = col, h = k
+    int h, w, c;
+    if (mode == 1) { h = row; w = k; c = col; }
+    else { h = k; w = col; c = row; }
+    v = in[(((long long)n * S + h) * S + w) * Cp + g * S + c];
+  }
+  out[i] = v;
+}
+
+// ------------------------------------------------------------------------------------ combiner
+// One block = 32 pixels of one image: probabilities staged in shared memory, each thread owns
+// 8 consecutive output channels of 2 pixels... kept simple: thread = (pixel, 8 channels).
+constexpr int CMB_PIX = 32;
+__global__ void __launch_bounds__(256) combiner_fwd_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
+                                                         const float* __restrict__ p2, const float* __restrict__ w,
+                                                         const __nv_bfloat16* __restrict__ inp,
+                                                         __nv_bfloat16* __restrict__ out, int J, int HW, int C) {
+  extern __shared__ float sm[];
+  const int K = 3 * J;
+  float* sp = sm;                 // [K][CMB_PIX]
+  float* sw = sm + K * CMB_PIX;   // [C][K]
+  const int n = blockIdx.y;
+  const int pix0 = blockIdx.x * CMB_PIX;
+  for (int i = threadIdx.x; i < K * CMB_PIX; i += blockDim.x) {
+    const int k = i / CMB_PIX, px = i - k * CMB_PIX;
+    const float* src = k < J ? p0 : (k < 2 * J ? p1 : p2);
+    const int j = k % J;
+    sp[i] = (pix0 + px < HW) ? src[((long long)n * J + j) * HW + pix0 + px] : 0.f;
+  }
+  for (int i = threadIdx.x; i < C * K; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int G = C / 8;
+  for (int i = threadIdx.x; i < CMB_PIX * G; i += blockDim.x) {
+    const int px = i / G, g = i - px * G;
+    if (pix0 + px >= HW) continue;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float pv = sp[k * CMB_PIX + px];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(sw[(g * 8 + j) * K + k], pv, acc[j]);
+    }
+    const long long o = ((long long)n * HW + pix0 + px) * C + g * 8;
+    float base[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(inp + o)), base);
+    // fp32 weights, fp32 probabilities, fp32 accumulate; the new stage input is rounded to bf16 once
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = base[j] + acc[j];
+    *reinterpret_cast<uint4*>(out + o) = pack8(acc);
+  }
+}
+
+// dp_k[n, j, pix] = sum_c w[c, k*J + j] * dout[pix, c];  dw[c, kk] += sum_pix dout[pix, c] * p[kk, pix]
+__global__ void __launch_bounds__(256) combiner_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                         const float* __restrict__ p0, const float* __restrict__ p1,
+                                                         const float* __restrict__ p2, const float* __restrict__ w,
+                                                         float* __restrict__ dp0, float* __restrict__ dp1,
+                                                         float* __restrict__ dp2, float* __restrict__ dw,
+                                                         int accumulate, int J, int HW, int C) {
+  extern __shared__ float sm[];
+  const int K = 3 * J;
+  float* sd = sm;                    // [CMB_PIX][C + 1]
+  float* sw = sd + CMB_PIX * (C + 1);   // [C][K]
+  float* sp = sw + C * K;            // [K][CMB_PIX]
+  const int n = blockIdx.y;
+  const int pix0 = blockIdx.x * CMB_PIX;
+  for (int i = threadIdx.x; i < CMB_PIX * C; i += blockDim.x) {
+    const int px = i / C, c = i - px * C;
+    sd[px * (C + 1) + c] =
+        (pix0 + px < HW) ? __bfloat162float(dout[((long long)n * HW + pix0 + px) * C + c]) : 0.f;
+  }
+  for (int i = threadIdx.x; i < C * K; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < K * CMB_PIX; i += blockDim.x) {
+    const int k = i / CMB_PIX, px = i - k * CMB_PIX;
+    const float* src = k < J ? p0 : (k < 2 * J ? p1 : p2);
+    sp[i] = (pix0 + px < HW) ? src[((long long)n * J + (k % J)) * HW + pix0 + px] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * CMB_PIX; i += blockDim.x) {
+    const int k = i / CMB_PIX, px = i - k * CMB_PIX;
+    if (pix0 + px >= HW) continue;
+    float acc = 0.f;
+    for (int c = 0; c < C; ++c) acc = fmaf(sw[c * K + k], sd[px * (C + 1) + c], acc);
+    float* dst = k < J ? dp0 : (k < 2 * J ? dp1 : dp2);
+    float* d = dst + ((long long)n * J + (k % J)) * HW + pix0 + px;
+    *d = accumulate ? *d + acc : acc;
+  }
+  for (int i = threadIdx.x; i < C * K; i += blockDim.x) {
+    const int c = i / K, k = i - c * K;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int px = 0; px < CMB_PIX; ++px) acc = fmaf(sd[px * (C + 1) + c], sp[k * CMB_PIX + px], acc);
+    atomicAdd(dw + i, acc);
+  }
+}
+
+// -------------------------------------------------------------------------------- stem im2col
+// patches[n, ho, wo, (r*7+s)*3 + c] = x[n, c, 2*ho + r - 3, 2*wo + s - 3]; 192 columns per row.
+__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
+                                   int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Ho * Wo * 24;   // 24 groups of 8 columns
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int g = (int)(i % 24);
+  long long t = i / 24;
+  const int wo = (int)(t % Wo); t /= Wo;
+  const int ho = (int)(t % Ho);
+  const int n = (int)(t / Ho);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = g * 8 + j;
+    float val = 0.f;
+    if (k < 147) {
+      const int tap = k / 3, c = k - tap * 3;
+      const int r = tap / 7, s = tap - r * 7;
+      const int h = 2 * ho + r - 3, w = 2 * wo + s - 3;
+      if (h >= 0 && h < H && w >= 0 && w < W) val = __ldg(x + (((long long)n * 3 + c) * H + h) * W + w);
+    }
+    v[j] = val;
+  }
+  *reinterpret_cast<uint4*>(out + (((long long)n * Ho + ho) * Wo + wo) * 192 + g * 8) = pack8(v);
+}
+
+// -------------------------------------------------------------------------------------- add_n
+__global__ void add_bf16_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, const __nv_bfloat16* c,
+                                const __nv_bfloat16* d, int n, __nv_bfloat16* out, long long groups) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups) return;
+  float acc[8], v[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(a) + i), acc);
+  const __nv_bfloat16* rest[3] = {b, c, d};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (k + 1 < n) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(rest[k]) + i), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+  reinterpret_cast<uint4*>(out)[i] = pack8(acc);
+}
+
+// ------------------------------------------------------------------------------- weight packing
+__global__ void pack_weights_kernel(const float* __restrict__ master, __nv_bfloat16* __restrict__ packed,
+                                    const mp_pack_entry* __restrict__ table, int n_entries, long long groups) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups) return;
+  const long long e0 = i * 8;   // first work element of this thread's 8
+  int lo = 0, hi = n_entries - 1;
+  while (lo < hi) {   // first entry with work_end > e0
+    const int mid = (lo + hi) >> 1;
+    if (table[mid].work_end > e0) hi = mid; else lo = mid + 1;
+  }
+  const mp_pack_entry E = table[lo];
+  const long long local = e0 - E.work_off;
+  const int c0 = (int)(local % E.cols_p);
+  const long long rt = local / E.cols_p;
+  const int t = (int)(rt % E.taps);
+  const int r = (int)(rt / E.taps);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    float val = 0.f;
+    if (!E.transpose) {
+      if (r < E.A && c < E.B) val = master[E.src_off + ((long long)r * E.taps + t) * E.B + c];
+    } else {
+      if (c < E.A && r < E.B) val = master[E.src_off + ((long long)c * E.taps + t) * E.B + r];
+    }
+    v[j] = val;
+  }
+  *reinterpret_cast<uint4*>(packed + E.dst_off + (long long)r * E.dst_row_stride + (long long)t * E.cols_p + c0) =
+      pack8(v);
+}
+
+// ------------------------------------------------------------------------------------------ SGD
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                           long long n, float lr, float mom, float damp, float wd, int nesterov, int first,
+                           float gscale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float grad = g[i] * gscale;
+  const float w = p[i];
+  if (wd != 0.f) grad = fmaf(wd, w, grad);
+  if (mom != 0.f) {
+    const float b = first ? grad : fmaf(mom, buf[i], (1.f - damp) * grad);
+    buf[i] = b;
+    grad = nesterov ? fmaf(mom, b, grad) : b;
+  }
+  p[i] = fmaf(-lr, grad, w);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mp_maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, void* stream) {
+  MP_CHECK_ARG(x && y && idx && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0,
+               "mp_maxpool_fwd: bad arguments");
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  maxpool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, idx, N, H, W, C);
+  MP_CHECK_LAUNCH("mp_maxpool_fwd");
+  return MP_OK;
+}
+
+int mp_maxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int N, int H, int W, int C, void* stream) {
+  MP_CHECK_ARG(dy && dx && idx && N > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "mp_maxpool_bwd: bad arguments");
+  const long long total = (long long)N * H * W * (C / 8);
+  maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dy, idx, (__nv_bfloat16*)dx, N, H, W, C);
+  MP_CHECK_LAUNCH("mp_maxpool_bwd");
+  return MP_OK;
+}
+
+int mp_axis_permute(const void* in, void* out, int mode, int N, int S, int C, int Cp, void* stream) {
+  MP_CHECK_ARG(in && out && in != out && (mode == 1 || mode == 2) && N > 0 && S > 0 && C % S == 0 && Cp >= C,
+               "mp_axis_permute: bad arguments (the spatial size must divide the channel count)");
+  const long long total = (long long)N * S * S * Cp;
+  axis_permute_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in, (__nv_bfloat16*)out, mode, N, S, C, Cp);
+  MP_CHECK_LAUNCH("mp_axis_permute");
+  return MP_OK;
+}
+
+int mp_combiner_fwd(const float* const p[3], const float* w, const void* inp, void* out, int N, int J, int HW,
+                    int C, void* stream) {
+  MP_CHECK_ARG(p && p[0] && p[1] && p[2] && w && inp && out && N > 0 && J > 0 && HW > 0 && C % 8 == 0,
+               "mp_combiner_fwd: bad arguments");
+  const size_t smem = (size_t)(3 * J * CMB_PIX + C * 3 * J) * sizeof(float);
+  MP_CHECK_ARG(smem <= 48 * 1024, "mp_combiner_fwd: J*C too large");
+  dim3 grid((HW + CMB_PIX - 1) / CMB_PIX, N);
+  combiner_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p[0], p[1], p[2], w, (const __nv_bfloat16*)inp,
+                                                                 (__nv_bfloat16*)out, J, HW, C);
+  MP_CHECK_LAUNCH("mp_combiner_fwd");
+  return MP_OK;
+}
+
+int mp_combiner_bwd(const void* dout, const float* const p[3], const float* w, float* const dp[3], float* dw,
+                    int accumulate, int N, int J, int HW, int C, void* stream) {
+  MP_CHECK_ARG(dout && p && p[0] && p[1] && p[2] && w && dp && dp[0] && dp[1] && dp[2] && dw && N > 0 && J > 0 &&
+                   HW > 0 && C > 0,
+               "mp_combiner_bwd: bad arguments");
+  const size_t smem = (size_t)(CMB_PIX * (C + 1) + C * 3 * J + 3 * J * CMB_PIX) * sizeof(float);
+  MP_CHECK_ARG(smem <= 48 * 1024, "mp_combiner_bwd: J*C too large");
+  dim3 grid((HW + CMB_PIX - 1) / CMB_PIX, N);
+  combiner_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, p[0], p[1], p[2], w,
+                                                                 dp[0], dp[1], dp[2], dw, accumulate, J, HW, C);
+  MP_CHECK_LAUNCH("mp_combiner_bwd");
+  return MP_OK;
+}
+
+int mp_stem_im2col(const float* x, void* patches, int N, int H, int W, void* stream) {
+  MP_CHECK_ARG(x && patches && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "mp_stem_im2col: bad arguments");
+  const long long total = (long long)N * (H / 2) * (W / 2) * 24;
+  stem_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, (__nv_bfloat16*)patches, N, H, W);
+  MP_CHECK_LAUNCH("mp_stem_im2col");
+  return MP_OK;
+}
+
+int mp_add_bf16(const void* const in[4], int n, void* out, int64_t count, void* stream) {
+  MP_CHECK_ARG(in && out && n >= 1 && n <= 4 && count > 0 && count % 8 == 0, "mp_add_bf16: bad arguments");
+  for (int i = 0; i < n; ++i) MP_CHECK_ARG(in[i] && mp_aligned16(in[i]), "mp_add_bf16: bad input %d", i);
+  const long long groups = count / 8;
+  add_bf16_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in[0], (const __nv_bfloat16*)(n > 1 ? in[1] : nullptr),
+      (const __nv_bfloat16*)(n > 2 ? in[2] : nullptr), (const __nv_bfloat16*)(n > 3 ? in[3] : nullptr), n,
+      (__nv_bfloat16*)out, groups);
+  MP_CHECK_LAUNCH("mp_add_bf16");
+  return MP_OK;
+}
+
+int mp_pack_weights(const float* master, void* packed, const mp_pack_entry* table, int n_entries,
+                    int64_t total_work, void* stream) {
+  MP_CHECK_ARG(master && packed && table && n_entries > 0 && total_work > 0 && total_work % 8 == 0,
+               "mp_pack_weights: bad arguments");
+  const long long groups = total_work / 8;
+  pack_weights_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      master, (__nv_bfloat16*)packed, table, n_entries, groups);
+  MP_CHECK_LAUNCH("mp_pack_weights");
+  return MP_OK;
+}
+
+int mp_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                float dampening, float weight_decay, int nesterov, int first_step, float grad_scale,
+                void* stream) {
+  MP_CHECK_ARG(param && grad && n > 0 && (momentum == 0.f || momentum_buf), "mp_sgd_step: bad arguments");
+  sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, momentum_buf, n, lr, momentum, dampening, weight_decay, nesterov, first_step, grad_scale);
+  MP_CHECK_LAUNCH("mp_sgd_step");
+  return MP_OK;
+}
+
+}  // extern "C"

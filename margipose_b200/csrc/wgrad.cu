@@ -28,7 +28,7 @@ struct WgradParams {
   int n_taps, T;
   int kp_w, kp_rows, chunks_w, chunks_h, chunks_total;
   int b_boxes, box_bytes, stage_bytes, stages, stage_tx, tmem_cols, ksteps;
-  int m_real, n_real, n_cols, n_slots;
+  int m_real, n_real, n_cols, n_slots, n_off;
   int vec_ok;
   float* dw;
 };
@@ -87,7 +87,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const mp_tap tap = P.taps[tap0 + t];
           for (int j = 0; j < P.b_boxes; ++j)
             tc::tma_load_5d(&tmB, &full[s], st + (size_t)(2 + t * P.b_boxes + j) * P.box_bytes,
-                            tap.c0 + j * 64, w0 + tap.dw, tap.p, h0 + tap.dh, img);
+                            tap.c0 + P.n_off + j * 64, w0 + tap.dw, tap.p, h0 + tap.dh, img);
         }
         if (++s == stages) { s = 0; ph ^= 1; }
       }
@@ -121,21 +121,22 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const bool valid = row < P.m_real;
     for (int t = 0; t < ntap; ++t) {
       const int slot = P.taps[tap0 + t].koff;
-      float* dst = P.dw + ((size_t)row * P.n_slots + slot) * P.n_real;
+      float* dst = P.dw + ((size_t)row * P.n_slots + slot) * P.n_real + P.n_off;
+      const int n_left = P.n_real - P.n_off;
       for (int c = 0; c < P.n_cols / 32; ++c) {
-        if (c * 32 >= P.n_real) break;   // warp-uniform
+        if (c * 32 >= n_left) break;   // warp-uniform
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * P.n_cols + c * 32), v);
         if (!valid) continue;
         if (P.vec_ok) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (c * 32 + j * 4 < P.n_real)
+            if (c * 32 + j * 4 < n_left)
               tc::red_add_v4(dst + c * 32 + j * 4, v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < P.n_real) atomicAdd(dst + c * 32 + j, v[j]);
+            if (c * 32 + j < n_left) atomicAdd(dst + c * 32 + j, v[j]);
         }
       }
     }
@@ -174,7 +175,8 @@ extern "C" int mp_conv_wgrad(const mp_wgrad_args* a, void* stream) {
   MP_CHECK_ARG(a->a.ptr && a->b.ptr && a->dw, "mp_conv_wgrad: null tensor");
   MP_CHECK_ARG(a->n_cols >= 64 && a->n_cols % 64 == 0 && a->n_cols <= 256,
                "mp_conv_wgrad: n_cols %d must be 64, 128, 192 or 256", a->n_cols);
-  MP_CHECK_ARG(a->m_real > 0 && a->n_real > 0 && a->n_real <= a->n_cols, "mp_conv_wgrad: bad channel counts");
+  MP_CHECK_ARG(a->m_real > 0 && a->n_real > 0 && a->n_off >= 0 && a->n_off % 64 == 0 && a->n_off < a->n_real,
+               "mp_conv_wgrad: bad channel counts");
   MP_CHECK_ARG(a->n_img > 0 && a->grid_h > 0 && a->grid_w > 0, "mp_conv_wgrad: empty pixel grid");
   for (int i = 0; i < a->n_taps; ++i)
     MP_CHECK_ARG(a->taps[i].koff >= 0 && a->taps[i].koff < a->n_slots, "mp_conv_wgrad: tap %d: bad slot", i);
@@ -208,7 +210,7 @@ extern "C" int mp_conv_wgrad(const mp_wgrad_args* a, void* stream) {
   P.ksteps = kp / 16;
   const int cols = T * a->n_cols;
   P.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-  P.m_real = a->m_real; P.n_real = a->n_real; P.n_cols = a->n_cols; P.n_slots = a->n_slots;
+  P.m_real = a->m_real; P.n_real = a->n_real; P.n_cols = a->n_cols; P.n_slots = a->n_slots; P.n_off = a->n_off;
   P.vec_ok = (a->n_real % 4 == 0) && mp_aligned16(a->dw);
   P.dw = a->dw;
 

@@ -1,0 +1,693 @@
+"""Static execution engine for the MargiPose network body on one B200.
+
+Walks the module tree of `margipose_b200.models.margipose_model.MargiPoseModel` (which mirrors
+/root/reference/src/margipose/models/margipose_model.py:153-200 and the truncated torchvision
+ResNet of :119-138) once per (batch, resolution), allocates every activation / gradient buffer
+up front (bf16 NHWC, channels padded to 64), and records the forward and backward passes as flat
+lists of C-ABI launches with pre-built argument structs.  Running a pass is then a loop of ctypes
+calls -- no allocation, no autograd graph, no host synchronisation -- which is also what makes
+the whole training step capturable in one CUDA graph.  The three HeatmapColumns of a stage are
+independent (margipose_model.py:196-198) and run on three streams.
+
+Parameters live in ONE flat fp32 buffer (conv weights in channels-last memory = the GEMM's
+[rows][taps][cols] order), gradients in a second flat buffer with the same layout, and the bf16
+GEMM operands in a third that one mp_pack_weights launch refreshes.  The nn.Parameters of the
+module tree are views into the flat buffers, so state_dict()/load_state_dict()/optimizers see
+ordinary tensors with the reference's key names and shapes.
+"""
+import ctypes
+
+import torch
+from torch import nn
+
+from . import convops as C
+from . import dsntnn as K
+from ._lib import (BnArgs, PackEntry, lib, check, stream_ptr, planes, MargiposeB200Error)
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+# ------------------------------------------------------------------------------------ parameters
+class _Slot:
+    """A parameter (or buffer) of the module tree and its place in a flat buffer."""
+
+    def __init__(self, mod, name, off, numel, master_shape=None, conv_k=None):
+        self.mod, self.name, self.off, self.numel = mod, name, off, numel
+        self.master_shape = master_shape     # conv weights: (rows, taps, cols)
+        self.conv_k = conv_k
+        self.data = None                     # flat view, master layout
+        self.grad = None
+
+
+class ParamBank:
+    """Flat storage for parameters, gradients, BatchNorm buffers and bf16 weight packs."""
+
+    def __init__(self):
+        self.params, self.buffers, self.counters = [], [], []
+        self.n_param = self.n_buffer = 0
+        self.pack_entries = []          # dicts; turned into a device table by finalize()
+        self.n_pack = self.n_work = 0
+        self._seen = {}
+        self.flat = self.flat_grad = self.flat_buf = self.flat_cnt = self.packs = None
+        self._mats = []
+
+    def _align(self, n, a=8):
+        return (n + a - 1) // a * a
+
+    def add_param(self, mod, name, master_shape=None, conv_k=None):
+        key = (id(mod), name)
+        if key in self._seen:
+            return self._seen[key]
+        p = getattr(mod, name)
+        s = _Slot(mod, name, self.n_param, p.numel(), master_shape, conv_k)
+        self.n_param += self._align(p.numel())
+        self.params.append(s)
+        self._seen[key] = s
+        return s
+
+    def add_buffer(self, mod, name):
+        key = (id(mod), name)
+        if key in self._seen:
+            return self._seen[key]
+        b = getattr(mod, name)
+        if b.dtype == torch.int64:
+            s = _Slot(mod, name, len(self.counters), 1)
+            self.counters.append(s)
+        else:
+            s = _Slot(mod, name, self.n_buffer, b.numel())
+            self.n_buffer += self._align(b.numel())
+            self.buffers.append(s)
+        self._seen[key] = s
+        return s
+
+    def add_matrix(self, rows_p, parts):
+        """A bf16 GEMM operand [rows_p][sum of taps*cols_p]; parts = [(slot, transpose, A, B, taps,
+        cols_p)] laid side by side along K.  Returns a handle with .t (tensor) after finalize()."""
+        k_total = sum(taps * cols_p for (_s, _tr, _a, _b, taps, cols_p) in parts)
+        mat = type('Mat', (), {})()
+        mat.rows, mat.k, mat.off, mat.koffs, mat.t = rows_p, k_total, self.n_pack, [], None
+        koff = 0
+        for slot, transpose, a, b, taps, cols_p in parts:
+            work = rows_p * taps * cols_p
+            self.pack_entries.append(dict(slot=slot, dst_off=self.n_pack + koff, row_stride=k_total,
+                                          work_off=self.n_work, work_end=self.n_work + work, A=a, B=b,
+                                          taps=taps, transpose=int(transpose), rows_p=rows_p,
+                                          cols_p=cols_p))
+            self.n_work += work
+            mat.koffs.append(koff)
+            koff += taps * cols_p
+        self.n_pack += rows_p * k_total
+        self._mats.append(mat)
+        return mat
+
+    def finalize(self, device):
+        self.flat = torch.zeros(max(self.n_param, 8), device=device)
+        self.flat_grad = torch.zeros_like(self.flat)
+        self.flat_buf = torch.zeros(max(self.n_buffer, 8), device=device)
+        self.flat_cnt = torch.zeros(max(len(self.counters), 1), dtype=torch.int64, device=device)
+        self.packs = torch.zeros(max(self.n_pack, 8), dtype=torch.bfloat16, device=device)
+        for s in self.params:
+            p = getattr(s.mod, s.name)
+            s.data = self.flat[s.off:s.off + s.numel]
+            s.grad = self.flat_grad[s.off:s.off + s.numel]
+            if s.master_shape is not None:      # conv weight: channels-last memory, torch-shaped view
+                rows, taps, cols = s.master_shape
+                k = s.conv_k
+                view = s.data.view(rows, k, k, -1).permute(0, 3, 1, 2)
+                gview = s.grad.view(rows, k, k, -1).permute(0, 3, 1, 2)
+                s.data = s.data.view(rows, taps, cols)
+                s.grad = s.grad.view(rows, taps, cols)
+            else:
+                view, gview = s.data.view(p.shape), s.grad.view(p.shape)
+            with torch.no_grad():
+                view.copy_(p.detach().to(device=device, dtype=torch.float32))
+            p.data = view
+            p.grad = None
+            s.view, s.gview = view, gview
+        for s in self.buffers:
+            b = getattr(s.mod, s.name)
+            s.data = self.flat_buf[s.off:s.off + s.numel]
+            s.data.copy_(b.detach().to(device=device, dtype=torch.float32))
+            s.mod._buffers[s.name] = s.data.view(b.shape)
+        for s in self.counters:
+            b = getattr(s.mod, s.name)
+            self.flat_cnt[s.off] = int(b)
+            s.mod._buffers[s.name] = self.flat_cnt[s.off]
+        table = (PackEntry * max(len(self.pack_entries), 1))()
+        for i, e in enumerate(self.pack_entries):
+            t = table[i]
+            t.src_off, t.dst_off, t.dst_row_stride = e['slot'].off, e['dst_off'], e['row_stride']
+            t.work_off, t.work_end = e['work_off'], e['work_end']
+            t.A, t.B, t.taps, t.transpose = e['A'], e['B'], e['taps'], e['transpose']
+            t.rows_p, t.cols_p = e['rows_p'], e['cols_p']
+        raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8)
+        self.pack_table = raw.to(device)
+        for m in self._mats:
+            m.t = self.packs[m.off:m.off + m.rows * m.k].view(m.rows, m.k)
+        self.device = device
+
+    def linked(self):
+        """True while every nn.Parameter still aliases its slice of the flat buffer."""
+        return all(getattr(s.mod, s.name).data_ptr() == s.view.data_ptr() for s in self.params[:4]) and \
+            all(getattr(s.mod, s.name).data_ptr() == s.view.data_ptr() for s in self.params[-4:])
+
+    def pack(self):
+        if not self.pack_entries:
+            return
+        check(lib().mp_pack_weights(self.flat.data_ptr(), self.packs.data_ptr(), self.pack_table.data_ptr(),
+                                    len(self.pack_entries), self.n_work, stream_ptr(self.device)),
+              'mp_pack_weights')
+
+    def attach_grads(self):
+        """Makes p.grad a view of the flat gradient buffer; zeroes the buffer when the caller has
+        cleared the grads (zero_grad(set_to_none=True)), so launches can accumulate (+=)."""
+        if all(getattr(s.mod, s.name).grad is None for s in self.params):
+            self.flat_grad.zero_()
+        for s in self.params:
+            p = getattr(s.mod, s.name)
+            if p.grad is None:
+                if p.requires_grad:
+                    p.grad = s.gview
+            elif p.grad.data_ptr() != s.gview.data_ptr():
+                s.gview.copy_(p.grad)
+                p.grad = s.gview
+
+
+# ---------------------------------------------------------------------------------------- layers
+class ConvL:
+    def __init__(self, bank, mod, stem=False):
+        self.mod, self.stem = mod, stem
+        if stem:
+            assert mod.kernel_size == (7, 7) and mod.stride == (2, 2) and mod.in_channels == 3
+            self.g = C.ConvGeom(147, mod.out_channels, 1)
+            master, k = (mod.out_channels, 1, 147), 7
+        else:
+            tr = isinstance(mod, nn.ConvTranspose2d)
+            k = mod.kernel_size[0]
+            assert mod.kernel_size == (k, k) and mod.stride[0] == mod.stride[1]
+            assert mod.padding == (k // 2, k // 2), 'only "same"-style padding is on the hot path'
+            if tr:
+                assert mod.stride == (2, 2) and mod.output_padding == (1, 1)
+            self.g = C.ConvGeom(mod.in_channels, mod.out_channels, k, mod.stride[0], tr)
+            master = self.g.master_shape
+        self.w = bank.add_param(mod, 'weight', master_shape=master, conv_k=k)
+        self.bias = bank.add_param(mod, 'bias') if mod.bias is not None else None
+        g = self.g
+        if g.transposed:
+            self.fwd = bank.add_matrix(g.cout_p, [(self.w, 1, g.cin, g.cout, g.taps, g.cin_p)])
+        else:
+            self.fwd = bank.add_matrix(g.cout_p, [(self.w, 0, g.cout, g.cin, g.taps, g.cin_p)])
+        self.bwd = None
+
+    def bwd_part(self):
+        g = self.g
+        if g.transposed:
+            return (self.w, 0, g.cin, g.cout, g.taps, g.cout_p)
+        return (self.w, 1, g.cout, g.cin, g.taps, g.cout_p)
+
+    def need_bwd(self, bank):
+        if self.bwd is None:
+            self.bwd = bank.add_matrix(self.g.cin_p, [self.bwd_part()])
+        return self.bwd
+
+
+class BNL:
+    def __init__(self, bank, layers, mod, conv_bias=None):
+        self.mod = mod
+        self.C = mod.num_features
+        self.Cp = C.pad64(self.C)
+        self.gamma = bank.add_param(mod, 'weight')
+        self.beta = bank.add_param(mod, 'bias')
+        self.rm = bank.add_buffer(mod, 'running_mean')
+        self.rv = bank.add_buffer(mod, 'running_var')
+        self.nbt = bank.add_buffer(mod, 'num_batches_tracked')
+        self.conv_bias = conv_bias
+        self.slot = layers.bn_floats          # fwd sums at slot (2*Cp); saved stats use the same offset
+        layers.bn_floats += 2 * self.Cp
+
+
+class _NS:
+    pass
+
+
+def _fusable(a, b):
+    return a.g.stride == b.g.stride and a.g.transposed == b.g.transposed and \
+        a.g.cin_p == b.g.cin_p and a.g.cout_p == b.g.cout_p
+
+
+def build_layers(model, bank):
+    """Layer graph of the reference network (margipose_model.py:103-200) over `bank` storage."""
+    L = _NS()
+    L.bn_floats = 0
+    inner = model.inner
+    L.n_stages, L.n_joints = inner.n_stages, model.n_joints
+    cnn = inner.in_cnn
+    L.stem = (ConvL(bank, cnn[0], stem=True), BNL(bank, L, cnn[1]))
+    L.res_blocks = []
+    for layer in (cnn[4], cnn[5]):
+        for blk in layer:
+            b = _NS()
+            names = ['conv1', 'conv2', 'conv3'] if hasattr(blk, 'conv3') else ['conv1', 'conv2']
+            b.chain = [(ConvL(bank, getattr(blk, c)), BNL(bank, L, getattr(blk, 'bn' + c[-1]))) for c in names]
+            b.down = None
+            if blk.downsample is not None:
+                b.down = (ConvL(bank, blk.downsample[0]), BNL(bank, L, blk.downsample[1]))
+            for conv, _bn in b.chain[1:]:
+                conv.need_bwd(bank)
+            b.fused = None
+            if b.down is not None and _fusable(b.chain[0][0], b.down[0]):
+                b.fused = bank.add_matrix(b.chain[0][0].g.cin_p,
+                                          [b.chain[0][0].bwd_part(), b.down[0].bwd_part()])
+            else:
+                b.chain[0][0].need_bwd(bank)
+                if b.down is not None:
+                    b.down[0].need_bwd(bank)
+            L.res_blocks.append(b)
+    L.adapter = None
+    if len(cnn) > 6:
+        conva = ConvL(bank, cnn[6])
+        conva.need_bwd(bank)
+        L.adapter = (conva, BNL(bank, L, cnn[7], conv_bias=conva.bias))
+
+    def rb_of(block):
+        r = _NS()
+        r.conv1, r.bn1 = ConvL(bank, block.module[0]), BNL(bank, L, block.module[1])
+        r.conv2, r.bn2 = ConvL(bank, block.module[3]), BNL(bank, L, block.module[4])
+        r.convs, r.bns = ConvL(bank, block.shortcut[0]), BNL(bank, L, block.shortcut[1])
+        r.conv2.need_bwd(bank)
+        assert _fusable(r.conv1, r.convs)
+        r.fused = bank.add_matrix(r.conv1.g.cin_p, [r.conv1.bwd_part(), r.convs.bwd_part()])
+        return r
+
+    L.columns = []
+    for t in range(L.n_stages):
+        row = []
+        for cols in (inner.xy_hm_cnns, inner.zy_hm_cnns, inner.xz_hm_cnns):
+            col = cols[t]
+            c = _NS()
+            c.mode = {'xy': 0, 'zy': 1, 'xz': 2}[col.heatmap_space]
+            c.down = [rb_of(b) for b in col.down_layers]
+            c.up = [rb_of(b) for b in col.up_layers]
+            c.mid_channels = c.down[-1].conv2.g.cout
+            row.append(c)
+        L.columns.append(row)
+    L.combiners = [bank.add_param(cmb.conv, 'weight', master_shape=(cmb.conv.out_channels, 1,
+                                                                    cmb.conv.in_channels), conv_k=1)
+                   for cmb in inner.hm_combiners]
+    return L
+
+
+class Engine:
+    """Buffers + launch programs for one (batch, height, width, mode)."""
+
+    def __init__(self, model, n, h, w, training, device):
+        self.model, self.n, self.h, self.w, self.training, self.device = model, n, h, w, training, device
+        self.bank, self.L = model._bank, model._layers
+        self._bufs = []
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(3)]
+        # per-BatchNorm fwd sums (2*Cp each) followed by the backward reductions (4*Cp per op)
+        self.stats = torch.zeros(max(3 * self.L.bn_floats, 8), device=device)
+        self.saves = torch.zeros(max(self.L.bn_floats, 8), device=device)
+        self._stat_n = self.L.bn_floats
+        self.fwd, self.bwd = [], []
+        self.trace = []        # (name, buffer, real channels) of every block output, in forward order
+        self._record()
+
+    def act(self, n, h, w, c, dtype=torch.bfloat16):
+        t = torch.zeros(n, h, w, c, dtype=dtype, device=self.device)
+        self._bufs.append(t)
+        return t
+
+    def activation_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self._bufs)
+
+    # ---- op recording helpers: an op is a zero-argument callable
+    def _launch(self, fn_name, args):
+        fn = getattr(lib(), fn_name)
+        ref = ctypes.byref(args)
+        dev = self.device
+
+        def op():
+            rc = fn(ref, stream_ptr(dev))
+            if rc != 0:
+                check(rc, fn_name)
+        op.args = args
+        op.name = fn_name
+        return op
+
+    def conv_ops(self, record):
+        """Runs `record()` (calls into convops) capturing its launches as ops."""
+        captured = []
+        old_i, old_w = C._igemm_launch, C._wgrad_launch
+        C._igemm_launch = lambda a, dev: captured.append(self._launch('mp_conv_igemm', a))
+        C._wgrad_launch = lambda a, dev: captured.append(self._launch('mp_conv_wgrad', a))
+        try:
+            record()
+        finally:
+            C._igemm_launch, C._wgrad_launch = old_i, old_w
+        return captured
+
+    def _call(self, fn_name, *argv):
+        """Op for a C-ABI entry point with scalar/pointer arguments + trailing stream."""
+        fn = getattr(lib(), fn_name)
+        dev = self.device
+
+        def op():
+            rc = fn(*argv, stream_ptr(dev))
+            if rc != 0:
+                check(rc, fn_name)
+        op.name = fn_name
+        return op
+
+    def bn_args(self, a, ya, b=None, yb=None, res=None, relu_a=False, relu_out=False, out=None,
+                out_nchw=None, hw=0):
+        args = BnArgs()
+        sbase, vbase = self.stats.data_ptr(), self.saves.data_ptr()
+
+        def fill(br, bn, y):
+            br.y = _ptr(y)
+            br.sum = sbase + 4 * bn.slot
+            br.sq = sbase + 4 * (bn.slot + bn.Cp)
+            br.gamma, br.beta = bn.gamma.data.data_ptr(), bn.beta.data.data_ptr()
+            br.running_mean, br.running_var = bn.rm.data.data_ptr(), bn.rv.data.data_ptr()
+            br.save_mean = vbase + 4 * bn.slot
+            br.save_invstd = vbase + 4 * (bn.slot + bn.Cp)
+            br.conv_bias = bn.conv_bias.data.data_ptr() if bn.conv_bias is not None else None
+            br.dgamma, br.dbeta = bn.gamma.grad.data_ptr(), bn.beta.grad.data_ptr()
+        fill(args.a, a, ya)
+        if b is not None:
+            fill(args.b, b, yb)
+        args.res = _ptr(res)
+        args.relu_a, args.relu_out = int(relu_a), int(relu_out)
+        args.out, args.out_nchw = _ptr(out), _ptr(out_nchw)
+        args.M = ya.numel() // ya.shape[-1]
+        args.C, args.Cp, args.HW = a.C, a.Cp, hw
+        args.training = int(self.training)
+        args.momentum = a.mod.momentum if a.mod.momentum is not None else 0.1
+        args.eps = a.mod.eps
+        return args
+
+    def stats_of(self, bn):
+        s = self.stats
+        return (s[bn.slot:bn.slot + bn.Cp], s[bn.slot + bn.Cp:bn.slot + 2 * bn.Cp])
+
+    def conv_fwd(self, prog, conv, x, bn):
+        g = conv.g
+        n, h, w, _ = x.shape
+        ho, wo = g.out_hw(h, w)
+        y = self.act(n, ho, wo, g.cout_p)
+        stats = self.stats_of(bn) if (self.training and bn is not None) else None
+        prog += self.conv_ops(lambda: C.conv_forward(g, x, conv.fwd.t, y, stats=stats))
+        return y
+
+    def bn_bwd(self, prog, fwd_args, dout=None, dout_nchw=None, dya=None, dyb=None, dres=None):
+        """Backward of a bn_fwd op: same argument struct plus the gradient pointers."""
+        args = BnArgs.from_buffer_copy(fwd_args)
+        args.dout, args.dout_nchw = _ptr(dout), _ptr(dout_nchw)
+        args.a.dy, args.b.dy, args.dres = _ptr(dya), _ptr(dyb), _ptr(dres)
+        args.sums = self.stats.data_ptr() + 4 * self._stat_n
+        self._stat_n += 4 * fwd_args.Cp
+        assert self._stat_n <= self.stats.numel()
+        prog.append(self._launch('mp_bn_bwd_reduce', args))
+        prog.append(self._launch('mp_bn_bwd_apply', args))
+
+    # ---- blocks: each returns (output buffer, backward builder)
+    def residual_block(self, fwd, rb, x, logits_out=None):
+        """MargiPose ResidualBlock (margipose_model.py:25-40)."""
+        y1 = self.conv_fwd(fwd, rb.conv1, x, rb.bn1)
+        ys = self.conv_fwd(fwd, rb.convs, x, rb.bns)
+        a1 = self.act(*y1.shape)
+        f1 = self.bn_args(rb.bn1, y1, relu_a=True, out=a1)
+        fwd.append(self._launch('mp_bn_fwd', f1))
+        y2 = self.conv_fwd(fwd, rb.conv2, a1, rb.bn2)
+        n, h, w, cp = y2.shape
+        out = None if logits_out is not None else self.act(n, h, w, cp)
+        f2 = self.bn_args(rb.bn2, y2, b=rb.bns, yb=ys, relu_a=True, out=out, out_nchw=logits_out, hw=h * w)
+        fwd.append(self._launch('mp_bn_fwd', f2))
+
+        def backward(bwd, dout=None, dout_nchw=None, need_dx=True):
+            dy2, dys = self.act(*y2.shape), self.act(*ys.shape)
+            self.bn_bwd(bwd, f2, dout=dout, dout_nchw=dout_nchw, dya=dy2, dyb=dys)
+            bwd += self.conv_ops(lambda: C.conv_wgrad(rb.conv2.g, a1, dy2, rb.conv2.w.grad))
+            da1 = self.act(*a1.shape)
+            bwd += self.conv_ops(lambda: C.conv_dgrad(rb.conv2.g, dy2, rb.conv2.bwd.t, da1))
+            dy1 = self.act(*y1.shape)
+            self.bn_bwd(bwd, f1, dout=da1, dya=dy1)
+            bwd += self.conv_ops(lambda: C.conv_wgrad(rb.conv1.g, x, dy1, rb.conv1.w.grad))
+            bwd += self.conv_ops(lambda: C.conv_wgrad(rb.convs.g, x, dys, rb.convs.w.grad))
+            if not need_dx:
+                return None
+            dx = self.act(*x.shape)
+            bwd += self.conv_ops(lambda: C.conv_dgrad(rb.conv1.g, dy1, rb.fused.t, dx,
+                                                      second=(rb.convs.g, dys, rb.fused.koffs[1])))
+            return dx
+        return (logits_out if logits_out is not None else out), backward
+
+    def resnet_block(self, fwd, blk, x):
+        """torchvision BasicBlock / Bottleneck: relu(bn_last(conv_last(...)) + identity)."""
+        chain, down = blk.chain, blk.down
+        acts, ys, fargs = [x], [], []
+        for i, (conv, bn) in enumerate(chain):
+            y = self.conv_fwd(fwd, conv, acts[-1], bn)
+            ys.append(y)
+            if i < len(chain) - 1:
+                a = self.act(*y.shape)
+                f = self.bn_args(bn, y, relu_a=True, out=a)
+                fwd.append(self._launch('mp_bn_fwd', f))
+                fargs.append(f)
+                acts.append(a)
+        out = self.act(*ys[-1].shape)
+        if down is not None:
+            yd = self.conv_fwd(fwd, down[0], x, down[1])
+            fl = self.bn_args(chain[-1][1], ys[-1], b=down[1], yb=yd, relu_out=True, out=out)
+        else:
+            yd = None
+            fl = self.bn_args(chain[-1][1], ys[-1], res=x, relu_out=True, out=out)
+        fwd.append(self._launch('mp_bn_fwd', fl))
+
+        def backward(bwd, dout, need_dx=True):
+            dyl = self.act(*ys[-1].shape)
+            dyd = self.act(*yd.shape) if yd is not None else None
+            dz = self.act(*x.shape) if (yd is None and need_dx) else None
+            self.bn_bwd(bwd, fl, dout=dout, dya=dyl, dyb=dyd, dres=dz)
+            dy = dyl
+            for i in range(len(chain) - 1, 0, -1):
+                conv = chain[i][0]
+                bwd += self.conv_ops(lambda conv=conv, i=i, dy=dy: C.conv_wgrad(conv.g, acts[i], dy, conv.w.grad))
+                da = self.act(*acts[i].shape)
+                bwd += self.conv_ops(lambda conv=conv, dy=dy, da=da: C.conv_dgrad(conv.g, dy, conv.bwd.t, da))
+                dy = self.act(*ys[i - 1].shape)
+                self.bn_bwd(bwd, fargs[i - 1], dout=da, dya=dy)
+            conv0 = chain[0][0]
+            bwd += self.conv_ops(lambda: C.conv_wgrad(conv0.g, x, dy, conv0.w.grad))
+            if down is not None:
+                bwd += self.conv_ops(lambda: C.conv_wgrad(down[0].g, x, dyd, down[0].w.grad))
+            if not need_dx:
+                return None
+            dx = self.act(*x.shape)
+            if down is None:
+                bwd += self.conv_ops(lambda: C.conv_dgrad(conv0.g, dy, conv0.bwd.t, dx, res=dz))
+            elif blk.fused is not None:
+                bwd += self.conv_ops(lambda: C.conv_dgrad(conv0.g, dy, blk.fused.t, dx,
+                                                          second=(down[0].g, dyd, blk.fused.koffs[1])))
+            else:   # different strides: full dgrad first, then the strided one accumulates in place
+                bwd += self.conv_ops(lambda: C.conv_dgrad(conv0.g, dy, conv0.bwd.t, dx))
+                bwd += self.conv_ops(lambda: C.conv_dgrad(down[0].g, dyd, down[0].bwd.t, dx, res=dx))
+            return dx
+        return out, backward
+
+    # ---- whole network
+    def _record(self):
+        L, dev, n, h, w = self.L, self.device, self.n, self.h, self.w
+        training = self.training
+        J = L.n_joints
+        fwd = []
+        # ---- stem (margipose_model.py:119-138)
+        self.x_in = torch.zeros(n, 3, h, w, device=dev)
+        patches = self.act(n, h // 2, w // 2, 192)
+        fwd.append(self._call('mp_stem_im2col', self.x_in.data_ptr(), patches.data_ptr(), n, h, w))
+        conv0, bn0 = L.stem
+        y0 = self.conv_fwd(fwd, conv0, patches, bn0)
+        a0 = self.act(*y0.shape)
+        f0 = self.bn_args(bn0, y0, relu_a=True, out=a0)
+        fwd.append(self._launch('mp_bn_fwd', f0))
+        hp, wp, c0 = h // 4, w // 4, y0.shape[-1]
+        p0 = self.act(n, hp, wp, c0)
+        idx = torch.zeros(n, hp, wp, c0, dtype=torch.uint8, device=dev)
+        self._bufs.append(idx)
+        fwd.append(self._call('mp_maxpool_fwd', a0.data_ptr(), p0.data_ptr(), idx.data_ptr(), n, h // 2, w // 2, c0))
+        self.trace += [('stem.relu', a0, bn0.C), ('stem.maxpool', p0, bn0.C)]
+        x = p0
+        res_bwd = []
+        for i, blk in enumerate(L.res_blocks):
+            x, b = self.resnet_block(fwd, blk, x)
+            res_bwd.append(b)
+            self.trace.append(('resnet.%d' % i, x, blk.chain[-1][1].C))
+        x_pre = x
+        if L.adapter is not None:
+            conva, bna = L.adapter
+            ya = self.conv_fwd(fwd, conva, x, bna)
+            x = self.act(*ya.shape)
+            fa = self.bn_args(bna, ya, relu_a=True, out=x)
+            fwd.append(self._launch('mp_bn_fwd', fa))
+            self.trace.append(('adapter', x, bna.C))
+        feats = x
+        hf, wf, cf = feats.shape[1], feats.shape[2], feats.shape[3]
+        self.heatmap_hw = (hf, wf)
+        # ---- stages (margipose_model.py:188-199)
+        segs = [('serial', fwd)]
+        inp = feats
+        self.probs, self.logits = [], []
+        inps, col_bwd, comb = [], [], []
+        for t in range(L.n_stages):
+            if t > 0:
+                prev, wc = self.probs[t - 1], L.combiners[t - 1]
+                new_inp = self.act(*inp.shape)
+                segs.append(('serial', [self._call('mp_combiner_fwd', planes(prev), wc.data.data_ptr(),
+                                                   inp.data_ptr(), new_inp.data_ptr(), n, J, hf * wf, cf)]))
+                comb.append((prev, wc))
+                inp = new_inp
+            inps.append(inp)
+            lanes, lane_bwd, lz, pr = [], [], [], []
+            for col in L.columns[t]:
+                ops, blk_b, perm = [], [], None
+                xcol = inp
+                for i, rb in enumerate(col.down):
+                    xcol, b = self.residual_block(ops, rb, xcol)
+                    blk_b.append(b)
+                    self.trace.append(('stage%d.col%d.down%d' % (t, col.mode, i), xcol, rb.bn2.C))
+                if col.mode != 0:
+                    s, cmid = xcol.shape[1], col.mid_channels
+                    if xcol.shape[1] != xcol.shape[2] or cmid % s != 0:
+                        raise MargiposeB200Error(
+                            'axis permutation needs a square mid feature map whose side (%d) divides '
+                            'the channel count (%d)' % (s, cmid))
+                    xp = self.act(*xcol.shape)
+                    ops.append(self._call('mp_axis_permute', xcol.data_ptr(), xp.data_ptr(), col.mode, n, s,
+                                          cmid, xcol.shape[-1]))
+                    perm = (col.mode, s, cmid, tuple(xcol.shape))
+                    xcol = xp
+                logits = torch.zeros(n, J, hf, wf, device=dev)
+                for i, rb in enumerate(col.up):
+                    last = i == len(col.up) - 1
+                    xcol, b = self.residual_block(ops, rb, xcol, logits_out=logits if last else None)
+                    blk_b.append(b)
+                    self.trace.append(('stage%d.col%d.up%d' % (t, col.mode, i), xcol, rb.bn2.C))
+                prob = torch.zeros(n, J, hf, wf, device=dev)
+                ops.append(lambda logits=logits, prob=prob: K._tail_fwd([logits, None, None], True,
+                                                                          prob=[prob, None, None]))
+                lanes.append(ops)
+                lz.append(logits)
+                pr.append(prob)
+                lane_bwd.append((blk_b, perm, len(col.down)))
+            segs.append(('parallel', lanes))
+            self.probs.append(pr)
+            self.logits.append(lz)
+            col_bwd.append(lane_bwd)
+        self.fwd = segs
+        if not training:
+            return
+
+        # ---- backward program
+        bsegs = []
+        self.gin = [[torch.zeros(n, J, hf, wf, device=dev) for _ in range(3)] for _ in range(L.n_stages)]
+        d_next = None
+        for t in range(L.n_stages - 1, -1, -1):
+            if t < L.n_stages - 1:
+                prev, wc = comb[t]
+                bsegs.append(('serial', [self._call(
+                    'mp_combiner_bwd', d_next.data_ptr(), planes(prev), wc.data.data_ptr(), planes(self.gin[t]),
+                    wc.grad.data_ptr(), 1, n, J, hf * wf, cf)]))
+            lanes, dxs = [], []
+            for k in range(3):
+                ops = []
+                blk_b, perm, n_down = col_bwd[t][k]
+                prob, g_in = self.probs[t][k], self.gin[t][k]
+                dlogits = torch.zeros(n, J, hf, wf, device=dev)
+                ops.append(lambda prob=prob, g_in=g_in, dlogits=dlogits: K._tail_bwd(
+                    [prob, None, None], [g_in, None, None], [dlogits, None, None], project=True))
+                d = None
+                for i in range(len(blk_b) - 1, -1, -1):
+                    if i == len(blk_b) - 1:
+                        d = blk_b[i](ops, dout_nchw=dlogits)
+                    else:
+                        d = blk_b[i](ops, dout=d)
+                    if perm is not None and i == n_down:
+                        mode, s, cmid, shp = perm
+                        dp = self.act(*shp)
+                        ops.append(self._call('mp_axis_permute', d.data_ptr(), dp.data_ptr(), mode, n, s, cmid,
+                                              shp[-1]))
+                        d = dp
+                lanes.append(ops)
+                dxs.append(d)
+            bsegs.append(('parallel', lanes))
+            d_inp = self.act(*inps[t].shape)
+            terms = dxs + ([d_next] if d_next is not None else [])
+            arr = (ctypes.c_void_p * 4)(*([x.data_ptr() for x in terms] + [None] * (4 - len(terms))))
+            bsegs.append(('serial', [self._call('mp_add_bf16', ctypes.byref(arr), len(terms), d_inp.data_ptr(),
+                                                d_inp.numel())]))
+            self._bufs.append(arr)
+            d_next = d_inp
+        # ---- stem backward
+        ops = []
+        d = d_next
+        if L.adapter is not None:
+            conva, bna = L.adapter
+            dya = self.act(*ya.shape)
+            self.bn_bwd(ops, fa, dout=d, dya=dya)
+            ops += self.conv_ops(lambda: C.conv_wgrad(conva.g, x_pre, dya, conva.w.grad))
+            d = self.act(*x_pre.shape)
+            ops += self.conv_ops(lambda: C.conv_dgrad(conva.g, dya, conva.bwd.t, d))
+        for i in range(len(res_bwd) - 1, -1, -1):
+            d = res_bwd[i](ops, d, need_dx=True)
+        da0 = self.act(*a0.shape)
+        ops.append(self._call('mp_maxpool_bwd', d.data_ptr(), idx.data_ptr(), da0.data_ptr(), n, h // 2, w // 2, c0))
+        dy0 = self.act(*y0.shape)
+        self.bn_bwd(ops, f0, dout=da0, dya=dy0)
+        ops += self.conv_ops(lambda: C.conv_wgrad(conv0.g, patches, dy0, conv0.w.grad))
+        bsegs.append(('serial', ops))
+        self.bwd = bsegs
+
+    # ---- execution
+    def _run(self, segs):
+        cur = torch.cuda.current_stream(self.device)
+        for kind, body in segs:
+            if kind == 'serial':
+                for op in body:
+                    op()
+            else:
+                for s, ops in zip(self.streams, body):
+                    s.wait_stream(cur)
+                    with torch.cuda.stream(s):
+                        for op in ops:
+                            op()
+                for s in self.streams:
+                    cur.wait_stream(s)
+
+    def launches(self, segs=None):
+        out = 0
+        for prog in ([self.fwd, self.bwd] if segs is None else [segs]):
+            for kind, body in prog:
+                out += len(body) if kind == 'serial' else sum(len(o) for o in body)
+        return out
+
+    def forward(self, x):
+        """x: fp32 (N, 3, H, W) on the device.  Returns probs[t][k], fp32 (N, J, h, w)."""
+        self.x_in.copy_(x)
+        if self.training:
+            self.stats.zero_()
+            self.bank.flat_cnt.add_(1)
+        self._run(self.fwd)
+        return self.probs
+
+    def backward(self, grads):
+        """grads[t][k]: fp32 (N, J, h, w) gradient w.r.t. the stage-t plane-k heatmap, or None."""
+        for t, row in enumerate(self.gin):
+            for k, g in enumerate(row):
+                if grads[t][k] is None:
+                    g.zero_()
+                else:
+                    g.copy_(grads[t][k])
+        self._run(self.bwd)

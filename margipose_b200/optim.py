@@ -1,0 +1,51 @@
+"""Flat SGD for the B200 engine: torch.optim.SGD semantics (the optimiser the reference trains
+with, /root/reference/src/margipose/bin/train_3d.py:338-340 + train_helpers.py:70-75) as ONE
+kernel launch over the flat parameter / gradient buffers instead of ~1100 per-tensor updates.
+
+It is a torch.optim.Optimizer, so LR / momentum schedulers that write `param_groups[i][name]`
+(the reference's 1-cycle HyperparameterScheduler, hyperparam_scheduler.py:24-42) keep working.
+"""
+import torch
+
+from . import ops
+
+
+class FlatSGD(torch.optim.Optimizer):
+    def __init__(self, model, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False):
+        if nesterov and (momentum <= 0 or dampening != 0):
+            raise ValueError('Nesterov momentum requires a momentum and zero dampening')
+        device = next(model.parameters()).device
+        if device.type != 'cuda':
+            raise ValueError('FlatSGD needs the model on a CUDA device (call model.cuda() first)')
+        model._ensure(device)
+        self.model = model
+        self.bank = model._bank
+        defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay,
+                        nesterov=nesterov)
+        super().__init__(list(model.parameters()), defaults)
+        self.momentum_buf = torch.zeros_like(self.bank.flat)
+        self._steps = 0
+        self.grad_scale = 1.0     # e.g. 1 / world_size after a summing all-reduce
+
+    def zero_grad(self, set_to_none=False):
+        self.bank.flat_grad.zero_()
+        if set_to_none:
+            for s in self.bank.params:
+                getattr(s.mod, s.name).grad = None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        if self.bank is not self.model._bank:
+            raise RuntimeError('the model was re-materialised (moved / re-created) after this optimiser '
+                               'was built; create the optimiser after model.cuda()')
+        g = self.param_groups[0]
+        ops.sgd_step(self.bank.flat, self.bank.flat_grad, self.momentum_buf, g['lr'], g['momentum'],
+                     g['dampening'], g['weight_decay'], g['nesterov'], first_step=(self._steps == 0),
+                     grad_scale=self.grad_scale)
+        self._steps += 1
+        self.model.mark_params_dirty()
+        return loss

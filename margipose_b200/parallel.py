@@ -1,0 +1,52 @@
+"""Data parallelism for the MargiPose hot path: one process per GPU, batch sharded across ranks,
+ONE gradient all-reduce per step over the flat gradient buffer.
+
+The reference has no multi-GPU path (single `--device`, /root/reference/src/margipose/cli.py:11);
+BatchNorm statistics stay per replica, as torch DistributedDataParallel would leave them.
+Collectives go through torch.distributed (NCCL over NVLink on the GPU box, gloo in CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_batch(global_batch, rank=None, world_size=None):
+    """Contiguous, near-equal shard [lo, hi) of a global batch for this rank."""
+    if rank is None:
+        rank, world_size = world()
+    base, extra = divmod(global_batch, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def broadcast_flat(tensors, src=0):
+    """Rank `src`'s flat buffers (parameters, BatchNorm buffers) to everyone, at start-up."""
+    _, ws = world()
+    if ws > 1:
+        for t in tensors:
+            dist.broadcast(t, src)
+
+
+def allreduce_mean_(flat_grad, extra=None):
+    """In-place mean of the flat gradient buffer across ranks: one collective for the step.
+    `extra` (optional small tensor, e.g. a loss / mask-count pair) is summed alongside."""
+    _, ws = world()
+    if ws == 1:
+        return flat_grad
+    dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+    flat_grad.mul_(1.0 / ws)
+    if extra is not None:
+        dist.all_reduce(extra, op=dist.ReduceOp.SUM)
+    return flat_grad
+
+
+def sync_model(model, src=0):
+    """Makes every replica start from rank `src`'s weights and buffers."""
+    bank = model._bank
+    broadcast_flat([bank.flat, bank.flat_buf, bank.flat_cnt], src)
+    model.mark_params_dirty()

@@ -39,6 +39,12 @@ class _Numerics:
 
     def __init__(self, emulate_bf16):
         self.emulate = emulate_bf16
+        self.trace = None      # set to a list to record every block output (layer-wise parity)
+
+    def rec(self, x):
+        if self.trace is not None:
+            self.trace.append(x.detach())
+        return x
 
     def q(self, x):
         return _bf16(x) if self.emulate else x
@@ -100,7 +106,7 @@ class ResidualBlock(nn.Module):
         main = F.relu(nm.bn(self.module[4], nm.conv(self.module[3], a)))
         short = nm.bn(self.shortcut[1], nm.conv(self.shortcut[0], x))
         out = main + short
-        return out if keep_fp32 else nm.q(out)
+        return nm.rec(out if keep_fp32 else nm.q(out))
 
 
 def _block(cin, cout, kind):
@@ -185,7 +191,7 @@ class BasicBlock(nn.Module):
             ident = nm.bn(self.downsample[1], nm.conv(self.downsample[0], x))
         else:
             ident = x
-        return nm.q(F.relu(main + ident))
+        return nm.rec(nm.q(F.relu(main + ident)))
 
 
 class Bottleneck(nn.Module):
@@ -215,7 +221,7 @@ class Bottleneck(nn.Module):
             ident = nm.bn(self.downsample[1], nm.conv(self.downsample[0], x))
         else:
             ident = x
-        return nm.q(F.relu(main + ident))
+        return nm.rec(nm.q(F.relu(main + ident)))
 
 
 _RESNETS = {  # name -> (block, layer1 count, layer2 count, layer2 output channels)
@@ -261,14 +267,14 @@ def make_image_feature_extractor(model_name):
 
 def run_feature_extractor(nm, net, x):
     x = nm.q(x)
-    x = nm.q(F.relu(nm.bn(net[1], nm.conv(net[0], x))))
-    x = net[3](x)
+    x = nm.rec(nm.q(F.relu(nm.bn(net[1], nm.conv(net[0], x)))))
+    x = nm.rec(net[3](x))
     for blk in net[4]:
         x = blk.run(nm, x)
     for blk in net[5]:
         x = blk.run(nm, x)
     if len(net) > 6:
-        x = nm.q(F.relu(nm.bn(net[7], nm.conv(net[6], x))))
+        x = nm.rec(nm.q(F.relu(nm.bn(net[7], nm.conv(net[6], x)))))
     return x
 
 

@@ -57,6 +57,7 @@ CASES = [  # cin, cout, k, stride, transposed, n, h, w
     (128, 192, 3, 2, False, 1, 48, 48),
     (192, 128, 3, 2, True, 1, 24, 24),
     (256, 512, 1, 1, False, 1, 16, 16),
+    (512, 128, 1, 1, False, 1, 16, 16),
     (64, 64, 3, 1, False, 1, 96, 96),
 ]
 
