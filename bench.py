@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Benchmark of the MargiPose training hot path on B200 (BASELINE.json metric: images/sec fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- 4-stage ResNet-34 MargiPose, 256x256,
+17 joints, batch 32 per GPU, one training step = forward + forward_3d_losses/average_loss +
+backward (+ one gradient all-reduce when N > 1) + SGD-momentum update, synthetic images/targets,
+seeded random-init weights (no network for datasets / checkpoints).
+
+  value : steps run from device-resident inputs (CUDA events, max over ranks)
+  e2e   : the same step through the public API (margipose_b200.train.TrainStep.__call__) fed from
+          pinned HOST buffers each step, loss read back to the host each step
+  roofline : the tcgen05 implicit-GEMM conv kernel (mp_conv_igemm: fprop + dgrad launches of
+          one step), algorithmic FLOPs / CUDA-event time per launch vs the measured bf16 peak
+  cpu_baseline / --impl reference : the reference algorithm's CPU path (the fp32 oracle port
+          of /root/reference/src/margipose, the unmodified reference cannot travel to the GPU box)
+          on the host cores, on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DESC = {'type': 'margipose', 'version': '6.0.1',
+        'settings': {'n_stages': 4, 'axis_permutation': True, 'feature_extractor': 'resnet34',
+                     'pixelwise_loss': 'jsd'}}
+RES, JOINTS = 256, 17
+FLOPS_PER_IMAGE = 161.35e9      # conv fwd+bwd, SURVEY.md section 6 (FlopCounterMode on the reference)
+METRIC = 'images/sec fwd+bwd (4-stage ResNet-34 MargiPose, 256x256, 17 joints)'
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p.get('bf16_tflops_sustained', 1415.1), p.get('hbm_gbs', 6449.1), 'measured'
+    return 1400.0, 6650.0, 'fallback'
+
+
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.path = tempfile.mktemp(suffix='.csv')
+        self.proc = None
+
+    def start(self):
+        try:
+            self.f = open(self.path, 'w')
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        self.proc.wait()
+        self.f.close()
+        sm, mx, reasons = [], 0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx = max(mx, float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def synthetic(batch, n_sets, seed, device=None, pinned=False):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    sets = []
+    for _ in range(n_sets):
+        x = torch.randn(batch, 3, RES, RES, generator=g)
+        t = torch.rand(batch, JOINTS, 3, generator=g) * 1.6 - 0.8
+        m = torch.ones(batch, JOINTS)
+        if pinned:
+            x, t, m = x.pin_memory(), t.pin_memory(), m.pin_memory()
+        elif device is not None:
+            x, t, m = x.to(device), t.to(device), m.to(device)
+        sets.append((x, t, m))
+    return sets
+
+
+# ------------------------------------------------------------------------------ CPU reference
+def cpu_reference(batch, steps, warmup, budget_s):
+    """fwd + loss + bwd + SGD of the reference algorithm on the host cores (fp32 oracle port)."""
+    import torch
+    from oracle import model_oracle as M
+    from oracle import dsnt_oracle as D
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    om = M.create_oracle(DESC).train()
+    opt = torch.optim.SGD(om.parameters(), lr=1e-3, momentum=0.9)
+    data = synthetic(batch, 2, seed=1)
+    times = []
+    t_begin = time.perf_counter()
+    done = 0
+    for i in range(warmup + steps):
+        x, t, m = data[i % len(data)]
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        out = om(x)
+        loss = D.average_loss(om.forward_3d_losses(out, t), m)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+            done += 1
+        if i >= warmup and time.perf_counter() - t_begin > budget_s:
+            break
+    total = sum(times)
+    return {'value': batch * done / total, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '%d step(s) of batch %d (fwd+loss+bwd+SGD) after %d warm-up, fp32 oracle port of the '
+                      'reference on CPU' % (done, batch, warmup),
+            'steps': done, 'ms_per_step': 1e3 * total / max(done, 1)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    base = cpu_reference(batch=4, steps=max(1, args.steps), warmup=1, budget_s=150.0)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'images/s', 'n_gpus': args.gpus,
+            'steps': base['steps'], 'warmup': 1, 'ms_per_step': base['ms_per_step'], 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'configs[1]: 4-stage ResNet-34 MargiPose 256x256 17 joints, training step; '
+                                   'CPU sample of batch 4 per step'},
+            'cpu_baseline': {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'e2e': {'value': base['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from margipose_b200.models import create_model
+    from margipose_b200.optim import FlatSGD
+    from margipose_b200.train import TrainStep
+    from margipose_b200 import parallel
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    torch.manual_seed(0)
+    model = create_model(DESC).to(dev).train()
+    opt = FlatSGD(model, lr=1e-3, momentum=0.9)
+    if world > 1:
+        parallel.sync_model(model)
+    step = TrainStep(model, opt, batch=B, height=RES, width=RES, use_graph=not args.no_graph)
+    dev_sets = synthetic(B, 4, seed=100 + rank, device=dev)
+    host_sets = synthetic(B, 2, seed=200 + rank, pinned=True)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # warm-up: >= W steps, and enough for the CUDA graph to be captured and replayed once
+    for i in range(max(W, step.warmup + 2)):
+        step.load(*dev_sets[i % len(dev_sets)])
+        step.run()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        step.load(*dev_sets[i % len(dev_sets)])
+        step.run()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+
+    # end to end: pinned host inputs every step, loss read back every step
+    for i in range(2):
+        step(*host_sets[i % len(host_sets)])
+    barrier()
+    t0 = time.perf_counter()
+    last = None
+    for i in range(K):
+        last = step(*host_sets[i % len(host_sets)])
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = e2e_s.item()
+    h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
+    d2h = 4
+
+    # roofline of the dominant kernel: every mp_conv_igemm launch of one step, timed alone
+    roof = None
+    if rank == 0:
+        eng = model.engine_for(B, RES, RES, True)
+        eng.stats.zero_()
+        stats = eng.time_ops(eng.fwd)
+        for name, rec in eng.time_ops(eng.bwd).items():
+            r = stats.setdefault(name, [0, 0.0, 0.0])
+            r[0] += rec[0]; r[1] += rec[1]; r[2] += rec[2]
+        torch.cuda.synchronize(dev)
+        peak_tf, peak_bw, src = peaks()
+        n, t_ms, fl = stats['mp_conv_igemm']
+        achieved = fl / (t_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'igemm_traffic.json')
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get('dram_bytes_per_launch')
+        roof = {'bound': 'tensor', 'kernel': 'igemm_kernel (mp_conv_igemm, fprop+dgrad)', 'achieved': achieved,
+                'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': traffic,
+                'peak_source': src + ' bf16 sustained', 'launches_per_step': n,
+                'avg_launch_us': 1e3 * t_ms / n, 'flops_per_launch': fl / n,
+                'kernel_time_share': {k: v[1] for k, v in stats.items()},
+                'wgrad_tflops': (stats['mp_conv_wgrad'][2] / (stats['mp_conv_wgrad'][1] * 1e-3) / 1e12)
+                if 'mp_conv_wgrad' in stats else None}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.skip_cpu:
+        cpu = cpu_reference(batch=4, steps=2, warmup=1, budget_s=60.0)
+        cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+    value = B * world * K / (ms * 1e-3)
+    line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'configs[1]: 4-stage ResNet-34 MargiPose, 256x256, 17 joints, batch %d per GPU, '
+                                   'fwd + 3D loss + bwd + SGD-momentum step' % B,
+                       'global_batch': B * world, 'parallelism': 'dp%d' % world,
+                       'cuda_graph': not args.no_graph,
+                       'l2': 'per-step working set (~10 GB of activations) exceeds the 126 MB L2; 4 input sets rotate'},
+            'conv_flops_per_image': FLOPS_PER_IMAGE,
+            'conv_tflops_whole_step': value / world * FLOPS_PER_IMAGE / 1e12,
+            'roofline': roof, 'cpu_baseline': cpu,
+            'e2e': {'value': B * world * K / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'last_loss': last},
+            'gpu_launches': step.launches_per_step() * K * 2, 'clocks': clocks}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=32, help='images per GPU per step')
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--skip-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

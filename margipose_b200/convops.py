@@ -128,7 +128,13 @@ def _igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out
     a.out_c = out_c
     if stats is not None:
         a.stat_sum, a.stat_sq = stats[0].data_ptr(), stats[1].data_ptr()
+    a._flops = 2.0 * n_img * out_h * out_w * len(taps) * _FLOP_CHANNELS[0]
     _igemm_launch(a, out.device)
+
+
+# real (unpadded) cin*cout of the layer being launched; set by conv_forward / conv_dgrad so the
+# per-launch algorithmic FLOP count ignores channel padding
+_FLOP_CHANNELS = [0]
 
 
 def _igemm_launch(a, device):
@@ -151,6 +157,7 @@ def _wgrad(a_t, b_t, b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, gri
         a.n_cols, a.n_off = min(256, n_cols - n_off), n_off
         a.n_img, a.grid_h, a.grid_w = n_img, grid_h, grid_w
         a.dw = dw.data_ptr()
+        a._flops = 2.0 * n_img * grid_h * grid_w * len(taps) * m_real * min(a.n_cols, n_real - n_off)
         if n_off < n_real:
             _wgrad_launch(a, dw.device)
 
@@ -179,6 +186,7 @@ def conv_forward(g, x, wpack, out, stats=None, res=None):
     ho, wo = g.out_hw(h, w)
     assert tuple(out.shape) == (n, ho, wo, g.cout_p) and tuple(wpack.shape) == g.fwd_pack_shape()
     cb = g.cin_p // 64
+    _FLOP_CHANNELS[0] = g.cin * g.cout
     if not g.transposed:
         if g.stride == 1:
             taps, src = _s1_taps(g.k, g.cin_p, +1), (x, False)
@@ -219,6 +227,7 @@ def conv_dgrad(g, dy, wpack_bwd, dx, res=None, second=None):
     shortcut); wpack_bwd then holds both layers' bwd packs side by side along K."""
     n, ho, wo, _ = dy.shape
     cb = g.cout_p // 64
+    _FLOP_CHANNELS[0] = g.cin * g.cout
     if second is not None:
         g2, dy2, koff0 = second
         assert g2.cout_p == g.cout_p and g2.cin_p == g.cin_p and g2.stride == g.stride and \

@@ -335,6 +335,7 @@ class Engine:
                 check(rc, fn_name)
         op.args = args
         op.name = fn_name
+        op.flops = getattr(args, '_flops', 0.0)
         return op
 
     def conv_ops(self, record):
@@ -665,6 +666,30 @@ class Engine:
                             op()
                 for s in self.streams:
                     cur.wait_stream(s)
+
+    def time_ops(self, segs):
+        """Runs `segs` serially on the current stream with a CUDA event pair around every op and
+        returns {kernel name: [launches, total ms, total algorithmic flops]} -- the per-kernel
+        durations bench.py's roofline uses (lanes are NOT overlapped here, so each duration is
+        that kernel alone on the GPU)."""
+        ops = []
+        for kind, body in segs:
+            for lane in ([body] if kind == 'serial' else body):
+                ops += lane
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops]
+        for op, (e0, e1) in zip(ops, evs):
+            e0.record()
+            op()
+            e1.record()
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for op, (e0, e1) in zip(ops, evs):
+            name = getattr(op, 'name', 'tail')
+            rec = out.setdefault(name, [0, 0.0, 0.0])
+            rec[0] += 1
+            rec[1] += e0.elapsed_time(e1)
+            rec[2] += getattr(op, 'flops', 0.0)
+        return out
 
     def launches(self, segs=None):
         out = 0

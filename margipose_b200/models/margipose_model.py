@@ -305,7 +305,12 @@ class MargiPoseModel(nn.Module):
         eng = self.engine_for(x.size(0), x.size(2), x.size(3), self.training)
         self._refresh_packs()
         if self.training and torch.is_grad_enabled():
-            flat = _Body.apply(eng, x, self.inner.in_cnn[0].weight)
+            # A fresh leaf ties the node into the autograd graph.  (Using a long-lived Parameter here
+            # would pin the node's leaf stream to whichever stream first used that Parameter -- usually
+            # the legacy default stream -- which autograd then touches at the end of backward and
+            # thereby invalidates a CUDA-graph capture of the training step.)
+            anchor = torch.empty(0, device=x.device, requires_grad=True)
+            flat = _Body.apply(eng, x, anchor)
         else:
             flat = [p for row in eng.forward(x) for p in row]
         n = len(flat) // 3
