@@ -131,7 +131,8 @@ typedef struct mp_tap {
  * out + n*out_sn + h*out_sh + w*out_sw (elements; lets a transposed conv scatter one output
  * parity class per launch); out_c channels are stored (multiple of 8).  When stat_sum/stat_sq are
  * given, the per-channel sum and sum of squares of the stored (bf16-rounded) values are
- * atomically added to them -- the BatchNorm batch statistics of nn.BatchNorm2d in train mode. */
+ * atomically added to them -- the BatchNorm batch statistics of nn.BatchNorm2d in train mode
+ * (optionally spread over stat_replicas copies that the BatchNorm kernels add up). */
 typedef struct mp_igemm_args {
   mp_view5 src[2];
   const void* wmat;
@@ -146,6 +147,8 @@ typedef struct mp_igemm_args {
   int32_t out_c;
   float* stat_sum;
   float* stat_sq;
+  int32_t stat_replicas;           /* >= 1: CTA b adds into replica (b % stat_replicas) ...          */
+  int64_t stat_stride;             /* ... at stat_sum/stat_sq + replica * stat_stride (spreads atomics) */
 } mp_igemm_args;
 
 MP_API int mp_conv_igemm(const mp_igemm_args* args, void* stream);
@@ -207,7 +210,9 @@ typedef struct mp_bn_args {
   const void* dout;         /* backward: bf16 (M, Cp) gradient w.r.t. out, or NULL */
   const float* dout_nchw;   /* backward: fp32 (N, C, HW) gradient w.r.t. out_nchw, or NULL */
   void* dres;               /* backward: bf16 (M, Cp) gradient w.r.t. res, or NULL */
-  float* sums;              /* backward workspace (4, Cp): zero before mp_bn_bwd_reduce */
+  float* sums;              /* backward workspace (stat_replicas, 4, Cp): zero before mp_bn_bwd_reduce */
+  int32_t stat_replicas;    /* >= 1: number of copies of sum / sq / sums the producers spread their atomics over */
+  int64_t stat_stride;      /* elements between copies of sum / sq (copies of sums are 4*Cp apart) */
   int64_t M;
   int32_t C, Cp, HW;
   int32_t training;

@@ -35,7 +35,8 @@ class IgemmArgs(ctypes.Structure):
                 ('cblocks', ctypes.c_int32), ('n_img', ctypes.c_int32), ('out_h', ctypes.c_int32),
                 ('out_w', ctypes.c_int32), ('out', c_void_p), ('res', c_void_p),
                 ('out_sn', ctypes.c_int64), ('out_sh', ctypes.c_int64), ('out_sw', ctypes.c_int64),
-                ('out_c', ctypes.c_int32), ('stat_sum', c_void_p), ('stat_sq', c_void_p)]
+                ('out_c', ctypes.c_int32), ('stat_sum', c_void_p), ('stat_sq', c_void_p),
+                ('stat_replicas', ctypes.c_int32), ('stat_stride', ctypes.c_int64)]
 
 
 class WgradArgs(ctypes.Structure):
@@ -55,6 +56,7 @@ class BnArgs(ctypes.Structure):
     _fields_ = [('a', BnBranch), ('b', BnBranch), ('res', c_void_p), ('relu_a', ctypes.c_int32),
                 ('relu_out', ctypes.c_int32), ('out', c_void_p), ('out_nchw', c_void_p),
                 ('dout', c_void_p), ('dout_nchw', c_void_p), ('dres', c_void_p), ('sums', c_void_p),
+                ('stat_replicas', ctypes.c_int32), ('stat_stride', ctypes.c_int64),
                 ('M', ctypes.c_int64), ('C', ctypes.c_int32), ('Cp', ctypes.c_int32),
                 ('HW', ctypes.c_int32), ('training', ctypes.c_int32), ('momentum', ctypes.c_float),
                 ('eps', ctypes.c_float)]

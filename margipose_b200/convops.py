@@ -128,6 +128,7 @@ def _igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out
     a.out_c = out_c
     if stats is not None:
         a.stat_sum, a.stat_sq = stats[0].data_ptr(), stats[1].data_ptr()
+        a.stat_replicas, a.stat_stride = (stats[2], stats[3]) if len(stats) > 2 else (1, 0)
     a._flops = 2.0 * n_img * out_h * out_w * len(taps) * _FLOP_CHANNELS[0]
     _igemm_launch(a, out.device)
 
@@ -181,7 +182,8 @@ def _s1_taps(k, k_stride, sign, src=0, koff0=0):
 
 def conv_forward(g, x, wpack, out, stats=None, res=None):
     """y = conv(x) (or conv_transpose(x)); x (N,H,W,cin_p), out (N,Ho,Wo,cout_p), both bf16 NHWC.
-    stats = (sum, sumsq) fp32 (cout_p) accumulators for the BatchNorm batch statistics."""
+    stats = (sum, sumsq[, replicas, stride]) fp32 (cout_p) accumulators for the BatchNorm batch
+    statistics (optionally `replicas` copies `stride` floats apart to spread the atomics)."""
     n, h, w, _ = x.shape
     ho, wo = g.out_hw(h, w)
     assert tuple(out.shape) == (n, ho, wo, g.cout_p) and tuple(wpack.shape) == g.fwd_pack_shape()

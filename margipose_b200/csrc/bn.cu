@@ -2,290 +2,366 @@
 //
 // Replaces nn.BatchNorm2d / nn.ReLU / the residual `+` of ResidualBlock
 // (/root/reference/src/margipose/models/margipose_model.py:31-40) and of the torchvision ResNet
-// blocks (:130-135), and their autograd.  HBM-bound elementwise work: every tensor is touched once
-// per pass with 128-bit loads/stores (8 bf16 channels per thread); the batch statistics arrive
-// pre-reduced from the conv epilogue (igemm.cu), so the forward is a single pass.  Algorithmic
-// bytes per pixel-channel: forward 2 per input tensor + 2 out; backward reduce 2 per tensor read,
-// apply 2 per tensor read + 2 per gradient written.
+// blocks (:130-135), and their autograd.  HBM/L2-bound elementwise work: every tensor is touched
+// once per pass with 128-bit loads/stores (8 bf16 channels per thread, U pixels in flight per
+// thread); the batch statistics arrive pre-reduced from the conv epilogue (igemm.cu), so the forward
+// is a single pass.  The backward is two passes (per-channel reductions, then the gradient), the
+// minimum for training-mode BatchNorm.  Algorithmic bytes per pixel-channel: forward 2 per input
+// tensor + 2 out; backward reduce 2 per tensor read; apply 2 per tensor read + 2 per gradient.
 #include "common.cuh"
 #include "../../include/margipose_b200.h"
 
 namespace {
 
 constexpr int MAXT = 256;
+constexpr int U = 4;    // pixels in flight per thread (forward, backward reduce)
+constexpr int UA = 2;   // ... in the backward apply pass (more coefficients live)
 
-struct Chan8 {
-  float v[8];
-};
-
-__device__ __forceinline__ Chan8 load8(const __nv_bfloat16* p) {
-  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
-  Chan8 r;
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
   float2 f;
-  f = unpack_bf16x2(u.x); r.v[0] = f.x; r.v[1] = f.y;
-  f = unpack_bf16x2(u.y); r.v[2] = f.x; r.v[3] = f.y;
-  f = unpack_bf16x2(u.z); r.v[4] = f.x; r.v[5] = f.y;
-  f = unpack_bf16x2(u.w); r.v[6] = f.x; r.v[7] = f.y;
-  return r;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
 }
-__device__ __forceinline__ void store8(__nv_bfloat16* p, const Chan8& r) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(r.v[0], r.v[1]), pack_bf16x2(r.v[2], r.v[3]),
-                                            pack_bf16x2(r.v[4], r.v[5]), pack_bf16x2(r.v[6], r.v[7]));
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                    pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ uint4 ldg16(const void* base, long long elem_off) {
+  return __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off));
 }
 
-// Per-thread BatchNorm coefficients of 8 consecutive channels.
-struct Coef {
-  float scale[8], shift[8], mean[8], invstd[8];
-};
+constexpr int MAXR = 8;   // replicas summed with all loads in flight (more fall back to a loop)
 
-// Forward: statistics from the conv epilogue sums (training) or the running buffers (eval).
-__device__ __forceinline__ void coef_fwd(const mp_bn_branch& br, int c0, int C, long long M, int training,
-                                         float eps, Coef& k) {
+// Sum over replicas of 8 consecutive channels of a per-channel statistic: 2 x 128-bit loads per
+// replica, all issued before the first add (one L2 round trip instead of a dependent chain).
+__device__ __forceinline__ void rsum8(const float* p, int c0, int replicas, long long stride, float (&out)[8]) {
+  float4 lo[MAXR], hi[MAXR];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = c0 + i;
-    float mean = 0.f, invstd = 0.f, g = 0.f, b = 0.f;
-    if (c < C) {
-      if (training) {
-        const float inv_m = 1.0f / (float)M;
-        mean = br.sum[c] * inv_m;
-        const float var = fmaxf(br.sq[c] * inv_m - mean * mean, 0.f);
-        invstd = rsqrtf(var + eps);
-      } else {
-        mean = br.running_mean[c] - (br.conv_bias ? br.conv_bias[c] : 0.f);
-        invstd = rsqrtf(br.running_var[c] + eps);
-      }
-      g = br.gamma[c];
-      b = br.beta[c];
+  for (int r = 0; r < MAXR; ++r) {
+    if (r < replicas) {
+      const float4* q = reinterpret_cast<const float4*>(p + (long long)r * stride + c0);
+      lo[r] = __ldg(q);
+      hi[r] = __ldg(q + 1);
     }
-    k.mean[i] = mean;
-    k.invstd[i] = invstd;
-    k.scale[i] = g * invstd;
-    k.shift[i] = fmaf(-mean, k.scale[i], b);
   }
-}
-// Backward: the same coefficients, from the saved mean / invstd (bitwise equal to the forward's).
-__device__ __forceinline__ void coef_bwd(const mp_bn_branch& br, int c0, int C, Coef& k) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = c0 + i;
-    float mean = 0.f, invstd = 0.f, g = 0.f, b = 0.f;
-    if (c < C) {
-      mean = br.save_mean[c];
-      invstd = br.save_invstd[c];
-      g = br.gamma[c];
-      b = br.beta[c];
+  for (int j = 0; j < 8; ++j) out[j] = 0.f;
+#pragma unroll
+  for (int r = 0; r < MAXR; ++r) {
+    if (r < replicas) {
+      out[0] += lo[r].x; out[1] += lo[r].y; out[2] += lo[r].z; out[3] += lo[r].w;
+      out[4] += hi[r].x; out[5] += hi[r].y; out[6] += hi[r].z; out[7] += hi[r].w;
     }
-    k.mean[i] = mean;
-    k.invstd[i] = invstd;
-    k.scale[i] = g * invstd;
-    k.shift[i] = fmaf(-mean, k.scale[i], b);
   }
+  for (int r = MAXR; r < replicas; ++r)
+    for (int j = 0; j < 8; ++j) out[j] += p[(long long)r * stride + c0 + j];
 }
 
-// blockDim = (Cp/8 channel groups, PY pixel rows); each block walks `ppb` consecutive pixels.
-__global__ void __launch_bounds__(MAXT) bn_fwd_kernel(const mp_bn_args A, int ppb) {
-  const int cg = threadIdx.x, c0 = cg * 8;
-  const bool has_b = A.b.y != nullptr;
-  Coef ka, kb;
-  coef_fwd(A.a, c0, A.C, A.M, A.training, A.eps, ka);
-  if (has_b) coef_fwd(A.b, c0, A.C, A.M, A.training, A.eps, kb);
-
-  if (blockIdx.x == 0 && threadIdx.y == 0) {   // bookkeeping: saved statistics + running buffers
+// mean / invstd / biased variance of 8 channels: forward from the conv-epilogue sums (training) or
+// the running buffers (eval); backward from what the forward saved (bitwise the same numbers).
+__device__ __forceinline__ void channel_stats8(const mp_bn_args& A, const mp_bn_branch& br, int c0, bool from_saved,
+                                               float (&mean)[8], float (&invstd)[8], float (&var)[8]) {
+  if (!from_saved && A.training) {
+    float s1[8], s2[8];
+    rsum8(br.sum, c0, A.stat_replicas, A.stat_stride, s1);
+    rsum8(br.sq, c0, A.stat_replicas, A.stat_stride, s2);
+    const float inv_m = 1.0f / (float)A.M;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
-      if (c >= A.C) continue;
-      for (int which = 0; which < (has_b ? 2 : 1); ++which) {
-        const mp_bn_branch& br = which ? A.b : A.a;
-        const Coef& k = which ? kb : ka;
+      mean[i] = s1[i] * inv_m;
+      var[i] = fmaxf(s2[i] * inv_m - mean[i] * mean[i], 0.f);
+      invstd[i] = rsqrtf(var[i] + A.eps);
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    mean[i] = invstd[i] = var[i] = 0.f;
+    if (c >= A.C) continue;
+    if (from_saved) {
+      mean[i] = br.save_mean[c];
+      invstd[i] = br.save_invstd[c];
+    } else {
+      mean[i] = br.running_mean[c] - (br.conv_bias ? br.conv_bias[c] : 0.f);
+      invstd[i] = rsqrtf(br.running_var[c] + A.eps);
+    }
+  }
+}
+
+__device__ __forceinline__ void affine(const mp_bn_args& A, const mp_bn_branch& br, int c0, bool from_saved,
+                                       float (&scale)[8], float (&shift)[8]) {
+  float mean[8], invstd[8], var[8];
+  channel_stats8(A, br, c0, from_saved, mean, invstd, var);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    scale[i] = 0.f;
+    shift[i] = 0.f;
+    if (c < A.C) {
+      scale[i] = br.gamma[c] * invstd[i];
+      shift[i] = fmaf(-mean[i], scale[i], br.beta[c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const mp_bn_args A) {
+  const int c0 = threadIdx.x * 8;
+  const bool has_b = A.b.y != nullptr;
+  float sa[8], ha[8], sb[8], hb[8];
+  affine(A, A.a, c0, false, sa, ha);
+  if (has_b) affine(A, A.b, c0, false, sb, hb);
+
+  if (blockIdx.x == 0 && threadIdx.y == 0) {   // bookkeeping: saved statistics + running buffers
+    for (int which = 0; which < (has_b ? 2 : 1); ++which) {
+      const mp_bn_branch& br = which ? A.b : A.a;
+      float mean[8], invstd[8], var[8];
+      channel_stats8(A, br, c0, false, mean, invstd, var);
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        if (c >= A.C) continue;
         if (br.save_mean) {
-          br.save_mean[c] = k.mean[i];
-          br.save_invstd[c] = k.invstd[i];
+          br.save_mean[c] = mean[i];
+          br.save_invstd[c] = invstd[i];
         }
         if (A.training && br.running_mean) {
-          const float inv_m = 1.0f / (float)A.M;
-          const float var = fmaxf(br.sq[c] * inv_m - k.mean[i] * k.mean[i], 0.f);
-          const float unbiased = A.M > 1 ? var * ((float)A.M / (float)(A.M - 1)) : var;
+          const float unbiased = A.M > 1 ? var[i] * ((float)A.M / (float)(A.M - 1)) : var[i];
           const float bias = br.conv_bias ? br.conv_bias[c] : 0.f;
-          br.running_mean[c] = (1.f - A.momentum) * br.running_mean[c] + A.momentum * (k.mean[i] + bias);
+          br.running_mean[c] = (1.f - A.momentum) * br.running_mean[c] + A.momentum * (mean[i] + bias);
           br.running_var[c] = (1.f - A.momentum) * br.running_var[c] + A.momentum * unbiased;
         }
       }
     }
   }
 
-  const __nv_bfloat16* ya = reinterpret_cast<const __nv_bfloat16*>(A.a.y);
-  const __nv_bfloat16* yb = reinterpret_cast<const __nv_bfloat16*>(A.b.y);
-  const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(A.res);
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(A.out);
-  const long long p0 = (long long)blockIdx.x * ppb;
-  for (int i = threadIdx.y; i < ppb; i += blockDim.y) {
-    const long long pix = p0 + i;
+  const long long p0 = (long long)blockIdx.x * (blockDim.y * U) + threadIdx.y;
+  uint4 la[U], lb[U];
+#pragma unroll
+  for (int i = 0; i < U; ++i) {
+    const long long pix = p0 + (long long)i * blockDim.y;
+    if (pix < A.M) {
+      const long long off = pix * A.Cp + c0;
+      la[i] = ldg16(A.a.y, off);
+      if (has_b) lb[i] = ldg16(A.b.y, off);
+      else if (A.res) lb[i] = ldg16(A.res, off);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < U; ++i) {
+    const long long pix = p0 + (long long)i * blockDim.y;
     if (pix >= A.M) break;
     const long long off = pix * A.Cp + c0;
-    Chan8 z = load8(ya + off);
+    float z[8], t[8];
+    unpack8(la[i], z);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      z.v[j] = fmaf(z.v[j], ka.scale[j], ka.shift[j]);
-      if (A.relu_a) z.v[j] = fmaxf(z.v[j], 0.f);
+      z[j] = fmaf(z[j], sa[j], ha[j]);
+      if (A.relu_a) z[j] = fmaxf(z[j], 0.f);
     }
     if (has_b) {
-      const Chan8 t = load8(yb + off);
+      unpack8(lb[i], t);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) z.v[j] += fmaf(t.v[j], kb.scale[j], kb.shift[j]);
-    } else if (res) {
-      const Chan8 t = load8(res + off);
+      for (int j = 0; j < 8; ++j) z[j] += fmaf(t[j], sb[j], hb[j]);
+    } else if (A.res) {
+      unpack8(lb[i], t);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) z.v[j] += t.v[j];
+      for (int j = 0; j < 8; ++j) z[j] += t[j];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (A.relu_out) z.v[j] = fmaxf(z.v[j], 0.f);
-      if (c0 + j >= A.C) z.v[j] = 0.f;
+      if (A.relu_out) z[j] = fmaxf(z[j], 0.f);
+      if (c0 + j >= A.C) z[j] = 0.f;
     }
-    if (out) store8(out + off, z);
+    if (A.out) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.out) + off) = pack8(z);
     if (A.out_nchw) {
       const long long n = pix / A.HW, hw = pix - n * A.HW;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (c0 + j < A.C) A.out_nchw[(n * A.C + c0 + j) * A.HW + hw] = z.v[j];
+        if (c0 + j < A.C) A.out_nchw[(n * A.C + c0 + j) * A.HW + hw] = z[j];
     }
   }
 }
 
-// dz of both branches at one pixel (shared by the reduce and apply passes).
-struct Dz {
-  Chan8 a, b, xa, xb;   // gradients w.r.t. the BN outputs and the normalised inputs x^
+// ------------------------------------------------------------------------------------ backward
+// Gradient w.r.t. the two BN outputs at one pixel: g masked by the post-ReLU (out > 0) and, for
+// branch a, by the pre-ReLU (bn_a(y_a) > 0, recomputed with the forward's exact coefficients).
+// NCHW = the incoming gradient is the fp32 (N, C, HW) logits gradient (last block of a column);
+// its 8 channel values then travel in the two 128-bit slots g / g2 instead of one bf16x8 load.
+struct Loads {
+  uint4 g, o, ya, yb;
+};
+template <bool NCHW>
+struct LoadsX : Loads {};
+template <>
+struct LoadsX<true> : Loads {
+  uint4 g2;
 };
 
-__device__ __forceinline__ void compute_dz(const mp_bn_args& A, const Coef& ka, const Coef& kb, bool has_b,
-                                           long long pix, int c0, Dz& d) {
+template <bool NCHW>
+__device__ __forceinline__ void load_pixel(const mp_bn_args& A, bool has_b, long long pix, int c0, LoadsX<NCHW>& L) {
   const long long off = pix * A.Cp + c0;
-  Chan8 g;
-  if (A.dout) {
-    g = load8(reinterpret_cast<const __nv_bfloat16*>(A.dout) + off);
+  if constexpr (!NCHW) {
+    L.g = ldg16(A.dout, off);
   } else {
     const long long n = pix / A.HW, hw = pix - n * A.HW;
+    float gn[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      g.v[j] = (c0 + j < A.C) ? __ldg(A.dout_nchw + (n * A.C + c0 + j) * A.HW + hw) : 0.f;
+    for (int j = 0; j < 8; ++j) gn[j] = (c0 + j < A.C) ? __ldg(A.dout_nchw + (n * A.C + c0 + j) * A.HW + hw) : 0.f;
+    L.g = make_uint4(__float_as_uint(gn[0]), __float_as_uint(gn[1]), __float_as_uint(gn[2]), __float_as_uint(gn[3]));
+    L.g2 = make_uint4(__float_as_uint(gn[4]), __float_as_uint(gn[5]), __float_as_uint(gn[6]), __float_as_uint(gn[7]));
+  }
+  if (A.relu_out) L.o = ldg16(A.out, off);
+  L.ya = ldg16(A.a.y, off);
+  if (has_b) L.yb = ldg16(A.b.y, off);
+}
+
+template <bool NCHW>
+__device__ __forceinline__ void grads_at(const mp_bn_args& A, const LoadsX<NCHW>& L, const float (&sa)[8],
+                                         const float (&ha)[8], int c0, float (&dza)[8], float (&dzb)[8],
+                                         float (&ya)[8]) {
+  float g[8];
+  if constexpr (!NCHW) {
+    unpack8(L.g, g);
+  } else {
+    g[0] = __uint_as_float(L.g.x); g[1] = __uint_as_float(L.g.y); g[2] = __uint_as_float(L.g.z);
+    g[3] = __uint_as_float(L.g.w); g[4] = __uint_as_float(L.g2.x); g[5] = __uint_as_float(L.g2.y);
+    g[6] = __uint_as_float(L.g2.z); g[7] = __uint_as_float(L.g2.w);
   }
   if (A.relu_out) {
-    const Chan8 o = load8(reinterpret_cast<const __nv_bfloat16*>(A.out) + off);
+    float o[8];
+    unpack8(L.o, o);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      if (!(o.v[j] > 0.f)) g.v[j] = 0.f;
+      if (!(o[j] > 0.f)) g[j] = 0.f;
   }
-  const Chan8 ya = load8(reinterpret_cast<const __nv_bfloat16*>(A.a.y) + off);
+  unpack8(L.ya, ya);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float dz = g.v[j];
-    if (A.relu_a && !(fmaf(ya.v[j], ka.scale[j], ka.shift[j]) > 0.f)) dz = 0.f;
-    if (c0 + j >= A.C) dz = 0.f;
-    d.a.v[j] = dz;
-    d.xa.v[j] = (ya.v[j] - ka.mean[j]) * ka.invstd[j];
-  }
-  if (has_b) {
-    const Chan8 yb = load8(reinterpret_cast<const __nv_bfloat16*>(A.b.y) + off);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      d.b.v[j] = (c0 + j < A.C) ? g.v[j] : 0.f;
-      d.xb.v[j] = (yb.v[j] - kb.mean[j]) * kb.invstd[j];
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) d.b.v[j] = (c0 + j < A.C) ? g.v[j] : 0.f;   // identity residual gradient
+    if (c0 + j >= A.C) g[j] = 0.f;
+    dzb[j] = g[j];
+    dza[j] = (A.relu_a && !(fmaf(ya[j], sa[j], ha[j]) > 0.f)) ? 0.f : g[j];
   }
 }
 
-__global__ void __launch_bounds__(MAXT) bn_bwd_reduce_kernel(const mp_bn_args A, int ppb) {
-  __shared__ float red[MAXT * 32];
+// sums layout per replica: [0] sum dz_a, [1] sum dz_a * y_a, [2] sum dz_b, [3] sum dz_b * y_b
+template <bool NCHW>
+__global__ void __launch_bounds__(MAXT, 2) bn_bwd_reduce_kernel(const mp_bn_args A) {
+  __shared__ float red[32 * MAXT];
   const int cg = threadIdx.x, c0 = cg * 8;
   const bool has_b = A.b.y != nullptr;
-  Coef ka, kb;
-  coef_bwd(A.a, c0, A.C, ka);
-  if (has_b) coef_bwd(A.b, c0, A.C, kb);
+  float sa[8], ha[8];
+  affine(A, A.a, c0, true, sa, ha);
   float acc[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-  const long long p0 = (long long)blockIdx.x * ppb;
-  for (int i = threadIdx.y; i < ppb; i += blockDim.y) {
-    const long long pix = p0 + i;
+
+  const long long p0 = (long long)blockIdx.x * (blockDim.y * U) + threadIdx.y;
+  LoadsX<NCHW> L[U];
+#pragma unroll
+  for (int i = 0; i < U; ++i) {
+    const long long pix = p0 + (long long)i * blockDim.y;
+    if (pix < A.M) load_pixel<NCHW>(A, has_b, pix, c0, L[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < U; ++i) {
+    const long long pix = p0 + (long long)i * blockDim.y;
     if (pix >= A.M) break;
-    Dz d;
-    compute_dz(A, ka, kb, has_b, pix, c0, d);
+    float dza[8], dzb[8], ya[8], yb[8];
+    grads_at<NCHW>(A, L[i], sa, ha, c0, dza, dzb, ya);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      acc[j] += d.a.v[j];
-      acc[8 + j] += d.a.v[j] * d.xa.v[j];
-      if (has_b) {
-        acc[16 + j] += d.b.v[j];
-        acc[24 + j] += d.b.v[j] * d.xb.v[j];
+      acc[j] += dza[j];
+      acc[8 + j] = fmaf(dza[j], ya[j], acc[8 + j]);
+    }
+    if (has_b) {
+      unpack8(L[i].yb, yb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[16 + j] += dzb[j];
+        acc[24 + j] = fmaf(dzb[j], yb[j], acc[24 + j]);
       }
     }
   }
-  const int G = blockDim.x, tid = threadIdx.y * G + cg;
+  // block reduction over the pixel rows, all threads take part; then one atomic per (sum, channel)
+  const int G = blockDim.x, PY = blockDim.y;
+  const int tid = threadIdx.y * G + cg;
   const int nsum = has_b ? 32 : 16;
 #pragma unroll
   for (int j = 0; j < 32; ++j)
     if (j < nsum) red[j * MAXT + tid] = acc[j];
   __syncthreads();
-  if (threadIdx.y == 0) {
-    for (int j = 0; j < nsum; ++j) {
-      float s = 0.f;
-      for (int y = 0; y < (int)blockDim.y; ++y) s += red[j * MAXT + y * G + cg];
-      atomicAdd(A.sums + (j >> 3) * A.Cp + c0 + (j & 7), s);
+  float* dst = A.sums + (long long)(blockIdx.x % A.stat_replicas) * 4 * A.Cp;
+  for (int j = threadIdx.y; j < nsum; j += PY) {
+    float s = 0.f;
+    for (int y = 0; y < PY; ++y) s += red[j * MAXT + y * G + cg];
+    atomicAdd(dst + (j >> 3) * A.Cp + c0 + (j & 7), s);
+  }
+}
+
+// dy = scale * (dz - mean(dz) - x^ * mean(dz * x^)) = scale*dz + kb*y + kc per channel
+__device__ __forceinline__ void bwd_coefs(const mp_bn_args& A, const mp_bn_branch& br, int which, int c0,
+                                          float (&scale)[8], float (&kb)[8], float (&kc)[8], bool write_param_grads) {
+  const float inv_m = 1.0f / (float)A.M;
+  float s1v[8], s2v[8];
+  rsum8(A.sums + (2 * which) * A.Cp, c0, A.stat_replicas, 4 * A.Cp, s1v);
+  rsum8(A.sums + (2 * which + 1) * A.Cp, c0, A.stat_replicas, 4 * A.Cp, s2v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    scale[i] = kb[i] = kc[i] = 0.f;
+    if (c >= A.C) continue;
+    const float mean = br.save_mean[c], invstd = br.save_invstd[c];
+    const float s1 = s1v[i], s2 = s2v[i];
+    const float dgamma = invstd * (s2 - mean * s1);     // sum dz * x^
+    const float sc = br.gamma[c] * invstd;
+    scale[i] = sc;
+    kb[i] = -sc * dgamma * inv_m * invstd;
+    kc[i] = -sc * s1 * inv_m - kb[i] * mean;
+    if (write_param_grads) {
+      if (br.dbeta) br.dbeta[c] += s1;
+      if (br.dgamma) br.dgamma[c] += dgamma;
     }
   }
 }
 
-__global__ void __launch_bounds__(MAXT) bn_bwd_apply_kernel(const mp_bn_args A, int ppb) {
-  const int cg = threadIdx.x, c0 = cg * 8;
+template <bool NCHW>
+__global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_kernel(const mp_bn_args A) {
+  const int c0 = threadIdx.x * 8;
   const bool has_b = A.b.y != nullptr;
-  Coef ka, kb;
-  coef_bwd(A.a, c0, A.C, ka);
-  if (has_b) coef_bwd(A.b, c0, A.C, kb);
-  const float inv_m = 1.0f / (float)A.M;
-  float m1a[8], m2a[8], m1b[8], m2b[8];
+  const bool first = blockIdx.x == 0 && threadIdx.y == 0;
+  float sa[8], ha[8], ka[8], ca[8], sb[8], kb[8], cb[8];
+  affine(A, A.a, c0, true, sa, ha);
+  bwd_coefs(A, A.a, 0, c0, sa, ka, ca, first);
+  if (has_b) bwd_coefs(A, A.b, 1, c0, sb, kb, cb, first);
+
+  const long long p0 = (long long)blockIdx.x * (blockDim.y * UA) + threadIdx.y;
+  LoadsX<NCHW> L[UA];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    m1a[j] = A.sums[0 * A.Cp + c0 + j] * inv_m;
-    m2a[j] = A.sums[1 * A.Cp + c0 + j] * inv_m;
-    m1b[j] = has_b ? A.sums[2 * A.Cp + c0 + j] * inv_m : 0.f;
-    m2b[j] = has_b ? A.sums[3 * A.Cp + c0 + j] * inv_m : 0.f;
+  for (int i = 0; i < UA; ++i) {
+    const long long pix = p0 + (long long)i * blockDim.y;
+    if (pix < A.M) load_pixel<NCHW>(A, has_b, pix, c0, L[i]);
   }
-  if (blockIdx.x == 0 && threadIdx.y == 0) {   // affine-parameter gradients
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      if (c >= A.C) continue;
-      if (A.a.dbeta) A.a.dbeta[c] += A.sums[0 * A.Cp + c];
-      if (A.a.dgamma) A.a.dgamma[c] += A.sums[1 * A.Cp + c];
-      if (has_b && A.b.dbeta) A.b.dbeta[c] += A.sums[2 * A.Cp + c];
-      if (has_b && A.b.dgamma) A.b.dgamma[c] += A.sums[3 * A.Cp + c];
-    }
-  }
-  __nv_bfloat16* dya = reinterpret_cast<__nv_bfloat16*>(A.a.dy);
-  __nv_bfloat16* dyb = reinterpret_cast<__nv_bfloat16*>(A.b.dy);
-  __nv_bfloat16* dres = reinterpret_cast<__nv_bfloat16*>(A.dres);
-  const long long p0 = (long long)blockIdx.x * ppb;
-  for (int i = threadIdx.y; i < ppb; i += blockDim.y) {
-    const long long pix = p0 + i;
+  for (int i = 0; i < UA; ++i) {
+    const long long pix = p0 + (long long)i * blockDim.y;
     if (pix >= A.M) break;
     const long long off = pix * A.Cp + c0;
-    Dz d;
-    compute_dz(A, ka, kb, has_b, pix, c0, d);
-    Chan8 o;
+    float dza[8], dzb[8], ya[8], o[8];
+    grads_at<NCHW>(A, L[i], sa, ha, c0, dza, dzb, ya);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o.v[j] = ka.scale[j] * (d.a.v[j] - m1a[j] - d.xa.v[j] * m2a[j]);
-    if (dya) store8(dya + off, o);
+    for (int j = 0; j < 8; ++j) o[j] = (c0 + j < A.C) ? fmaf(sa[j], dza[j], fmaf(ka[j], ya[j], ca[j])) : 0.f;
+    if (A.a.dy) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.a.dy) + off) = pack8(o);
     if (has_b) {
+      float yb[8];
+      unpack8(L[i].yb, yb);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o.v[j] = kb.scale[j] * (d.b.v[j] - m1b[j] - d.xb.v[j] * m2b[j]);
-      if (dyb) store8(dyb + off, o);
-    } else if (dres) {
-      store8(dres + off, d.b);
+      for (int j = 0; j < 8; ++j) o[j] = (c0 + j < A.C) ? fmaf(sb[j], dzb[j], fmaf(kb[j], yb[j], cb[j])) : 0.f;
+      if (A.b.dy) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.b.dy) + off) = pack8(o);
+    } else if (A.dres) {
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.dres) + off) = pack8(dzb);
     }
   }
 }
@@ -297,6 +373,8 @@ int check_args(const mp_bn_args* a, const char* what, bool bwd) {
   MP_CHECK_ARG(a->a.gamma && a->a.beta, "%s: missing affine parameters", what);
   MP_CHECK_ARG(!a->b.y || (a->b.gamma && a->b.beta), "%s: missing affine parameters of branch b", what);
   MP_CHECK_ARG(!(a->b.y && a->res), "%s: a second BN branch and an identity residual are exclusive", what);
+  MP_CHECK_ARG(a->stat_replicas >= 1 && a->stat_replicas <= 64, "%s: stat_replicas %d out of range", what,
+               a->stat_replicas);
   if (!bwd) {
     MP_CHECK_ARG(a->out || a->out_nchw, "%s: no output", what);
     if (a->training) {
@@ -317,13 +395,13 @@ int check_args(const mp_bn_args* a, const char* what, bool bwd) {
   return MP_OK;
 }
 
-void launch_dims(const mp_bn_args* a, int pix_per_thread, dim3* grid, dim3* block, int* ppb) {
+void launch_dims(const mp_bn_args* a, dim3* grid, dim3* block, int u = U) {
   const int G = a->Cp / 8;
   int py = MAXT / G;
   if (py < 1) py = 1;
   *block = dim3(G, py);
-  *ppb = py * pix_per_thread;
-  *grid = dim3((unsigned)((a->M + *ppb - 1) / *ppb));
+  const long long ppb = (long long)py * u;
+  *grid = dim3((unsigned)((a->M + ppb - 1) / ppb));
 }
 
 }  // namespace
@@ -334,9 +412,8 @@ int mp_bn_fwd(const mp_bn_args* a, void* stream) {
   int rc = check_args(a, "mp_bn_fwd", false);
   if (rc != MP_OK) return rc;
   dim3 grid, block;
-  int ppb;
-  launch_dims(a, 4, &grid, &block, &ppb);
-  bn_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*a, ppb);
+  launch_dims(a, &grid, &block);
+  bn_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*a);
   MP_CHECK_LAUNCH("mp_bn_fwd");
   return MP_OK;
 }
@@ -345,9 +422,9 @@ int mp_bn_bwd_reduce(const mp_bn_args* a, void* stream) {
   int rc = check_args(a, "mp_bn_bwd_reduce", true);
   if (rc != MP_OK) return rc;
   dim3 grid, block;
-  int ppb;
-  launch_dims(a, 8, &grid, &block, &ppb);
-  bn_bwd_reduce_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*a, ppb);
+  launch_dims(a, &grid, &block);
+  if (a->dout) bn_bwd_reduce_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
+  else bn_bwd_reduce_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
   MP_CHECK_LAUNCH("mp_bn_bwd_reduce");
   return MP_OK;
 }
@@ -356,9 +433,9 @@ int mp_bn_bwd_apply(const mp_bn_args* a, void* stream) {
   int rc = check_args(a, "mp_bn_bwd_apply", true);
   if (rc != MP_OK) return rc;
   dim3 grid, block;
-  int ppb;
-  launch_dims(a, 4, &grid, &block, &ppb);
-  bn_bwd_apply_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*a, ppb);
+  launch_dims(a, &grid, &block, UA);
+  if (a->dout) bn_bwd_apply_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
+  else bn_bwd_apply_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
   MP_CHECK_LAUNCH("mp_bn_bwd_apply");
   return MP_OK;
 }

@@ -37,6 +37,8 @@ struct IgemmParams {
   int out_c;
   float* stat_sum;
   float* stat_sq;
+  int stat_replicas;
+  long long stat_stride;
 };
 
 __global__ void __launch_bounds__(NTHREADS)
@@ -51,8 +53,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   uint64_t* empty = full + stages;
   uint64_t* tmem_full = empty + stages;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* s_stat = reinterpret_cast<float*>(tmem_holder + 4);   // [2][256] per-CTA channel sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (P.stat_sum)
+    for (int i = threadIdx.x; i < 512; i += NTHREADS) s_stat[i] = 0.f;
   int t = blockIdx.x;
   const int tw = t % P.tiles_w; t /= P.tiles_w;
   const int th = t % P.tiles_h;
@@ -166,9 +171,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         }
         const float a1 = tc::warp_transpose_sum(s1);
         const float a2 = tc::warp_transpose_sum(s2);
-        if (ch + lane < P.out_c) {
-          atomicAdd(P.stat_sum + ch + lane, a1);
-          atomicAdd(P.stat_sq + ch + lane, a2);
+        atomicAdd(s_stat + c * 32 + lane, a1);          // 4 epilogue warps meet in shared memory ...
+        atomicAdd(s_stat + 256 + c * 32 + lane, a2);
+      }
+    }
+    if (P.stat_sum) {   // ... and the CTA issues ONE global atomic per channel and statistic
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const long long rep = (long long)(blockIdx.x % P.stat_replicas) * P.stat_stride;
+      for (int i = threadIdx.x - 64; i < P.n_tile; i += 128) {
+        if (n0 + i < P.out_c) {
+          atomicAdd(P.stat_sum + rep + n0 + i, s_stat[i]);
+          atomicAdd(P.stat_sq + rep + n0 + i, s_stat[256 + i]);
         }
       }
     }
@@ -250,7 +263,7 @@ extern "C" int mp_conv_igemm(const mp_igemm_args* a, void* stream) {
   MP_CHECK_ARG(a->w_rows % P.n_tile == 0, "mp_conv_igemm: w_rows %lld not tileable", (long long)a->w_rows);
   P.b_stage_bytes = P.n_tile * 128;
   const int stage_bytes = A_STAGE_BYTES + P.b_stage_bytes;
-  const int overhead = 1024 + 256;   // alignment slack + barriers
+  const int overhead = 1024 + 256 + 2048;   // alignment slack + barriers + per-CTA channel sums
   int stages = (int)((g_igemm_smem - overhead) / stage_bytes);
   if (stages < 2) stages = 2;
   if (stages > 8) stages = 8;
@@ -265,6 +278,8 @@ extern "C" int mp_conv_igemm(const mp_igemm_args* a, void* stream) {
   P.out_c = a->out_c;
   P.stat_sum = a->stat_sum;
   P.stat_sq = a->stat_sq;
+  P.stat_replicas = a->stat_replicas > 1 ? a->stat_replicas : 1;
+  P.stat_stride = a->stat_stride;
 
   CUtensorMap tmA0, tmA1, tmB;
   const uint32_t boxA[5] = {64, (uint32_t)P.tile_w, 1, (uint32_t)P.tile_rows, 1};

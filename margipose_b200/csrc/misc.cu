@@ -165,6 +165,10 @@ __global__ void __launch_bounds__(256) combiner_fwd_kernel(const float* __restri
 }
 
 // dp_k[n, j, pix] = sum_c w[c, k*J + j] * dout[pix, c];  dw[c, kk] += sum_pix dout[pix, c] * p[kk, pix]
+// One block walks CMB_TILES tiles of 32 pixels of one image; the weight-gradient partial sums stay in
+// registers across the tiles, so the block issues one atomic per weight at the end.
+constexpr int CMB_TILES = 8;
+constexpr int CMB_WPT = 26;   // weights per thread: ceil(128 * 51 / 256)
 __global__ void __launch_bounds__(256) combiner_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
                                                          const float* __restrict__ p0, const float* __restrict__ p1,
                                                          const float* __restrict__ p2, const float* __restrict__ w,
@@ -175,36 +179,52 @@ __global__ void __launch_bounds__(256) combiner_bwd_kernel(const __nv_bfloat16* 
   const int K = 3 * J;
   float* sd = sm;                    // [CMB_PIX][C + 1]
   float* sw = sd + CMB_PIX * (C + 1);   // [C][K]
-  float* sp = sw + C * K;            // [K][CMB_PIX]
+  float* sp = sw + C * K;            // [K][CMB_PIX + 1] (padded: the dW loop walks k across lanes)
   const int n = blockIdx.y;
-  const int pix0 = blockIdx.x * CMB_PIX;
-  for (int i = threadIdx.x; i < CMB_PIX * C; i += blockDim.x) {
-    const int px = i / C, c = i - px * C;
-    sd[px * (C + 1) + c] =
-        (pix0 + px < HW) ? __bfloat162float(dout[((long long)n * HW + pix0 + px) * C + c]) : 0.f;
-  }
   for (int i = threadIdx.x; i < C * K; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < K * CMB_PIX; i += blockDim.x) {
-    const int k = i / CMB_PIX, px = i - k * CMB_PIX;
-    const float* src = k < J ? p0 : (k < 2 * J ? p1 : p2);
-    sp[i] = (pix0 + px < HW) ? src[((long long)n * J + (k % J)) * HW + pix0 + px] : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < K * CMB_PIX; i += blockDim.x) {
-    const int k = i / CMB_PIX, px = i - k * CMB_PIX;
-    if (pix0 + px >= HW) continue;
-    float acc = 0.f;
-    for (int c = 0; c < C; ++c) acc = fmaf(sw[c * K + k], sd[px * (C + 1) + c], acc);
-    float* dst = k < J ? dp0 : (k < 2 * J ? dp1 : dp2);
-    float* d = dst + ((long long)n * J + (k % J)) * HW + pix0 + px;
-    *d = accumulate ? *d + acc : acc;
-  }
-  for (int i = threadIdx.x; i < C * K; i += blockDim.x) {
-    const int c = i / K, k = i - c * K;
-    float acc = 0.f;
+  float wacc[CMB_WPT];
+#pragma unroll
+  for (int q = 0; q < CMB_WPT; ++q) wacc[q] = 0.f;
+  for (int tile = 0; tile < CMB_TILES; ++tile) {
+    const int pix0 = (blockIdx.x * CMB_TILES + tile) * CMB_PIX;
+    if (pix0 >= HW) break;
+    __syncthreads();
+    for (int i = threadIdx.x; i < CMB_PIX * C; i += blockDim.x) {
+      const int px = i / C, c = i - px * C;
+      sd[px * (C + 1) + c] =
+          (pix0 + px < HW) ? __bfloat162float(dout[((long long)n * HW + pix0 + px) * C + c]) : 0.f;
+    }
+    for (int i = threadIdx.x; i < K * CMB_PIX; i += blockDim.x) {
+      const int k = i / CMB_PIX, px = i - k * CMB_PIX;
+      const float* src = k < J ? p0 : (k < 2 * J ? p1 : p2);
+      sp[k * (CMB_PIX + 1) + px] = (pix0 + px < HW) ? src[((long long)n * J + (k % J)) * HW + pix0 + px] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * CMB_PIX; i += blockDim.x) {
+      const int k = i / CMB_PIX, px = i - k * CMB_PIX;
+      if (pix0 + px >= HW) continue;
+      float acc = 0.f;
+      for (int c = 0; c < C; ++c) acc = fmaf(sw[c * K + k], sd[px * (C + 1) + c], acc);
+      float* dst = k < J ? dp0 : (k < 2 * J ? dp1 : dp2);
+      float* d = dst + ((long long)n * J + (k % J)) * HW + pix0 + px;
+      *d = accumulate ? *d + acc : acc;
+    }
+#pragma unroll
+    for (int q = 0; q < CMB_WPT; ++q) {
+      const int i = threadIdx.x + q * 256;
+      if (i < C * K) {
+        const int c = i / K, k = i - c * K;
+        float acc = wacc[q];
 #pragma unroll 8
-    for (int px = 0; px < CMB_PIX; ++px) acc = fmaf(sd[px * (C + 1) + c], sp[k * CMB_PIX + px], acc);
-    atomicAdd(dw + i, acc);
+        for (int px = 0; px < CMB_PIX; ++px) acc = fmaf(sd[px * (C + 1) + c], sp[k * (CMB_PIX + 1) + px], acc);
+        wacc[q] = acc;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < CMB_WPT; ++q) {
+    const int i = threadIdx.x + q * 256;
+    if (i < C * K) atomicAdd(dw + i, wacc[q]);
   }
 }
 
@@ -357,9 +377,14 @@ int mp_combiner_bwd(const void* dout, const float* const p[3], const float* w, f
   MP_CHECK_ARG(dout && p && p[0] && p[1] && p[2] && w && dp && dp[0] && dp[1] && dp[2] && dw && N > 0 && J > 0 &&
                    HW > 0 && C > 0,
                "mp_combiner_bwd: bad arguments");
-  const size_t smem = (size_t)(CMB_PIX * (C + 1) + C * 3 * J + 3 * J * CMB_PIX) * sizeof(float);
-  MP_CHECK_ARG(smem <= 48 * 1024, "mp_combiner_bwd: J*C too large");
-  dim3 grid((HW + CMB_PIX - 1) / CMB_PIX, N);
+  const size_t smem = (size_t)(CMB_PIX * (C + 1) + C * 3 * J + 3 * J * (CMB_PIX + 1)) * sizeof(float);
+  MP_CHECK_ARG(smem <= 96 * 1024 && (long long)C * 3 * J <= 256 * CMB_WPT, "mp_combiner_bwd: J*C too large");
+  static bool attr_set = false;
+  if (!attr_set) {
+    MP_CUDA(cudaFuncSetAttribute(combiner_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((HW + CMB_PIX * CMB_TILES - 1) / (CMB_PIX * CMB_TILES), N);
   combiner_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, p[0], p[1], p[2], w,
                                                                  dp[0], dp[1], dp[2], dw, accumulate, J, HW, C);
   MP_CHECK_LAUNCH("mp_combiner_bwd");

@@ -307,10 +307,12 @@ class Engine:
         self.bank, self.L = model._bank, model._layers
         self._bufs = []
         self.streams = [torch.cuda.Stream(device=device) for _ in range(3)]
-        # per-BatchNorm fwd sums (2*Cp each) followed by the backward reductions (4*Cp per op)
-        self.stats = torch.zeros(max(3 * self.L.bn_floats, 8), device=device)
+        # R replicas of the per-BatchNorm fwd sums (2*Cp each, replica stride = bn_floats), followed
+        # by the backward reductions (R * 4*Cp per op); producers spread their atomics over replicas
+        self.R = 8
+        self.stats = torch.zeros(max(3 * self.R * self.L.bn_floats, 8), device=device)
         self.saves = torch.zeros(max(self.L.bn_floats, 8), device=device)
-        self._stat_n = self.L.bn_floats
+        self._stat_n = self.R * self.L.bn_floats
         self.fwd, self.bwd = [], []
         self.trace = []        # (name, buffer, real channels) of every block output, in forward order
         self._record()
@@ -386,13 +388,14 @@ class Engine:
         args.M = ya.numel() // ya.shape[-1]
         args.C, args.Cp, args.HW = a.C, a.Cp, hw
         args.training = int(self.training)
+        args.stat_replicas, args.stat_stride = self.R, self.L.bn_floats
         args.momentum = a.mod.momentum if a.mod.momentum is not None else 0.1
         args.eps = a.mod.eps
         return args
 
     def stats_of(self, bn):
         s = self.stats
-        return (s[bn.slot:bn.slot + bn.Cp], s[bn.slot + bn.Cp:bn.slot + 2 * bn.Cp])
+        return (s[bn.slot:bn.slot + bn.Cp], s[bn.slot + bn.Cp:bn.slot + 2 * bn.Cp], self.R, self.L.bn_floats)
 
     def conv_fwd(self, prog, conv, x, bn):
         g = conv.g
@@ -409,7 +412,7 @@ class Engine:
         args.dout, args.dout_nchw = _ptr(dout), _ptr(dout_nchw)
         args.a.dy, args.b.dy, args.dres = _ptr(dya), _ptr(dyb), _ptr(dres)
         args.sums = self.stats.data_ptr() + 4 * self._stat_n
-        self._stat_n += 4 * fwd_args.Cp
+        self._stat_n += 4 * fwd_args.Cp * self.R
         assert self._stat_n <= self.stats.numel()
         prog.append(self._launch('mp_bn_bwd_reduce', args))
         prog.append(self._launch('mp_bn_bwd_apply', args))

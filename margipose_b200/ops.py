@@ -28,7 +28,8 @@ class BnBranchT:
 
 
 def bn_args(a, b=None, res=None, relu_a=False, relu_out=False, out=None, out_nchw=None, dout=None,
-            dout_nchw=None, dres=None, sums=None, C=None, hw=0, training=True, momentum=0.1, eps=1e-5):
+            dout_nchw=None, dres=None, sums=None, C=None, hw=0, training=True, momentum=0.1, eps=1e-5,
+            stat_replicas=1, stat_stride=0):
     args = BnArgs()
     a.fill(args.a)
     if b is not None:
@@ -41,6 +42,7 @@ def bn_args(a, b=None, res=None, relu_a=False, relu_out=False, out=None, out_nch
     args.C = C if C is not None else a.gamma.numel()
     args.HW = hw
     args.training, args.momentum, args.eps = int(training), momentum, eps
+    args.stat_replicas, args.stat_stride = stat_replicas, stat_stride
     return args
 
 
