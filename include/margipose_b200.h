@@ -133,6 +133,8 @@ typedef struct mp_tap {
  * given, the per-channel sum and sum of squares of the stored (bf16-rounded) values are
  * atomically added to them -- the BatchNorm batch statistics of nn.BatchNorm2d in train mode
  * (optionally spread over stat_replicas copies that the BatchNorm kernels add up). */
+struct mp_bn_branch;
+
 typedef struct mp_igemm_args {
   mp_view5 src[2];
   const void* wmat;
@@ -149,9 +151,23 @@ typedef struct mp_igemm_args {
   float* stat_sq;
   int32_t stat_replicas;           /* >= 1: CTA b adds into replica (b % stat_replicas) ...          */
   int64_t stat_stride;             /* ... at stat_sum/stat_sq + replica * stat_stride (spreads atomics) */
+  /* BatchNorm finalize fused into the conv: the LAST CTA to add its statistics (ticket counter over
+   * bn_total_ctas arrivals, which may span several launches, e.g. the 4 parity classes of a
+   * transposed conv) turns sum/sq into mean / 1/std / scale / shift, saves them and updates the
+   * running buffers -- so the BatchNorm forward kernels start with one small load instead of a
+   * reduction.  bn: HOST pointer to the branch (gamma, beta, running_*, save_*, scale, shift,
+   * conv_bias are used) or NULL.  Requires stat_replicas == 1. */
+  const struct mp_bn_branch* bn;
+  uint32_t* bn_counter;            /* device counter, zero before the first contributing launch */
+  int32_t bn_total_ctas;           /* arrivals that complete the statistics (see mp_conv_igemm_ctas) */
+  int32_t bn_channels;             /* real channel count C */
+  int64_t bn_count;                /* elements per channel (N*H*W of the BatchNorm input) */
+  float bn_momentum, bn_eps;
 } mp_igemm_args;
 
 MP_API int mp_conv_igemm(const mp_igemm_args* args, void* stream);
+/* Number of CTAs (statistics arrivals) mp_conv_igemm launches for `args`. */
+MP_API int mp_conv_igemm_ctas(const mp_igemm_args* args);
 
 /* Weight gradient: dw[m][slot][n] += sum over the (n_img, grid_h, grid_w) pixel grid of
  *   a(pix, m) * b[tap](pix + shift, n)
@@ -196,6 +212,11 @@ typedef struct mp_bn_branch {
   float* save_mean;         /* (Cp) written by forward, read by backward */
   float* save_invstd;       /* (Cp) */
   const float* conv_bias;   /* (C) bias of the producing conv or NULL (only shifts the mean) */
+  float* scale;             /* (Cp) gamma/std, written by the producing conv's finalize (see mp_igemm_args.bn) */
+  float* shift;             /* (Cp) beta - mean*scale; when scale/shift are NULL the BatchNorm kernels derive
+                               them from sum/sq (training) or the running buffers (eval) themselves */
+  float* coef;              /* backward: (3, Cp) dy = coef0*dz + coef1*y + coef2, written by the last block
+                               of mp_bn_bwd_reduce, read by mp_bn_bwd_apply; NULL = recompute per block */
   void* dy;                 /* backward: bf16 (M, Cp) gradient w.r.t. y */
   float* dgamma;            /* backward: (C), accumulated (+=) */
   float* dbeta;             /* backward: (C), accumulated (+=) */
@@ -211,6 +232,7 @@ typedef struct mp_bn_args {
   const float* dout_nchw;   /* backward: fp32 (N, C, HW) gradient w.r.t. out_nchw, or NULL */
   void* dres;               /* backward: bf16 (M, Cp) gradient w.r.t. res, or NULL */
   float* sums;              /* backward workspace (stat_replicas, 4, Cp): zero before mp_bn_bwd_reduce */
+  uint32_t* bwd_counter;    /* backward: ticket counter (zero before mp_bn_bwd_reduce) for the coef finalize, or NULL */
   int32_t stat_replicas;    /* >= 1: number of copies of sum / sq / sums the producers spread their atomics over */
   int64_t stat_stride;      /* elements between copies of sum / sq (copies of sums are 4*Cp apart) */
   int64_t M;
@@ -281,7 +303,10 @@ MP_API int mp_sgd_step(float* param, const float* grad, float* momentum_buf, int
 
 /* Tunables for experiments (name -> value); returns MP_ERR_ARG for unknown names.
  *   "igemm_smem"  : shared-memory budget per CTA of mp_conv_igemm in bytes (default 101376)
- *   "wgrad_ctas"  : target CTA count of mp_conv_wgrad (default 296) */
+ *   "wgrad_ctas"  : target CTA count of mp_conv_wgrad (default 148)
+ *   "wgrad_taps"  : filter taps accumulated per CTA (default 1)
+ *   "wgrad_kp"    : pixels per pipeline stage of mp_conv_wgrad (default 128)
+ *   "wgrad_dbg"   : experiment switches (1 = skip the gradient atomics, 2 = issue MMAs twice, 4 = no MMA) */
 MP_API int mp_set_tunable(const char* name, int64_t value);
 
 #ifdef __cplusplus

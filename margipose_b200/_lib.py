@@ -36,7 +36,10 @@ class IgemmArgs(ctypes.Structure):
                 ('out_w', ctypes.c_int32), ('out', c_void_p), ('res', c_void_p),
                 ('out_sn', ctypes.c_int64), ('out_sh', ctypes.c_int64), ('out_sw', ctypes.c_int64),
                 ('out_c', ctypes.c_int32), ('stat_sum', c_void_p), ('stat_sq', c_void_p),
-                ('stat_replicas', ctypes.c_int32), ('stat_stride', ctypes.c_int64)]
+                ('stat_replicas', ctypes.c_int32), ('stat_stride', ctypes.c_int64),
+                ('bn', c_void_p), ('bn_counter', c_void_p), ('bn_total_ctas', ctypes.c_int32),
+                ('bn_channels', ctypes.c_int32), ('bn_count', ctypes.c_int64),
+                ('bn_momentum', ctypes.c_float), ('bn_eps', ctypes.c_float)]
 
 
 class WgradArgs(ctypes.Structure):
@@ -49,13 +52,13 @@ class WgradArgs(ctypes.Structure):
 class BnBranch(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ('y', 'sum', 'sq', 'gamma', 'beta', 'running_mean',
                                         'running_var', 'save_mean', 'save_invstd', 'conv_bias',
-                                        'dy', 'dgamma', 'dbeta')]
+                                        'scale', 'shift', 'coef', 'dy', 'dgamma', 'dbeta')]
 
 
 class BnArgs(ctypes.Structure):
     _fields_ = [('a', BnBranch), ('b', BnBranch), ('res', c_void_p), ('relu_a', ctypes.c_int32),
                 ('relu_out', ctypes.c_int32), ('out', c_void_p), ('out_nchw', c_void_p),
-                ('dout', c_void_p), ('dout_nchw', c_void_p), ('dres', c_void_p), ('sums', c_void_p),
+                ('dout', c_void_p), ('dout_nchw', c_void_p), ('dres', c_void_p), ('sums', c_void_p), ('bwd_counter', c_void_p),
                 ('stat_replicas', ctypes.c_int32), ('stat_stride', ctypes.c_int64),
                 ('M', ctypes.c_int64), ('C', ctypes.c_int32), ('Cp', ctypes.c_int32),
                 ('HW', ctypes.c_int32), ('training', ctypes.c_int32), ('momentum', ctypes.c_float),
@@ -90,6 +93,7 @@ def _signatures():
         'mp_euclid_bwd': (I, [P, P, P, P, I, I, P, P]),
         'mp_make_gauss': (I, [P, P, I, D, I, I, I, P]),
         'mp_conv_igemm': (I, [ctypes.POINTER(IgemmArgs), P]),
+        'mp_conv_igemm_ctas': (I, [ctypes.POINTER(IgemmArgs)]),
         'mp_conv_wgrad': (I, [ctypes.POINTER(WgradArgs), P]),
         'mp_set_tunable': (I, [ctypes.c_char_p, ctypes.c_int64]),
         'mp_bn_fwd': (I, [ctypes.POINTER(BnArgs), P]),

@@ -112,8 +112,11 @@ def _fill_taps(args, taps):
 
 
 def _igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_c, res=None,
-           stats=None, out_offset=0):
-    """srcs: list of (tensor, parity) pairs; see mp_conv_igemm in include/margipose_b200.h."""
+           stats=None, out_offset=0, bn=None, defer=None):
+    """srcs: list of (tensor, parity) pairs; see mp_conv_igemm in include/margipose_b200.h.
+    bn = dict(branch=BnBranch, counter=ptr, channels=C, count=M, momentum=, eps=): fuse the BatchNorm
+    finalize into the launch(es); defer = list collecting the argument structs of a multi-launch
+    conv so the caller can set the shared arrival total before launching."""
     a = IgemmArgs()
     for i, (t, parity) in enumerate(srcs):
         a.src[i] = _view(t, parity)
@@ -130,7 +133,16 @@ def _igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out
         a.stat_sum, a.stat_sq = stats[0].data_ptr(), stats[1].data_ptr()
         a.stat_replicas, a.stat_stride = (stats[2], stats[3]) if len(stats) > 2 else (1, 0)
     a._flops = 2.0 * n_img * out_h * out_w * len(taps) * _FLOP_CHANNELS[0]
-    _igemm_launch(a, out.device)
+    if bn is not None:
+        a._keep = bn['branch']
+        a.bn = ctypes.addressof(bn['branch'])
+        a.bn_counter, a.bn_channels, a.bn_count = bn['counter'], bn['channels'], bn['count']
+        a.bn_momentum, a.bn_eps = bn['momentum'], bn['eps']
+        a.bn_total_ctas = 0
+    if defer is not None:
+        defer.append((a, out.device))
+    else:
+        _igemm_launch(a, out.device)
 
 
 # real (unpadded) cin*cout of the layer being launched; set by conv_forward / conv_dgrad so the
@@ -180,7 +192,7 @@ def _s1_taps(k, k_stride, sign, src=0, koff0=0):
     return taps
 
 
-def conv_forward(g, x, wpack, out, stats=None, res=None):
+def conv_forward(g, x, wpack, out, stats=None, res=None, bn=None):
     """y = conv(x) (or conv_transpose(x)); x (N,H,W,cin_p), out (N,Ho,Wo,cout_p), both bf16 NHWC.
     stats = (sum, sumsq[, replicas, stride]) fp32 (cout_p) accumulators for the BatchNorm batch
     statistics (optionally `replicas` copies `stride` floats apart to spread the atomics)."""
@@ -195,18 +207,19 @@ def conv_forward(g, x, wpack, out, stats=None, res=None):
         else:
             taps, src = _down_taps(g.k, g.cin_p, g.cin_p), (x, True)
         _igemm([src], wpack, taps, cb, n, ho, wo, out, (ho * wo * g.cout_p, wo * g.cout_p, g.cout_p),
-               g.cout_p, res=res, stats=stats)
+               g.cout_p, res=res, stats=stats, bn=bn)
     else:
-        _scatter_up(g.k, (x, False), wpack, g.cin_p, cb, n, h, w, out, g.cout_p, stats, res)
+        _scatter_up(g.k, (x, False), wpack, g.cin_p, cb, n, h, w, out, g.cout_p, stats, res, bn=bn)
 
 
-def _scatter_up(k, src, wpack, k_stride, cb, n, h, w, out, c_out_p, stats, res, extra=None):
+def _scatter_up(k, src, wpack, k_stride, cb, n, h, w, out, c_out_p, stats, res, extra=None, bn=None):
     """The stride-2 'up' relation out[2a+ph, 2b+pw] = sum of taps over in[a+dh, b+dw]: one launch
     per output parity class, scattered into the (N, 2h, 2w, C) output.  Classes no tap reaches
     (1x1 kernels) stay zero in `out` (the buffer is zero-initialised once by its owner).
     extra = (k2, src2, k_stride2, koff0): a second source fused into the same accumulation."""
     wo = 2 * w
     strides = (4 * h * w * c_out_p, 2 * wo * c_out_p, 2 * c_out_p)
+    pending = [] if bn is not None else None
     for ph in (0, 1):
         for pw in (0, 1):
             taps = [(0, 0, dw, 0, dh, (r * k + s) * k_stride)
@@ -220,7 +233,12 @@ def _scatter_up(k, src, wpack, k_stride, cb, n, h, w, out, c_out_p, stats, res, 
             if not taps:
                 continue
             _igemm(srcs, wpack, taps, cb, n, h, w, out, strides, c_out_p, res=res, stats=stats,
-                   out_offset=(ph * wo + pw) * c_out_p)
+                   out_offset=(ph * wo + pw) * c_out_p, bn=bn, defer=pending)
+    if pending:   # the BatchNorm statistics are complete when the CTAs of ALL parity classes have arrived
+        total = sum(lib().mp_conv_igemm_ctas(ctypes.byref(a)) for a, _dev in pending)
+        for a, dev in pending:
+            a.bn_total_ctas = total
+            _igemm_launch(a, dev)
 
 
 def conv_dgrad(g, dy, wpack_bwd, dx, res=None, second=None):

@@ -91,8 +91,19 @@ __device__ __forceinline__ void channel_stats8(const mp_bn_args& A, const mp_bn_
   }
 }
 
+__device__ __forceinline__ void load8f(const float* p, int c0, float (&v)[8]) {
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(p + c0));
+  const float4 hi = __ldg(reinterpret_cast<const float4*>(p + c0) + 1);
+  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+
 __device__ __forceinline__ void affine(const mp_bn_args& A, const mp_bn_branch& br, int c0, bool from_saved,
                                        float (&scale)[8], float (&shift)[8]) {
+  if (br.scale && A.training) {   // finalised by the producing conv's last CTA (igemm.cu)
+    load8f(br.scale, c0, scale);
+    load8f(br.shift, c0, shift);
+    return;
+  }
   float mean[8], invstd[8], var[8];
   channel_stats8(A, br, c0, from_saved, mean, invstd, var);
 #pragma unroll
@@ -118,6 +129,7 @@ __global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const mp_bn_args A) {
   if (blockIdx.x == 0 && threadIdx.y == 0) {   // bookkeeping: saved statistics + running buffers
     for (int which = 0; which < (has_b ? 2 : 1); ++which) {
       const mp_bn_branch& br = which ? A.b : A.a;
+      if (br.scale && A.training) continue;     // the producing conv already did it
       float mean[8], invstd[8], var[8];
       channel_stats8(A, br, c0, false, mean, invstd, var);
       for (int i = 0; i < 8; ++i) {
@@ -137,7 +149,9 @@ __global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const mp_bn_args A) {
     }
   }
 
-  const long long p0 = (long long)blockIdx.x * (blockDim.y * U) + threadIdx.y;
+  const long long ppb = (long long)blockDim.y * U;
+  for (long long base = (long long)blockIdx.x * ppb; base < A.M; base += (long long)gridDim.x * ppb) {
+  const long long p0 = base + threadIdx.y;
   uint4 la[U], lb[U];
 #pragma unroll
   for (int i = 0; i < U; ++i) {
@@ -182,6 +196,7 @@ __global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const mp_bn_args A) {
       for (int j = 0; j < 8; ++j)
         if (c0 + j < A.C) A.out_nchw[(n * A.C + c0 + j) * A.HW + hw] = z[j];
     }
+  }
   }
 }
 
@@ -258,7 +273,9 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_reduce_kernel(const mp_bn_args
 #pragma unroll
   for (int j = 0; j < 32; ++j) acc[j] = 0.f;
 
-  const long long p0 = (long long)blockIdx.x * (blockDim.y * U) + threadIdx.y;
+  const long long ppb = (long long)blockDim.y * U;
+  for (long long base = (long long)blockIdx.x * ppb; base < A.M; base += (long long)gridDim.x * ppb) {
+  const long long p0 = base + threadIdx.y;
   LoadsX<NCHW> L[U];
 #pragma unroll
   for (int i = 0; i < U; ++i) {
@@ -285,6 +302,7 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_reduce_kernel(const mp_bn_args
       }
     }
   }
+  }
   // block reduction over the pixel rows, all threads take part; then one atomic per (sum, channel)
   const int G = blockDim.x, PY = blockDim.y;
   const int tid = threadIdx.y * G + cg;
@@ -299,21 +317,53 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_reduce_kernel(const mp_bn_args
     for (int y = 0; y < PY; ++y) s += red[j * MAXT + y * G + cg];
     atomicAdd(dst + (j >> 3) * A.Cp + c0 + (j & 7), s);
   }
+  if (A.bwd_counter == nullptr) return;
+  // Last block to arrive turns the sums into the per-channel coefficients of the apply pass
+  // (dy = coef0*dz + coef1*y + coef2) and accumulates the affine-parameter gradients.
+  __shared__ unsigned s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(A.bwd_counter, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  __threadfence();
+  const float inv_m = 1.0f / (float)A.M;
+  for (int c = tid; c < A.Cp; c += G * PY) {
+    for (int which = 0; which < (has_b ? 2 : 1); ++which) {
+      const mp_bn_branch& br = which ? A.b : A.a;
+      float k0 = 0.f, k1 = 0.f, k2 = 0.f;
+      if (c < A.C) {
+        const float mean = br.save_mean[c], invstd = br.save_invstd[c];
+        const float s1 = __ldcg(A.sums + (2 * which) * A.Cp + c), s2 = __ldcg(A.sums + (2 * which + 1) * A.Cp + c);
+        const float dgamma = invstd * (s2 - mean * s1);
+        k0 = br.gamma[c] * invstd;
+        k1 = -k0 * dgamma * inv_m * invstd;
+        k2 = -k0 * s1 * inv_m - k1 * mean;
+        if (br.dbeta) br.dbeta[c] += s1;
+        if (br.dgamma) br.dgamma[c] += dgamma;
+      }
+      br.coef[c] = k0;
+      br.coef[A.Cp + c] = k1;
+      br.coef[2 * A.Cp + c] = k2;
+    }
+  }
 }
 
 // dy = scale * (dz - mean(dz) - x^ * mean(dz * x^)) = scale*dz + kb*y + kc per channel
 __device__ __forceinline__ void bwd_coefs(const mp_bn_args& A, const mp_bn_branch& br, int which, int c0,
                                           float (&scale)[8], float (&kb)[8], float (&kc)[8], bool write_param_grads) {
   const float inv_m = 1.0f / (float)A.M;
-  float s1v[8], s2v[8];
+  float s1v[8], s2v[8], meanv[8], invv[8];
   rsum8(A.sums + (2 * which) * A.Cp, c0, A.stat_replicas, 4 * A.Cp, s1v);
   rsum8(A.sums + (2 * which + 1) * A.Cp, c0, A.stat_replicas, 4 * A.Cp, s2v);
+  load8f(br.save_mean, c0, meanv);      // (Cp)-sized buffers: vector loads, all in flight together
+  load8f(br.save_invstd, c0, invv);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = c0 + i;
     scale[i] = kb[i] = kc[i] = 0.f;
     if (c >= A.C) continue;
-    const float mean = br.save_mean[c], invstd = br.save_invstd[c];
+    const float mean = meanv[i], invstd = invv[i];
     const float s1 = s1v[i], s2 = s2v[i];
     const float dgamma = invstd * (s2 - mean * s1);     // sum dz * x^
     const float sc = br.gamma[c] * invstd;
@@ -334,10 +384,22 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_kernel(const mp_bn_args 
   const bool first = blockIdx.x == 0 && threadIdx.y == 0;
   float sa[8], ha[8], ka[8], ca[8], sb[8], kb[8], cb[8];
   affine(A, A.a, c0, true, sa, ha);
-  bwd_coefs(A, A.a, 0, c0, sa, ka, ca, first);
-  if (has_b) bwd_coefs(A, A.b, 1, c0, sb, kb, cb, first);
+  if (A.a.coef && A.bwd_counter) {   // finalised by the last block of the reduce pass
+    load8f(A.a.coef + A.Cp, c0, ka);
+    load8f(A.a.coef + 2 * A.Cp, c0, ca);
+    if (has_b) {
+      load8f(A.b.coef, c0, sb);
+      load8f(A.b.coef + A.Cp, c0, kb);
+      load8f(A.b.coef + 2 * A.Cp, c0, cb);
+    }
+  } else {
+    bwd_coefs(A, A.a, 0, c0, sa, ka, ca, first);
+    if (has_b) bwd_coefs(A, A.b, 1, c0, sb, kb, cb, first);
+  }
 
-  const long long p0 = (long long)blockIdx.x * (blockDim.y * UA) + threadIdx.y;
+  const long long ppb = (long long)blockDim.y * UA;
+  for (long long base = (long long)blockIdx.x * ppb; base < A.M; base += (long long)gridDim.x * ppb) {
+  const long long p0 = base + threadIdx.y;
   LoadsX<NCHW> L[UA];
 #pragma unroll
   for (int i = 0; i < UA; ++i) {
@@ -363,6 +425,7 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_kernel(const mp_bn_args 
     } else if (A.dres) {
       *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.dres) + off) = pack8(dzb);
     }
+  }
   }
 }
 
@@ -390,18 +453,24 @@ int check_args(const mp_bn_args* a, const char* what, bool bwd) {
     MP_CHECK_ARG(a->sums && a->a.save_mean && a->a.save_invstd, "%s: missing saved statistics / workspace", what);
     MP_CHECK_ARG(!a->b.y || (a->b.save_mean && a->b.save_invstd), "%s: missing saved statistics of branch b", what);
     MP_CHECK_ARG(!a->relu_out || a->out, "%s: relu_out needs the forward output", what);
+    MP_CHECK_ARG(!a->bwd_counter || (a->stat_replicas == 1 && a->a.coef && (!a->b.y || a->b.coef)),
+                 "%s: the fused coefficient finalize needs coef buffers and un-replicated sums", what);
   }
   MP_CHECK_ARG(!(a->out_nchw || a->dout_nchw) || a->HW > 0, "%s: HW missing", what);
   return MP_OK;
 }
 
-void launch_dims(const mp_bn_args* a, dim3* grid, dim3* block, int u = U) {
+// Grid-stride kernels: at most `cap` blocks (2 per SM resident), so the per-block prologue and, in
+// the reduce pass, the per-block atomics are amortised over many pixels.
+void launch_dims(const mp_bn_args* a, dim3* grid, dim3* block, int u, int cap) {
   const int G = a->Cp / 8;
   int py = MAXT / G;
   if (py < 1) py = 1;
   *block = dim3(G, py);
   const long long ppb = (long long)py * u;
-  *grid = dim3((unsigned)((a->M + ppb - 1) / ppb));
+  long long blocks = (a->M + ppb - 1) / ppb;
+  if (blocks > cap) blocks = cap;
+  *grid = dim3((unsigned)blocks);
 }
 
 }  // namespace
@@ -412,7 +481,7 @@ int mp_bn_fwd(const mp_bn_args* a, void* stream) {
   int rc = check_args(a, "mp_bn_fwd", false);
   if (rc != MP_OK) return rc;
   dim3 grid, block;
-  launch_dims(a, &grid, &block);
+  launch_dims(a, &grid, &block, U, 2 * 148);
   bn_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*a);
   MP_CHECK_LAUNCH("mp_bn_fwd");
   return MP_OK;
@@ -422,7 +491,7 @@ int mp_bn_bwd_reduce(const mp_bn_args* a, void* stream) {
   int rc = check_args(a, "mp_bn_bwd_reduce", true);
   if (rc != MP_OK) return rc;
   dim3 grid, block;
-  launch_dims(a, &grid, &block);
+  launch_dims(a, &grid, &block, U, 148);
   if (a->dout) bn_bwd_reduce_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
   else bn_bwd_reduce_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
   MP_CHECK_LAUNCH("mp_bn_bwd_reduce");
@@ -433,7 +502,7 @@ int mp_bn_bwd_apply(const mp_bn_args* a, void* stream) {
   int rc = check_args(a, "mp_bn_bwd_apply", true);
   if (rc != MP_OK) return rc;
   dim3 grid, block;
-  launch_dims(a, &grid, &block, UA);
+  launch_dims(a, &grid, &block, UA, 2 * 148);
   if (a->dout) bn_bwd_apply_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
   else bn_bwd_apply_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
   MP_CHECK_LAUNCH("mp_bn_bwd_apply");

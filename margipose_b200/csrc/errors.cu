@@ -27,6 +27,8 @@ extern "C" int mp_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "igemm_smem")) { mp_set_igemm_smem(value); return MP_OK; }
   if (!strcmp(name, "wgrad_ctas")) { mp_set_wgrad_tunable(0, value); return MP_OK; }
   if (!strcmp(name, "wgrad_taps")) { mp_set_wgrad_tunable(1, value); return MP_OK; }
+  if (!strcmp(name, "wgrad_dbg")) { mp_set_wgrad_tunable(2, value); return MP_OK; }
+  if (!strcmp(name, "wgrad_kp")) { mp_set_wgrad_tunable(3, value); return MP_OK; }
   mp_set_error("mp_set_tunable: unknown tunable '%s'", name);
   return MP_ERR_ARG;
 }

