@@ -310,6 +310,9 @@ class Engine:
         self.bank, self.L = model._bank, model._layers
         self._bufs = []
         self.streams = [torch.cuda.Stream(device=device) for _ in range(3)]
+        # one auxiliary stream per lane: weight gradients (nothing downstream waits for them) and the
+        # shortcut conv of a block run beside the lane's dependent chain
+        self.aux = [torch.cuda.Stream(device=device) for _ in range(3)]
         # R replicas of the per-BatchNorm fwd sums (2*Cp each, replica stride = bn_floats), followed
         # by the backward reductions (R * 4*Cp per op); producers spread their atomics over replicas
         # (R = 1: the conv epilogue pre-reduces in shared memory and its last CTA finalises the
@@ -363,6 +366,12 @@ class Engine:
         finally:
             C._igemm_launch, C._wgrad_launch = old_i, old_w
         return captured
+
+    @staticmethod
+    def _on_aux(ops):
+        for op in ops:
+            op.aux = True
+        return ops
 
     def _call(self, fn_name, *argv):
         """Op for a C-ABI entry point with scalar/pointer arguments + trailing stream."""
@@ -447,8 +456,10 @@ class Engine:
     # ---- blocks: each returns (output buffer, backward builder)
     def residual_block(self, fwd, rb, x, logits_out=None):
         """MargiPose ResidualBlock (margipose_model.py:25-40)."""
+        side = []
+        ys = self.conv_fwd(side, rb.convs, x, rb.bns)
+        fwd += self._on_aux(side)
         y1 = self.conv_fwd(fwd, rb.conv1, x, rb.bn1)
-        ys = self.conv_fwd(fwd, rb.convs, x, rb.bns)
         a1 = self.act(*y1.shape)
         f1 = self.bn_args(rb.bn1, y1, relu_a=True, out=a1)
         fwd.append(self._launch('mp_bn_fwd', f1))
@@ -457,17 +468,18 @@ class Engine:
         out = None if logits_out is not None else self.act(n, h, w, cp)
         f2 = self.bn_args(rb.bn2, y2, b=rb.bns, yb=ys, relu_a=True, out=out, out_nchw=logits_out, hw=h * w)
         fwd.append(self._launch('mp_bn_fwd', f2))
+        fwd[-1].join_aux = True
 
         def backward(bwd, dout=None, dout_nchw=None, need_dx=True):
             dy2, dys = self.act(*y2.shape), self.act(*ys.shape)
             self.bn_bwd(bwd, f2, dout=dout, dout_nchw=dout_nchw, dya=dy2, dyb=dys)
-            bwd += self.conv_ops(lambda: C.conv_wgrad(rb.conv2.g, a1, dy2, rb.conv2.w.grad))
+            bwd += self._on_aux(self.conv_ops(lambda: C.conv_wgrad(rb.conv2.g, a1, dy2, rb.conv2.w.grad)))
+            bwd += self._on_aux(self.conv_ops(lambda: C.conv_wgrad(rb.convs.g, x, dys, rb.convs.w.grad)))
             da1 = self.act(*a1.shape)
             bwd += self.conv_ops(lambda: C.conv_dgrad(rb.conv2.g, dy2, rb.conv2.bwd.t, da1))
             dy1 = self.act(*y1.shape)
             self.bn_bwd(bwd, f1, dout=da1, dya=dy1)
-            bwd += self.conv_ops(lambda: C.conv_wgrad(rb.conv1.g, x, dy1, rb.conv1.w.grad))
-            bwd += self.conv_ops(lambda: C.conv_wgrad(rb.convs.g, x, dys, rb.convs.w.grad))
+            bwd += self._on_aux(self.conv_ops(lambda: C.conv_wgrad(rb.conv1.g, x, dy1, rb.conv1.w.grad)))
             if not need_dx:
                 return None
             dx = self.act(*x.shape)
@@ -506,15 +518,15 @@ class Engine:
             dy = dyl
             for i in range(len(chain) - 1, 0, -1):
                 conv = chain[i][0]
-                bwd += self.conv_ops(lambda conv=conv, i=i, dy=dy: C.conv_wgrad(conv.g, acts[i], dy, conv.w.grad))
+                bwd += self._on_aux(self.conv_ops(lambda conv=conv, i=i, dy=dy: C.conv_wgrad(conv.g, acts[i], dy, conv.w.grad)))
                 da = self.act(*acts[i].shape)
                 bwd += self.conv_ops(lambda conv=conv, dy=dy, da=da: C.conv_dgrad(conv.g, dy, conv.bwd.t, da))
                 dy = self.act(*ys[i - 1].shape)
                 self.bn_bwd(bwd, fargs[i - 1], dout=da, dya=dy)
             conv0 = chain[0][0]
-            bwd += self.conv_ops(lambda: C.conv_wgrad(conv0.g, x, dy, conv0.w.grad))
+            bwd += self._on_aux(self.conv_ops(lambda: C.conv_wgrad(conv0.g, x, dy, conv0.w.grad)))
             if down is not None:
-                bwd += self.conv_ops(lambda: C.conv_wgrad(down[0].g, x, dyd, down[0].w.grad))
+                bwd += self._on_aux(self.conv_ops(lambda: C.conv_wgrad(down[0].g, x, dyd, down[0].w.grad)))
             if not need_dx:
                 return None
             dx = self.act(*x.shape)
@@ -682,18 +694,34 @@ class Engine:
         self.bwd = bsegs
 
     # ---- execution
-    def _run(self, segs):
+    def _run_lane(self, ops, main, aux):
+        """Ops in program order on `main` (the current stream); ops flagged .aux go to `aux` after
+        waiting for everything issued on `main` so far; an op flagged .join_aux first waits for aux."""
+        pending = False
+        for op in ops:
+            if getattr(op, 'aux', False):
+                aux.wait_stream(main)
+                with torch.cuda.stream(aux):
+                    op()
+                pending = True
+            else:
+                if pending and getattr(op, 'join_aux', False):
+                    main.wait_stream(aux)
+                    pending = False
+                op()
+        if pending:
+            main.wait_stream(aux)
+
+    def _run(self, segs, use_aux=True):
         cur = torch.cuda.current_stream(self.device)
         for kind, body in segs:
             if kind == 'serial':
-                for op in body:
-                    op()
+                self._run_lane(body, cur, self.aux[0] if use_aux else cur)
             else:
-                for s, ops in zip(self.streams, body):
+                for s, a, ops in zip(self.streams, self.aux, body):
                     s.wait_stream(cur)
                     with torch.cuda.stream(s):
-                        for op in ops:
-                            op()
+                        self._run_lane(ops, s, a if use_aux else s)
                 for s in self.streams:
                     cur.wait_stream(s)
 

@@ -1,0 +1,121 @@
+"""CPU checks of the host side: registry / factory behaviour (mirror of
+/root/reference/src/margipose/models/__init__.py:16-27 and model_factory.py), state_dict surface,
+joint bookkeeping, the C ABI exports, and that the product path refuses to run without CUDA."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import model_oracle as M
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = torch.load(os.path.join(ROOT, 'tests', 'golden', 'margipose_golden.pt'), weights_only=False)
+
+
+def desc(**settings):
+    s = dict(n_stages=1, feature_extractor='resnet18', axis_permutation=True, pixelwise_loss='jsd')
+    s.update(settings)
+    return {'type': 'margipose', 'version': '6.0.1', 'settings': s}
+
+
+def test_registry_matches_reference_behaviour():
+    from margipose_b200.models import create_model, MODEL_FACTORIES
+    from margipose_b200.model_factory import Version, Spec
+    assert len(MODEL_FACTORIES) == 1 and MODEL_FACTORIES[0].is_for('margipose', Version('6.0.1'))
+    assert Version('6.3.2') in Spec('^6.0.0') and Version('7.0.0') not in Spec('^6.0.0')
+    assert Version('5.9.9') not in Spec('^6.0.0') and Version('6.0.0') in Spec('^6.0.0')
+    with pytest.raises(Exception, match='unrecognised model chatterbox v1.0.0'):
+        create_model({'type': 'chatterbox', 'version': '1.0.0', 'settings': {}})
+    with pytest.raises(Exception, match='unrecognised model margipose v7.0.0'):
+        create_model({'type': 'margipose', 'version': '7.0.0', 'settings': {}})
+    with pytest.raises(Exception, match='unsupported image feature extractor'):
+        create_model(desc(feature_extractor='vgg16'))
+    with pytest.raises(Exception, match='unsupported image feature extractor'):
+        create_model({'type': 'margipose', 'version': '6.0.1', 'settings': {}})    # default = inceptionv4
+
+
+@pytest.mark.parametrize('case', GOLD['model'], ids=lambda c: c['name'])
+def test_state_dict_surface_is_the_references(case):
+    from margipose_b200.models import create_model
+    model = create_model(case['desc'])
+    sd = model.state_dict()
+    assert list(sd.keys()) == case['state_keys']
+    assert sum(p.numel() for p in model.parameters()) == case['n_params']
+    torch.manual_seed(0)
+    om = M.create_oracle(case['desc'])
+    model.load_state_dict(om.state_dict())          # shapes agree
+    om.load_state_dict(model.state_dict())
+    assert model.data_specs.input_specs.height == 256 and model.data_specs.output_specs.n_dims == 3
+    assert model.xy_heatmaps is None
+
+
+def test_param_count_symmetry_of_columns():
+    # /root/reference/tests/test_models.py:11-16
+    from margipose_b200.models.margipose_model import HeatmapColumn
+    n = [sum(p.numel() for p in HeatmapColumn(17, s).parameters()) for s in ('xy', 'zy', 'xz')]
+    assert n[0] == n[1] == n[2] == 4739599
+
+
+def test_joint_bookkeeping_is_bit_exact():
+    from margipose_b200.skeleton import CanonicalSkeletonDesc as S
+    assert S.joint_names == GOLD['joint_names'] == M.JOINT_NAMES
+    assert S.joint_tree == GOLD['joint_tree'] and S.hflip_indices == GOLD['hflip_indices']
+    assert S.n_joints == 17 and S.root_joint_id == 14
+
+
+def test_flat_bank_layout_roundtrip_on_cpu():
+    """Parameters become views of one flat buffer in channels-last (GEMM) order without changing
+    what state_dict() / load_state_dict() see."""
+    from margipose_b200.models import create_model
+    from margipose_b200.engine import ParamBank, build_layers
+    torch.manual_seed(3)
+    model = create_model(desc(n_stages=2))
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    bank = ParamBank()
+    layers = build_layers(model, bank)
+    bank.finalize(torch.device('cpu'))
+    after = model.state_dict()
+    for k in before:
+        assert torch.equal(before[k].float(), after[k].float()), k
+    w = model.inner.xy_hm_cnns[0].down_layers[0].module[0].weight
+    assert w.shape == (128, 128, 3, 3) and w.is_contiguous(memory_format=torch.channels_last)
+    assert bank.linked()
+    assert layers.n_bn == sum(isinstance(m, torch.nn.BatchNorm2d) for m in model.modules())
+    # every pack-table entry stays inside the bf16 pack buffer and work ranges tile [0, n_work)
+    pos = 0
+    for e in bank.pack_entries:
+        assert e['work_off'] == pos
+        pos = e['work_end']
+        last = e['dst_off'] + (e['rows_p'] - 1) * e['row_stride'] + e['taps'] * e['cols_p']
+        assert last <= bank.n_pack
+    assert pos == bank.n_work
+    with torch.no_grad():
+        w.mul_(2.0)                                  # writes through to the flat buffer
+    assert torch.equal(model.state_dict()['inner.xy_hm_cnns.0.down_layers.0.module.0.weight'], before[
+        'inner.xy_hm_cnns.0.down_layers.0.module.0.weight'] * 2)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from margipose_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'margipose_b200.h')).read()
+    declared = set(re.findall(r'MP_API\s+[\w\s\*]+?\b(mp_\w+)\s*\(', header))
+    assert declared, 'no declarations parsed'
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert declared == set(_lib.exported_symbols())
+    assert _lib.lib().mp_abi_version() >= 1
+
+
+def test_no_cpu_fallback():
+    from margipose_b200.models import create_model
+    from margipose_b200 import dsntnn as K
+    from margipose_b200._lib import MargiposeB200Error
+    with pytest.raises(MargiposeB200Error):
+        create_model(desc())(torch.randn(1, 3, 256, 256))
+    with pytest.raises(MargiposeB200Error):
+        K.flat_softmax(torch.randn(1, 17, 32, 32))
+    with pytest.raises(MargiposeB200Error):
+        K.dsnt(torch.rand(1, 17, 32, 32))
