@@ -302,7 +302,7 @@ MP_API int mp_sgd_step(float* param, const float* grad, float* momentum_buf, int
                        int first_step, float grad_scale, void* stream);
 
 /* Tunables for experiments (name -> value); returns MP_ERR_ARG for unknown names.
- *   "igemm_smem"  : shared-memory budget per CTA of mp_conv_igemm in bytes (default 101376)
+ *   "igemm_smem"  : shared-memory budget per CTA of mp_conv_igemm in bytes (default 115712)
  *   "wgrad_ctas"  : target CTA count of mp_conv_wgrad (default 148)
  *   "wgrad_taps"  : filter taps accumulated per CTA (default 1)
  *   "wgrad_kp"    : pixels per pipeline stage of mp_conv_wgrad (default 128)

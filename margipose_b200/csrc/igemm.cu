@@ -229,7 +229,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   if (warp == 1) tc::tmem_dealloc(tmem, P.tmem_cols);
 }
 
-long long g_igemm_smem = 101376;   // lets two CTAs share an SM (epilogue of one overlaps the other)
+long long g_igemm_smem = 115712;   // 113 KB: two CTAs share an SM (one's epilogue overlaps the other's main loop)
 bool g_attr_set = false;
 
 int view_to_tmap(CUtensorMap* tm, const mp_view5& v, const uint32_t box[5], const char* what) {

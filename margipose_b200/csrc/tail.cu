@@ -475,6 +475,360 @@ __global__ void __launch_bounds__(NT) make_gauss_kernel(const float* __restrict_
   }
 }
 
+// =====================================================================================
+// Warp-sliced fast path (16-byte aligned planes with W % 4 == 0 and H*W <= 4096*...): every
+// plane is covered by `wpp` warps holding NV float4 per lane in registers, all loads are issued
+// before the first use, reductions are warp shuffles plus ONE shared-memory hop per quantity, and a
+// CTA runs `groups` (sample, joint) pairs x `np` planes side by side -- 4 block barriers per CTA
+// instead of ~8 per plane, which is what lets the kernel approach the HBM roofline on 32x32 planes.
+struct WarpPlan {
+  int wpp, groups, np, BJ;
+  int seq;      // 1: the CTA's warps all work on one plane at a time (large planes), planes in sequence
+  int pid[3];   // plane slot -> plane index (only planes that are present get warps)
+};
+
+template <int NV, bool FROM_LOGITS>
+__global__ void __launch_bounds__(512, 2) tail_fwd_warp_kernel(const FwdArgs A, const WarpPlan P) {
+  extern __shared__ float sm[];
+  const int W = A.g.W, H = A.g.H, HW = A.g.HW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nslots = P.groups * P.np;
+  const int nseq = P.seq ? P.np : 1;
+  for (int it = 0; it < nseq; ++it) {
+  const int slot = P.seq ? it : warp / P.wpp;
+  const int s = P.seq ? warp : warp - slot * P.wpp;
+  const int g = slot / P.np, ks = slot - g * P.np;
+  const int k = P.pid[ks];
+  const int bj = blockIdx.x * P.groups + g;
+  const bool active = bj < P.BJ;
+  float* tab = sm + slot * 2 * (W + H);                   // ecol[W], erow[H], then their logs
+  float* ltab = tab + (W + H);
+  float* red = sm + nslots * 2 * (W + H) + slot * (P.wpp * 4);   // per warp: sum, sum*cw, sum*ch, max
+  float* jsr = sm + nslots * 2 * (W + H) + nslots * P.wpp * 4 + slot * P.wpp;   // per warp JS partial
+  float* res = sm + nslots * 2 * (W + H) + nslots * P.wpp * 5 + slot * 2;       // per plane (a, b)
+
+  const int b = active ? bj / A.J : 0;
+  const bool is3d = (active && A.valid_depth) ? (A.valid_depth[b] != 0) : true;
+  float tx = 0.f, ty = 0.f, tz = 0.f;
+  if (active && A.target) {
+    tx = A.target[bj * 3 + 0]; ty = A.target[bj * 3 + 1]; tz = A.target[bj * 3 + 2];
+  }
+  float mc = 0.f, mr = 0.f;
+  bool want_js = false;
+  if (active) {
+    if (A.mu[k]) {
+      mc = A.mu[k][bj * 2 + 0]; mr = A.mu[k][bj * 2 + 1];
+      want_js = A.js[k] != nullptr;
+    } else {
+      mc = (k == 1) ? tz : tx;
+      mr = (k == 2) ? tz : ty;
+      want_js = A.target && A.pixelwise && (A.loss || A.js[k]) && (k == 0 || is3d);
+    }
+  }
+  const size_t off = (size_t)bj * HW;
+  const float fill = FROM_LOGITS ? -INFINITY : 0.f;
+  float4 x[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = ((s * NV + i) * 32 + lane) * 4;
+    x[i] = (active && e < HW) ? __ldg(reinterpret_cast<const float4*>(A.in[k] + off + e))
+                              : make_float4(fill, fill, fill, fill);
+  }
+  float ginv = 0.f;
+  if (want_js) {   // every warp of the plane computes the (tiny) normaliser; slice 0 publishes the factors
+    float sc = 0.f, sr = 0.f;
+    for (int i = lane; i < W; i += 32) {
+      const float d = centre(i, A.g.cw_step, A.g.cw_first) - mc;
+      const float lg = __fmul_rn(__fmul_rn(d, d), A.g.kw);
+      const float ev = expf(lg);
+      sc += ev;
+      if (s == 0) { tab[i] = ev; ltab[i] = lg; }
+    }
+    for (int i = lane; i < H; i += 32) {
+      const float d = centre(i, A.g.ch_step, A.g.ch_first) - mr;
+      const float lg = __fmul_rn(__fmul_rn(d, d), A.g.kh);
+      const float ev = expf(lg);
+      sr += ev;
+      if (s == 0) { tab[W + i] = ev; ltab[W + i] = lg; }
+    }
+    ginv = 1.0f / (warp_sum(sc) * warp_sum(sr) + KL_EPS);
+  }
+  const float log_ginv = want_js ? logf(ginv) : 0.f;
+  float m = -INFINITY;
+  if (FROM_LOGITS) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) m = fmaxf(m, fmaxf(fmaxf(x[i].x, x[i].y), fmaxf(x[i].z, x[i].w)));
+    m = warp_max(m);
+    if (lane == 0) red[s * 4 + 3] = m;
+  }
+  __syncthreads();   // #1: Gaussian factors + per-warp maxima visible
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  if (FROM_LOGITS) {
+    for (int q = 0; q < P.wpp; ++q) m = fmaxf(m, red[q * 4 + 3]);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = ((s * NV + i) * 32 + lane) * 4;
+    const int h = e / W, w0 = e - h * W;
+    const float ch = centre(h, A.g.ch_step, A.g.ch_first);
+    float v[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+    float rowsum = 0.f;
+    // logits path: keep t = x - max in the registers (log p = t - log(sum) needs no log call later)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float ev = v[j];
+      if (FROM_LOGITS) {
+        v[j] = v[j] - m;          // fill = -inf stays -inf -> exp = 0
+        ev = __expf(v[j]);
+      }
+      rowsum += ev;
+      acc1 += ev * centre(w0 + j, A.g.cw_step, A.g.cw_first);
+    }
+    acc0 += rowsum;
+    acc2 += rowsum * ch;
+    x[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  acc0 = warp_sum(acc0); acc1 = warp_sum(acc1); acc2 = warp_sum(acc2);
+  if (lane == 0) { red[s * 4 + 0] = acc0; red[s * 4 + 1] = acc1; red[s * 4 + 2] = acc2; }
+  __syncthreads();   // #2
+  acc0 = acc1 = acc2 = 0.f;
+  for (int q = 0; q < P.wpp; ++q) { acc0 += red[q * 4 + 0]; acc1 += red[q * 4 + 1]; acc2 += red[q * 4 + 2]; }
+  float ea, eb;
+  float inv = 1.f, log_inv = 0.f;
+  if (FROM_LOGITS) {
+    inv = 1.0f / acc0;
+    log_inv = -logf(acc0);
+    ea = acc1 * inv; eb = acc2 * inv;
+  } else {
+    ea = acc1; eb = acc2;
+  }
+  // probabilities + JS.  log p and log q come in closed form (log-softmax; the Gaussian's exponent),
+  // clamped like log(. + 1e-24) clamps them; only log((p+q)/2) needs the special-function unit.
+  const float LOG_EPS = -55.262042231857096f;   // log(1e-24)
+  float jsp = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = ((s * NV + i) * 32 + lane) * 4;
+    const int h = e / W, w0 = e - h * W;
+    float pv[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+    float lp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (FROM_LOGITS) {
+        lp[j] = fmaxf(pv[j] + log_inv, LOG_EPS);
+        pv[j] = __expf(pv[j]) * inv;
+      } else if (want_js) {
+        lp[j] = __logf(pv[j] + KL_EPS);
+      }
+    }
+    x[i] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    if (want_js && e < HW) {
+      const float er = tab[W + h] * ginv;
+      const float lr = ltab[W + h] + log_ginv;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float q = tab[w0 + j] * er;
+        const float lq = fmaxf(ltab[w0 + j] + lr, LOG_EPS);
+        const float lm = __logf(0.5f * (pv[j] + q) + KL_EPS);
+        jsp += pv[j] * (lp[j] - lm) + q * (lq - lm);
+      }
+    }
+  }
+  if (want_js) jsp = warp_sum(jsp);
+  if (lane == 0) {
+    jsr[s] = jsp;
+    if (s == 0) { res[0] = ea; res[1] = eb; }
+  }
+  if (active && A.prob[k]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = ((s * NV + i) * 32 + lane) * 4;
+      if (e < HW) *reinterpret_cast<float4*>(A.prob[k] + off + e) = x[i];
+    }
+  }
+  __syncthreads();   // #3: per-plane results complete
+  if (!active || s != 0 || lane != 0) continue;
+  float js = 0.f;
+  for (int q = 0; q < P.wpp; ++q) js += jsr[q];
+  js *= 0.5f;
+  if (A.ab[k]) { A.ab[k][bj * 2 + 0] = ea; A.ab[k][bj * 2 + 1] = eb; }
+  if (A.js[k]) A.js[k][bj] = js;
+  if (ks != P.np - 1 && P.seq) continue;     // sequential mode: combine after the last plane
+  if (ks != 0 && !P.seq) continue;
+  // one leader combines the planes (models/margipose_model.py:254-261)
+  float pa[3] = {0.f, 0.f, 0.f}, pb[3] = {0.f, 0.f, 0.f}, pj[3] = {0.f, 0.f, 0.f};
+  for (int q = 0; q < P.np; ++q) {
+    const int slot_q = g * P.np + q;
+    const float* rq = sm + nslots * 2 * (W + H) + nslots * P.wpp * 5 + slot_q * 2;
+    const float* jq = sm + nslots * 2 * (W + H) + nslots * P.wpp * 4 + slot_q * P.wpp;
+    float t = 0.f;
+    for (int u = 0; u < P.wpp; ++u) t += jq[u];
+    pa[P.pid[q]] = rq[0]; pb[P.pid[q]] = rq[1]; pj[P.pid[q]] = 0.5f * t;
+  }
+  const float px = pa[0], py = pb[0], pz = 0.5f * (pa[1] + pb[2]);
+  if (A.coords) { A.coords[bj * 3 + 0] = px; A.coords[bj * 3 + 1] = py; A.coords[bj * 3 + 2] = pz; }
+  if (A.loss && A.target) {
+    const float dx = px - tx, dy = py - ty, dz = pz - tz;
+    float l;
+    if (is3d) l = pj[0] + pj[1] + pj[2] + sqrtf(dx * dx + dy * dy + dz * dz);
+    else l = pj[0] + sqrtf(dx * dx + dy * dy);
+    A.loss[bj] = A.accumulate ? A.loss[bj] + l : l;
+  }
+  }
+}
+
+template <int NV, bool PROJECT>
+__global__ void __launch_bounds__(512, 2) tail_bwd_warp_kernel(const BwdArgs A, const WarpPlan P) {
+  extern __shared__ float sm[];
+  const int W = A.g.W, H = A.g.H, HW = A.g.HW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nslots = P.groups * P.np;
+  const int nseq = P.seq ? P.np : 1;
+  for (int it = 0; it < nseq; ++it) {
+  const int slot = P.seq ? it : warp / P.wpp;
+  const int s = P.seq ? warp : warp - slot * P.wpp;
+  const int g = slot / P.np, ks = slot - g * P.np;
+  const int k = P.pid[ks];
+  const int bj = blockIdx.x * P.groups + g;
+  const bool active = bj < P.BJ;
+  float* tab = sm + slot * (W + H);
+  float* red = sm + nslots * (W + H) + slot * P.wpp;
+
+  float wjs = 0.f, cc = 0.f, cr = 0.f, mc = 0.f, mr = 0.f;
+  bool want_js = false;
+  if (active) {
+    const int b = bj / A.J;
+    const bool is3d = A.valid_depth ? (A.valid_depth[b] != 0) : true;
+    if (A.coef[k]) {
+      wjs = A.coef[k][bj * 3 + 0]; cc = A.coef[k][bj * 3 + 1]; cr = A.coef[k][bj * 3 + 2];
+      mc = A.mu[k] ? A.mu[k][bj * 2 + 0] : 0.f;
+      mr = A.mu[k] ? A.mu[k][bj * 2 + 1] : 0.f;
+      want_js = A.mu[k] != nullptr;
+    } else if (A.target) {
+      const float tx = A.target[bj * 3 + 0], ty = A.target[bj * 3 + 1], tz = A.target[bj * 3 + 2];
+      const float w = A.w[bj];
+      const float dx = A.coords[bj * 3 + 0] - tx, dy = A.coords[bj * 3 + 1] - ty;
+      const float dz = is3d ? A.coords[bj * 3 + 2] - tz : 0.f;
+      const float inv = w / sqrtf(dx * dx + dy * dy + dz * dz);   // infinite at 0, like dsntnn.py:149-150
+      mc = (k == 1) ? tz : tx;
+      mr = (k == 2) ? tz : ty;
+      wjs = (A.pixelwise && (k == 0 || is3d)) ? w : 0.f;
+      cc = (k == 0) ? dx * inv : (k == 1 ? 0.5f * dz * inv : 0.f);
+      cr = (k == 0) ? dy * inv : (k == 2 ? 0.5f * dz * inv : 0.f);
+      want_js = wjs != 0.f;
+    }
+  }
+  const size_t off = (size_t)bj * HW;
+  float4 p[NV], d[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = ((s * NV + i) * 32 + lane) * 4;
+    const bool ok = active && e < HW;
+    p[i] = ok ? __ldg(reinterpret_cast<const float4*>(A.prob[k] + off + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    d[i] = (ok && A.gup[k]) ? __ldg(reinterpret_cast<const float4*>(A.gup[k] + off + e))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float ginv = 0.f;
+  if (want_js) {
+    float sc = 0.f, sr = 0.f;
+    for (int i = lane; i < W; i += 32) {
+      const float dd = centre(i, A.g.cw_step, A.g.cw_first) - mc;
+      const float ev = expf(__fmul_rn(__fmul_rn(dd, dd), A.g.kw));
+      sc += ev;
+      if (s == 0) tab[i] = ev;
+    }
+    for (int i = lane; i < H; i += 32) {
+      const float dd = centre(i, A.g.ch_step, A.g.ch_first) - mr;
+      const float ev = expf(__fmul_rn(__fmul_rn(dd, dd), A.g.kh));
+      sr += ev;
+      if (s == 0) tab[W + i] = ev;
+    }
+    ginv = 1.0f / (warp_sum(sc) * warp_sum(sr) + KL_EPS);
+  }
+  __syncthreads();   // #1
+  float part = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = ((s * NV + i) * 32 + lane) * 4;
+    if (e < HW) {
+      const int h = e / W, w0 = e - h * W;
+      const float lin_r = cr * centre(h, A.g.ch_step, A.g.ch_first);
+      const float er = want_js ? tab[W + h] * ginv : 0.f;
+      const float pv[4] = {p[i].x, p[i].y, p[i].z, p[i].w};
+      float dv[4] = {d[i].x, d[i].y, d[i].z, d[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        dv[j] += cc * centre(w0 + j, A.g.cw_step, A.g.cw_first) + lin_r;
+        if (want_js) {
+          const float q = tab[w0 + j] * er;
+          const float mm = 0.5f * (pv[j] + q);
+          dv[j] += wjs * 0.5f * (__logf(pv[j] + KL_EPS) - __logf(mm + KL_EPS) +
+                                 __fdividef(pv[j], pv[j] + KL_EPS) - __fdividef(mm, mm + KL_EPS));
+        }
+        part += pv[j] * dv[j];
+      }
+      d[i] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    }
+  }
+  if (PROJECT) {
+    part = warp_sum(part);
+    if (lane == 0) red[s] = part;
+    __syncthreads();   // #2
+    part = 0.f;
+    for (int q = 0; q < P.wpp; ++q) part += red[q];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      d[i].x = p[i].x * (d[i].x - part); d[i].y = p[i].y * (d[i].y - part);
+      d[i].z = p[i].z * (d[i].z - part); d[i].w = p[i].w * (d[i].w - part);
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = ((s * NV + i) * 32 + lane) * 4;
+      if (e < HW) *reinterpret_cast<float4*>(A.out[k] + off + e) = d[i];
+    }
+  }
+  if (!PROJECT && P.seq) __syncthreads();
+  }
+}
+
+// Chooses warps per plane / pairs per CTA for the warp-sliced kernels; false -> use the block kernels.
+bool plan_warps(int HW, int np, int BJ, WarpPlan* P, int* nv) {
+  if (np < 1) return false;
+  const int vecs = HW / 4;
+  P->np = np;
+  P->BJ = BJ;
+  // Few float4 per lane (NV <= 4) keeps the register count low enough for ~30 resident warps per SM;
+  // planes run side by side when np * wpp fits in 16 warps, otherwise one plane at a time.
+  for (int cap = 4; cap <= 8; cap += 4) {
+    for (int wpp = 1; wpp <= 16; ++wpp) {
+      const int need = (vecs + wpp * 32 - 1) / (wpp * 32);
+      if (need > cap) continue;
+      P->wpp = wpp;
+      *nv = need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : need <= 6 ? 6 : 8;
+      if (np * wpp <= 16) {
+        P->seq = 0;
+        int groups = 8 / (np * wpp);
+        if (groups < 1) groups = 1;
+        if (groups > 4) groups = 4;
+        P->groups = groups;
+      } else {
+        P->seq = 1;
+        P->groups = 1;
+      }
+      return true;
+    }
+  }
+  return false;
+}
+
+size_t warp_smem(const WarpPlan& P, int H, int W, bool fwd) {
+  const int nslots = P.groups * P.np;
+  return sizeof(float) * (size_t)(nslots * (fwd ? 2 : 1) * (W + H) + nslots * P.wpp * (fwd ? 5 : 1) +
+                                  (fwd ? nslots * 2 : 0));
+}
+
 Geom make_geom(int H, int W, double sigma) {
   Geom g;
   g.H = H; g.W = W; g.HW = H * W;
@@ -491,6 +845,23 @@ Geom make_geom(int H, int W, double sigma) {
 template <bool FROM_LOGITS>
 int launch_fwd(const FwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
   const int HW = A.g.HW;
+  if (vec4) {
+    WarpPlan P;
+    int np = 0, nv = 0;
+    for (int k = 0; k < 3; ++k)
+      if (A.in[k]) P.pid[np++] = k;
+    for (int k = np; k < 3; ++k) P.pid[k] = 0;
+    if (plan_warps(HW, np, BJ, &P, &nv)) {
+      const int threads = (P.seq ? 1 : P.groups * P.np) * P.wpp * 32;
+      const int blocks = (BJ + P.groups - 1) / P.groups;
+      const size_t smem = warp_smem(P, A.g.H, A.g.W, true);
+#define MP_FWDW(NV) tail_fwd_warp_kernel<NV, FROM_LOGITS><<<blocks, threads, smem, st>>>(A, P)
+      if (nv == 1) MP_FWDW(1); else if (nv == 2) MP_FWDW(2); else if (nv == 4) MP_FWDW(4);
+      else if (nv == 6) MP_FWDW(6); else MP_FWDW(8);
+#undef MP_FWDW
+      return MP_OK;
+    }
+  }
 #define MP_FWD(VEC, V) tail_fwd_kernel<VEC, V, FROM_LOGITS><<<BJ, NT, 0, st>>>(A)
   if (vec4) {
     const int v = (HW / 4 + NT - 1) / NT;
@@ -514,6 +885,23 @@ int launch_fwd(const FwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
 template <bool PROJECT>
 int launch_bwd(const BwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
   const int HW = A.g.HW;
+  if (vec4) {
+    WarpPlan P;
+    int np = 0, nv = 0;
+    for (int k = 0; k < 3; ++k)
+      if (A.out[k]) P.pid[np++] = k;
+    for (int k = np; k < 3; ++k) P.pid[k] = 0;
+    if (plan_warps(HW, np, BJ, &P, &nv)) {
+      const int threads = (P.seq ? 1 : P.groups * P.np) * P.wpp * 32;
+      const int blocks = (BJ + P.groups - 1) / P.groups;
+      const size_t smem = warp_smem(P, A.g.H, A.g.W, false);
+#define MP_BWDW(NV) tail_bwd_warp_kernel<NV, PROJECT><<<blocks, threads, smem, st>>>(A, P)
+      if (nv == 1) MP_BWDW(1); else if (nv == 2) MP_BWDW(2); else if (nv == 4) MP_BWDW(4);
+      else if (nv == 6) MP_BWDW(6); else MP_BWDW(8);
+#undef MP_BWDW
+      return MP_OK;
+    }
+  }
 #define MP_BWD(VEC, V) tail_bwd_kernel<VEC, V, PROJECT><<<BJ, NT, 0, st>>>(A)
   if (vec4) {
     const int v = (HW / 4 + NT - 1) / NT;

@@ -309,6 +309,7 @@ class Engine:
         self.model, self.n, self.h, self.w, self.training, self.device = model, n, h, w, training, device
         self.bank, self.L = model._bank, model._layers
         self._bufs = []
+        self._keep = []
         self.streams = [torch.cuda.Stream(device=device) for _ in range(3)]
         # one auxiliary stream per lane: weight gradients (nothing downstream waits for them) and the
         # shortcut conv of a block run beside the lane's dependent chain
@@ -671,7 +672,7 @@ class Engine:
             arr = (ctypes.c_void_p * 4)(*([x.data_ptr() for x in terms] + [None] * (4 - len(terms))))
             bsegs.append(('serial', [self._call('mp_add_bf16', ctypes.byref(arr), len(terms), d_inp.data_ptr(),
                                                 d_inp.numel())]))
-            self._bufs.append(arr)
+            self._keep.append(arr)
             d_next = d_inp
         # ---- stem backward
         ops = []
