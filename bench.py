@@ -230,31 +230,30 @@ def run_b200(args):
     h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
     d2h = 4
 
-    # roofline of the dominant kernel: every mp_conv_igemm launch of one step, timed alone
+    # roofline of the dominant kernel: every mp_conv_igemm launch of one step (fprop + dgrad), each
+    # alone on the GPU, in program order, replayed from a CUDA graph and timed with CUDA events
     roof = None
     if rank == 0:
         eng = model.engine_for(B, RES, RES, True)
-        eng.stats.zero_()
-        stats = eng.time_ops(eng.fwd)
-        for name, rec in eng.time_ops(eng.bwd).items():
-            r = stats.setdefault(name, [0, 0.0, 0.0])
-            r[0] += rec[0]; r[1] += rec[1]; r[2] += rec[2]
-        torch.cuda.synchronize(dev)
         peak_tf, peak_bw, src = peaks()
-        n, t_ms, fl = stats['mp_conv_igemm']
+        classes = {}
+        for name in ('mp_conv_igemm', 'mp_conv_wgrad', 'mp_bn_fwd', 'mp_bn_bwd_reduce', 'mp_bn_bwd_apply'):
+            classes[name] = eng.time_kernel_class(name)
+        n, t_ms, fl = classes['mp_conv_igemm']
         achieved = fl / (t_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'igemm_traffic.json')
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get('dram_bytes_per_launch')
-        roof = {'bound': 'tensor', 'kernel': 'igemm_kernel (mp_conv_igemm, fprop+dgrad)', 'achieved': achieved,
+        wn, wt, wf = classes['mp_conv_wgrad']
+        roof = {'bound': 'tensor', 'kernel': 'igemm_kernel (mp_conv_igemm: conv fprop + dgrad)', 'achieved': achieved,
                 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': traffic,
-                'peak_source': src + ' bf16 sustained', 'launches_per_step': n,
+                'traffic_note': 'DRAM bytes of the 128->128 3x3 @32x32 launch (profiles/r01_igemm_ncu.md)',
+                'peak_source': src + ' bf16 sustained (MEASURED_PEAKS.json)', 'launches_per_step': n,
                 'avg_launch_us': 1e3 * t_ms / n, 'flops_per_launch': fl / n,
-                'kernel_time_share': {k: v[1] for k, v in stats.items()},
-                'wgrad_tflops': (stats['mp_conv_wgrad'][2] / (stats['mp_conv_wgrad'][1] * 1e-3) / 1e12)
-                if 'mp_conv_wgrad' in stats else None}
+                'serial_ms_per_step': {k: v[1] for k, v in classes.items()},
+                'wgrad_tflops': wf / (wt * 1e-3) / 1e12 if wn else None}
 
     if rank != 0:
         if world > 1:

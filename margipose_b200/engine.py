@@ -726,29 +726,34 @@ class Engine:
                 for s in self.streams:
                     cur.wait_stream(s)
 
-    def time_ops(self, segs):
-        """Runs `segs` serially on the current stream with a CUDA event pair around every op and
-        returns {kernel name: [launches, total ms, total algorithmic flops]} -- the per-kernel
-        durations bench.py's roofline uses (lanes are NOT overlapped here, so each duration is
-        that kernel alone on the GPU)."""
+    def time_kernel_class(self, name, reps=3):
+        """GPU time of every launch of C-ABI entry point `name` in one step (forward + backward
+        programs), run back to back in program order on one stream and replayed from a CUDA graph --
+        i.e. each kernel alone on the GPU, no host overhead.  Returns (launches, total ms per step,
+        total algorithmic flops per step)."""
         ops = []
-        for kind, body in segs:
-            for lane in ([body] if kind == 'serial' else body):
-                ops += lane
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops]
-        for op, (e0, e1) in zip(ops, evs):
-            e0.record()
+        for segs in (self.fwd, self.bwd):
+            for kind, body in segs:
+                for lane in ([body] if kind == 'serial' else body):
+                    ops += [op for op in lane if getattr(op, 'name', 'tail') == name]
+        if not ops:
+            return 0, 0.0, 0.0
+        for op in ops:
             op()
-            e1.record()
         torch.cuda.synchronize(self.device)
-        out = {}
-        for op, (e0, e1) in zip(ops, evs):
-            name = getattr(op, 'name', 'tail')
-            rec = out.setdefault(name, [0, 0.0, 0.0])
-            rec[0] += 1
-            rec[1] += e0.elapsed_time(e1)
-            rec[2] += getattr(op, 'flops', 0.0)
-        return out
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for op in ops:
+                op()
+        g.replay()
+        torch.cuda.synchronize(self.device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize(self.device)
+        return len(ops), e0.elapsed_time(e1) / reps, sum(getattr(op, 'flops', 0.0) for op in ops)
 
     def launches(self, segs=None):
         out = 0
