@@ -14,8 +14,8 @@
 namespace {
 
 constexpr int MAXT = 256;
-constexpr int U = 4;    // pixels in flight per thread (forward, backward reduce)
-constexpr int UA = 2;   // ... in the backward apply pass (more coefficients live)
+constexpr int U = 2;    // pixels per thread per iteration (forward, backward reduce); the NEXT iteration's
+constexpr int UA = 1;   // loads are issued before the current one is consumed (software pipelining)
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
   float2 f;
@@ -150,53 +150,61 @@ __global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const mp_bn_args A) {
   }
 
   const long long ppb = (long long)blockDim.y * U;
-  for (long long base = (long long)blockIdx.x * ppb; base < A.M; base += (long long)gridDim.x * ppb) {
-  const long long p0 = base + threadIdx.y;
-  uint4 la[U], lb[U];
+  const long long stride = (long long)gridDim.x * ppb;
+  auto load = [&](long long p0, uint4 (&la)[U], uint4 (&lb)[U]) {
 #pragma unroll
-  for (int i = 0; i < U; ++i) {
-    const long long pix = p0 + (long long)i * blockDim.y;
-    if (pix < A.M) {
+    for (int i = 0; i < U; ++i) {
+      const long long pix = p0 + (long long)i * blockDim.y;
+      if (pix < A.M) {
+        const long long off = pix * A.Cp + c0;
+        la[i] = ldg16(A.a.y, off);
+        if (has_b) lb[i] = ldg16(A.b.y, off);
+        else if (A.res) lb[i] = ldg16(A.res, off);
+      }
+    }
+  };
+  uint4 la[U], lb[U], na[U], nb[U];
+  long long base = (long long)blockIdx.x * ppb;
+  if (base < A.M) load(base + threadIdx.y, la, lb);
+  for (; base < A.M; base += stride) {
+    if (base + stride < A.M) load(base + stride + threadIdx.y, na, nb);
+    const long long p0 = base + threadIdx.y;
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const long long pix = p0 + (long long)i * blockDim.y;
+      if (pix >= A.M) break;
       const long long off = pix * A.Cp + c0;
-      la[i] = ldg16(A.a.y, off);
-      if (has_b) lb[i] = ldg16(A.b.y, off);
-      else if (A.res) lb[i] = ldg16(A.res, off);
+      float z[8], t[8];
+      unpack8(la[i], z);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        z[j] = fmaf(z[j], sa[j], ha[j]);
+        if (A.relu_a) z[j] = fmaxf(z[j], 0.f);
+      }
+      if (has_b) {
+        unpack8(lb[i], t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] += fmaf(t[j], sb[j], hb[j]);
+      } else if (A.res) {
+        unpack8(lb[i], t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] += t[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (A.relu_out) z[j] = fmaxf(z[j], 0.f);
+        if (c0 + j >= A.C) z[j] = 0.f;
+      }
+      if (A.out) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.out) + off) = pack8(z);
+      if (A.out_nchw) {
+        const long long n = pix / A.HW, hw = pix - n * A.HW;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < A.C) A.out_nchw[(n * A.C + c0 + j) * A.HW + hw] = z[j];
+      }
     }
-  }
 #pragma unroll
-  for (int i = 0; i < U; ++i) {
-    const long long pix = p0 + (long long)i * blockDim.y;
-    if (pix >= A.M) break;
-    const long long off = pix * A.Cp + c0;
-    float z[8], t[8];
-    unpack8(la[i], z);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      z[j] = fmaf(z[j], sa[j], ha[j]);
-      if (A.relu_a) z[j] = fmaxf(z[j], 0.f);
-    }
-    if (has_b) {
-      unpack8(lb[i], t);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] += fmaf(t[j], sb[j], hb[j]);
-    } else if (A.res) {
-      unpack8(lb[i], t);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) z[j] += t[j];
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (A.relu_out) z[j] = fmaxf(z[j], 0.f);
-      if (c0 + j >= A.C) z[j] = 0.f;
-    }
-    if (A.out) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.out) + off) = pack8(z);
-    if (A.out_nchw) {
-      const long long n = pix / A.HW, hw = pix - n * A.HW;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (c0 + j < A.C) A.out_nchw[(n * A.C + c0 + j) * A.HW + hw] = z[j];
-    }
-  }
+    for (int i = 0; i < U; ++i) { la[i] = na[i]; lb[i] = nb[i]; }
   }
 }
 
@@ -274,34 +282,42 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_reduce_kernel(const mp_bn_args
   for (int j = 0; j < 32; ++j) acc[j] = 0.f;
 
   const long long ppb = (long long)blockDim.y * U;
-  for (long long base = (long long)blockIdx.x * ppb; base < A.M; base += (long long)gridDim.x * ppb) {
-  const long long p0 = base + threadIdx.y;
-  LoadsX<NCHW> L[U];
+  const long long stride = (long long)gridDim.x * ppb;
+  auto load = [&](long long p0, LoadsX<NCHW> (&L)[U]) {
 #pragma unroll
-  for (int i = 0; i < U; ++i) {
-    const long long pix = p0 + (long long)i * blockDim.y;
-    if (pix < A.M) load_pixel<NCHW>(A, has_b, pix, c0, L[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < U; ++i) {
-    const long long pix = p0 + (long long)i * blockDim.y;
-    if (pix >= A.M) break;
-    float dza[8], dzb[8], ya[8], yb[8];
-    grads_at<NCHW>(A, L[i], sa, ha, c0, dza, dzb, ya);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[j] += dza[j];
-      acc[8 + j] = fmaf(dza[j], ya[j], acc[8 + j]);
+    for (int i = 0; i < U; ++i) {
+      const long long pix = p0 + (long long)i * blockDim.y;
+      if (pix < A.M) load_pixel<NCHW>(A, has_b, pix, c0, L[i]);
     }
-    if (has_b) {
-      unpack8(L[i].yb, yb);
+  };
+  LoadsX<NCHW> L[U], Ln[U];
+  long long base = (long long)blockIdx.x * ppb;
+  if (base < A.M) load(base + threadIdx.y, L);
+  for (; base < A.M; base += stride) {
+    if (base + stride < A.M) load(base + stride + threadIdx.y, Ln);
+    const long long p0 = base + threadIdx.y;
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const long long pix = p0 + (long long)i * blockDim.y;
+      if (pix >= A.M) break;
+      float dza[8], dzb[8], ya[8], yb[8];
+      grads_at<NCHW>(A, L[i], sa, ha, c0, dza, dzb, ya);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        acc[16 + j] += dzb[j];
-        acc[24 + j] = fmaf(dzb[j], yb[j], acc[24 + j]);
+        acc[j] += dza[j];
+        acc[8 + j] = fmaf(dza[j], ya[j], acc[8 + j]);
+      }
+      if (has_b) {
+        unpack8(L[i].yb, yb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[16 + j] += dzb[j];
+          acc[24 + j] = fmaf(dzb[j], yb[j], acc[24 + j]);
+        }
       }
     }
-  }
+#pragma unroll
+    for (int i = 0; i < U; ++i) L[i] = Ln[i];
   }
   // block reduction over the pixel rows, all threads take part; then one atomic per (sum, channel)
   const int G = blockDim.x, PY = blockDim.y;
@@ -398,34 +414,42 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_kernel(const mp_bn_args 
   }
 
   const long long ppb = (long long)blockDim.y * UA;
-  for (long long base = (long long)blockIdx.x * ppb; base < A.M; base += (long long)gridDim.x * ppb) {
-  const long long p0 = base + threadIdx.y;
-  LoadsX<NCHW> L[UA];
+  const long long stride = (long long)gridDim.x * ppb;
+  auto load = [&](long long p0, LoadsX<NCHW> (&L)[UA]) {
 #pragma unroll
-  for (int i = 0; i < UA; ++i) {
-    const long long pix = p0 + (long long)i * blockDim.y;
-    if (pix < A.M) load_pixel<NCHW>(A, has_b, pix, c0, L[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < UA; ++i) {
-    const long long pix = p0 + (long long)i * blockDim.y;
-    if (pix >= A.M) break;
-    const long long off = pix * A.Cp + c0;
-    float dza[8], dzb[8], ya[8], o[8];
-    grads_at<NCHW>(A, L[i], sa, ha, c0, dza, dzb, ya);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = (c0 + j < A.C) ? fmaf(sa[j], dza[j], fmaf(ka[j], ya[j], ca[j])) : 0.f;
-    if (A.a.dy) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.a.dy) + off) = pack8(o);
-    if (has_b) {
-      float yb[8];
-      unpack8(L[i].yb, yb);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (c0 + j < A.C) ? fmaf(sb[j], dzb[j], fmaf(kb[j], yb[j], cb[j])) : 0.f;
-      if (A.b.dy) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.b.dy) + off) = pack8(o);
-    } else if (A.dres) {
-      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.dres) + off) = pack8(dzb);
+    for (int i = 0; i < UA; ++i) {
+      const long long pix = p0 + (long long)i * blockDim.y;
+      if (pix < A.M) load_pixel<NCHW>(A, has_b, pix, c0, L[i]);
     }
-  }
+  };
+  LoadsX<NCHW> L[UA], Ln[UA];
+  long long base = (long long)blockIdx.x * ppb;
+  if (base < A.M) load(base + threadIdx.y, L);
+  for (; base < A.M; base += stride) {
+    if (base + stride < A.M) load(base + stride + threadIdx.y, Ln);
+    const long long p0 = base + threadIdx.y;
+#pragma unroll
+    for (int i = 0; i < UA; ++i) {
+      const long long pix = p0 + (long long)i * blockDim.y;
+      if (pix >= A.M) break;
+      const long long off = pix * A.Cp + c0;
+      float dza[8], dzb[8], ya[8], o[8];
+      grads_at<NCHW>(A, L[i], sa, ha, c0, dza, dzb, ya);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (c0 + j < A.C) ? fmaf(sa[j], dza[j], fmaf(ka[j], ya[j], ca[j])) : 0.f;
+      if (A.a.dy) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.a.dy) + off) = pack8(o);
+      if (has_b) {
+        float yb[8];
+        unpack8(L[i].yb, yb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (c0 + j < A.C) ? fmaf(sb[j], dzb[j], fmaf(kb[j], yb[j], cb[j])) : 0.f;
+        if (A.b.dy) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.b.dy) + off) = pack8(o);
+      } else if (A.dres) {
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.dres) + off) = pack8(dzb);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < UA; ++i) L[i] = Ln[i];
   }
 }
 
