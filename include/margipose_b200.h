@@ -303,6 +303,9 @@ MP_API int mp_sgd_step(float* param, const float* grad, float* momentum_buf, int
 
 /* Tunables for experiments (name -> value); returns MP_ERR_ARG for unknown names.
  *   "igemm_smem"  : shared-memory budget per CTA of mp_conv_igemm in bytes (default 115712)
+ *   "igemm_cluster": max thread-block-cluster size of mp_conv_igemm (1, 2 or 4; default 1): the CTAs of a cluster
+ *                   each fetch 1/cluster of the weight tile and TMA-multicast it to the others
+ *   "igemm_split_n": mp_conv_igemm halves its N tile when it would launch fewer CTAs than this (default 100)
  *   "wgrad_ctas"  : target CTA count of mp_conv_wgrad (default 148)
  *   "wgrad_taps"  : filter taps accumulated per CTA (default 1)
  *   "wgrad_kp"    : pixels per pipeline stage of mp_conv_wgrad (default 128)

@@ -20,11 +20,15 @@ const char* mp_last_error(void) { return g_err; }
 // ---- tunables (experiments only; defaults are what the benchmarks use)
 #include <string.h>
 void mp_set_igemm_smem(long long v);
+void mp_set_igemm_split_n(long long v);
+void mp_set_igemm_cluster(long long v);
 void mp_set_wgrad_tunable(int which, long long v);
 
 extern "C" int mp_set_tunable(const char* name, int64_t value) {
   if (!name) { mp_set_error("mp_set_tunable: null name"); return MP_ERR_ARG; }
   if (!strcmp(name, "igemm_smem")) { mp_set_igemm_smem(value); return MP_OK; }
+  if (!strcmp(name, "igemm_split_n")) { mp_set_igemm_split_n(value); return MP_OK; }
+  if (!strcmp(name, "igemm_cluster")) { mp_set_igemm_cluster(value); return MP_OK; }
   if (!strcmp(name, "wgrad_ctas")) { mp_set_wgrad_tunable(0, value); return MP_OK; }
   if (!strcmp(name, "wgrad_taps")) { mp_set_wgrad_tunable(1, value); return MP_OK; }
   if (!strcmp(name, "wgrad_dbg")) { mp_set_wgrad_tunable(2, value); return MP_OK; }

@@ -31,6 +31,7 @@ struct IgemmParams {
   int tile_w, tile_rows, tiles_w, tiles_h;
   int out_h, out_w;
   int n_tile, stages, b_stage_bytes, stage_tx, tmem_cols;
+  int cluster;   // CTAs per cluster along the M tiles (1, 2 or 4): each loads 1/cluster of the weight tile, multicast to all
   __nv_bfloat16* out;
   const __nv_bfloat16* res;
   long long out_sn, out_sh, out_sw;
@@ -72,10 +73,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   const int w0 = tw * P.tile_w, h0 = th * P.tile_rows;
   const int n0 = blockIdx.y * P.n_tile;
 
+  const int C = P.cluster;
+  const uint32_t crank = C > 1 ? tc::cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << C) - 1);
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
       tc::mbar_init(&full[s], 1);
-      tc::mbar_init(&empty[s], 1);
+      tc::mbar_init(&empty[s], C);   // every CTA of the cluster must have consumed a slot peers multicast into
     }
     tc::mbar_init(tmem_full, 1);
     tc::mbar_fence_init();
@@ -86,6 +90,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   if (warp == 1) tc::tmem_alloc(tmem_holder, P.tmem_cols);
   tc::tc_fence_before();
   __syncthreads();
+  if (C > 1) tc::cluster_sync_all();   // peers' barriers are initialised before anyone signals them
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_holder;
 
@@ -101,7 +106,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           tc::mbar_arrive_expect_tx(&full[s], P.stage_tx);
           tc::tma_load_5d(tmA, &full[s], sA + (size_t)s * A_STAGE_BYTES, tap.c0 + cb * 64, w0 + tap.dw,
                           tap.p, h0 + tap.dh, img);
-          tc::tma_load_2d(&tmB, &full[s], sB + (size_t)s * P.b_stage_bytes, tap.koff + cb * 64, n0);
+          if (C == 1) {
+            tc::tma_load_2d(&tmB, &full[s], sB + (size_t)s * P.b_stage_bytes, tap.koff + cb * 64, n0);
+          } else {   // my 1/C of the weight tile goes to every CTA of the cluster
+            const int rows = P.n_tile / C;
+            tc::tma_load_2d_multicast(&tmB, &full[s], sB + (size_t)s * P.b_stage_bytes + (size_t)crank * rows * 128,
+                                      tap.koff + cb * 64, n0 + (int)crank * rows, cmask);
+          }
           if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
@@ -121,7 +132,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         for (int k = 0; k < 4; ++k)   // 4 x (K = 16 bf16 = 32 bytes inside the 128B swizzle atom)
           tc::mma_bf16(tmem, tc::desc_kmajor_sw128(a + k * 32), tc::desc_kmajor_sw128(b + k * 32), idesc,
                        (kb | k) != 0);
-        tc::mma_commit(&empty[s]);   // frees the smem slot once these MMAs have read it
+        if (C == 1) tc::mma_commit(&empty[s]);   // frees the smem slot once these MMAs have read it
+        else tc::mma_commit_multicast(&empty[s], cmask);
         if (++s == stages) { s = 0; ph ^= 1; }
       }
       tc::mma_commit(tmem_full);
@@ -226,6 +238,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (C > 1) tc::cluster_sync_all();   // nobody leaves while peers may still signal its barriers
   if (warp == 1) tc::tmem_dealloc(tmem, P.tmem_cols);
 }
 
@@ -264,11 +277,22 @@ int mp_pick_tile(int out_h, int out_w, int max_pix, int* tile_w, int* tile_rows)
 
 void mp_set_igemm_smem(long long v) { g_igemm_smem = v; }
 
+long long g_igemm_cluster = 1;    // max CTAs per cluster sharing a multicast weight tile (measured: no gain, the
+                                  // kernel is bound by shared-memory bandwidth, not by L2 -> SM traffic)
+void mp_set_igemm_cluster(long long v) { g_igemm_cluster = v; }
+long long g_igemm_split_n = 100;   // split N in two when the launch would have fewer CTAs than this
+void mp_set_igemm_split_n(long long v) { g_igemm_split_n = v; }
+
 static void igemm_grid(const mp_igemm_args* a, int* tile_w, int* tile_rows, int* tiles_w, int* tiles_h, int* n_tile) {
   mp_pick_tile(a->out_h, a->out_w, 128, tile_w, tile_rows);
   *tiles_w = (a->out_w + *tile_w - 1) / *tile_w;
   *tiles_h = (a->out_h + *tile_rows - 1) / *tile_rows;
   *n_tile = a->w_rows <= 256 ? (int)a->w_rows : 256;
+  // Small pixel grids (e.g. 16x16 maps at batch 32 = 64 M-tiles) leave most of the 148 SMs idle:
+  // give each M-tile two CTAs with half the output channels each (the A tile is then fetched twice,
+  // from L2, which is cheaper than idle tensor cores).
+  const long long ctas = (long long)a->n_img * *tiles_h * *tiles_w * (a->w_rows / *n_tile);
+  if (ctas < g_igemm_split_n && *n_tile >= 128 && (*n_tile / 2) % 32 == 0) *n_tile /= 2;
 }
 
 extern "C" int mp_conv_igemm_ctas(const mp_igemm_args* a) {
@@ -346,6 +370,12 @@ extern "C" int mp_conv_igemm(const mp_igemm_args* a, void* stream) {
                                        : a->n_img * P.tiles_h * P.tiles_w * (int)(a->w_rows / P.n_tile);
   }
 
+  {   // cluster size: M tiles must split evenly, weight-tile slices must stay 1024-byte aligned
+    const long long m_tiles = (long long)a->n_img * P.tiles_h * P.tiles_w;
+    int c = (int)g_igemm_cluster;
+    while (c > 1 && (m_tiles % c != 0 || (P.n_tile / c) % 8 != 0 || P.n_tile % c != 0)) c /= 2;
+    P.cluster = c < 1 ? 1 : c;
+  }
   CUtensorMap tmA0, tmA1, tmB;
   const uint32_t boxA[5] = {64, (uint32_t)P.tile_w, 1, (uint32_t)P.tile_rows, 1};
   int rc = view_to_tmap(&tmA0, a->src[0], boxA, "mp_conv_igemm src[0]");
@@ -360,7 +390,7 @@ extern "C" int mp_conv_igemm(const mp_igemm_args* a, void* stream) {
     MP_CHECK_ARG(mp_aligned16(a->wmat), "mp_conv_igemm: wmat not 16-byte aligned");
     const uint64_t dims[2] = {(uint64_t)a->w_k, (uint64_t)a->w_rows};
     const uint64_t strides[2] = {2, (uint64_t)a->w_k * 2};
-    const uint32_t box[2] = {64, (uint32_t)P.n_tile};
+    const uint32_t box[2] = {64, (uint32_t)(P.n_tile / P.cluster)};
     rc = tc::encode_tmap(&tmB, a->wmat, 2, dims, strides, box);
     if (rc != MP_OK) return rc;
   }
@@ -371,7 +401,19 @@ extern "C" int mp_conv_igemm(const mp_igemm_args* a, void* stream) {
     g_attr_set = true;
   }
   dim3 grid((unsigned)(a->n_img * P.tiles_h * P.tiles_w), (unsigned)(a->w_rows / P.n_tile));
-  igemm_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, P);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = P.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel, tmA0, tmA1, tmB, P));
   MP_CHECK_LAUNCH("mp_conv_igemm");
   return MP_OK;
 }

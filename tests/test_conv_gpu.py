@@ -24,3 +24,17 @@ def test_conv_dgrad_and_wgrad(case):
 def test_fused_block_dgrad(stride, tr):
     K.DEV = 'cuda'
     K.check_fused_block_dgrad(stride, tr)
+
+
+@pytest.mark.parametrize('cluster', [2, 4])
+def test_conv_forward_with_multicast_clusters(cluster):
+    """The weight tile can be fetched once per thread-block cluster and TMA-multicast to its CTAs
+    (tunable igemm_cluster); results must not depend on it."""
+    from margipose_b200._lib import lib
+    K.DEV = 'cuda'
+    try:
+        assert lib().mp_set_tunable(b'igemm_cluster', cluster) == 0
+        K.check_conv_forward_and_stats(K.CASES[0])
+        K.check_conv_dgrad_and_wgrad(K.CASES[1])
+    finally:
+        lib().mp_set_tunable(b'igemm_cluster', 1)
