@@ -109,6 +109,7 @@ MP_API int mp_make_gauss(const float* mu, float* out, int normalize, double sigm
  *              through c0 (0 or C) and the row parity through p.
  */
 #define MP_MAX_TAPS 10
+#define MP_MAX_GROUP 3   /* problems per grouped launch (the three HeatmapColumns of a stage) */
 
 typedef struct mp_view5 {
   const void* ptr;       /* bf16 */
@@ -166,6 +167,10 @@ typedef struct mp_igemm_args {
 } mp_igemm_args;
 
 MP_API int mp_conv_igemm(const mp_igemm_args* args, void* stream);
+/* n_problems (1..MP_MAX_GROUP) convolutions of identical geometry (taps, shapes, strides, flags) on different
+ * tensors in ONE launch (grid z = problem): the xy / zy / xz HeatmapColumns of a MargiPose stage
+ * (models/margipose_model.py:196-198) are three such problems at every layer.  args: contiguous array. */
+MP_API int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, void* stream);
 /* Number of CTAs (statistics arrivals) mp_conv_igemm launches for `args`. */
 MP_API int mp_conv_igemm_ctas(const mp_igemm_args* args);
 
@@ -187,6 +192,8 @@ typedef struct mp_wgrad_args {
 } mp_wgrad_args;
 
 MP_API int mp_conv_wgrad(const mp_wgrad_args* args, void* stream);
+/* n_problems weight gradients of identical geometry in one launch (see mp_conv_igemm_grouped). */
+MP_API int mp_conv_wgrad_grouped(const mp_wgrad_args* args, int n_problems, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * BatchNorm + activation + residual, forward and backward (nn.BatchNorm2d / nn.ReLU / `+` in
@@ -245,6 +252,11 @@ MP_API int mp_bn_fwd(const mp_bn_args* args, void* stream);
 /* backward = two launches: per-channel reductions, then the elementwise gradient. */
 MP_API int mp_bn_bwd_reduce(const mp_bn_args* args, void* stream);
 MP_API int mp_bn_bwd_apply(const mp_bn_args* args, void* stream);
+/* Grouped variants: n_problems (1..MP_MAX_GROUP) BatchNorm passes of identical shape and flags on different
+ * tensors in one launch (grid y = problem); args is a contiguous array. */
+MP_API int mp_bn_fwd_grouped(const mp_bn_args* args, int n_problems, void* stream);
+MP_API int mp_bn_bwd_reduce_grouped(const mp_bn_args* args, int n_problems, void* stream);
+MP_API int mp_bn_bwd_apply_grouped(const mp_bn_args* args, int n_problems, void* stream);
 
 /* nn.MaxPool2d(3, 2, 1) of the ResNet stem on bf16 NHWC; idx (N, H/2, W/2, C) uint8 records the
  * arg-max tap (first maximum in row-major window order, as ATen does) for the backward. */
@@ -303,13 +315,15 @@ MP_API int mp_sgd_step(float* param, const float* grad, float* momentum_buf, int
 
 /* Tunables for experiments (name -> value); returns MP_ERR_ARG for unknown names.
  *   "igemm_smem"  : shared-memory budget per CTA of mp_conv_igemm in bytes (default 115712)
- *   "igemm_cluster": max thread-block-cluster size of mp_conv_igemm (1, 2 or 4; default 1): the CTAs of a cluster
- *                   each fetch 1/cluster of the weight tile and TMA-multicast it to the others
+ *   "igemm_halo"  : 1 (default) = filter taps that differ only by their row shift share one activation box of
+ *                   tile_rows + 2 rows (fetched once, read through row-shifted descriptors); 0 = one box per tap
+ *   "igemm_pair"  : 1 = two CTAs of a cluster pair up on M=256 tcgen05.mma.cta_group::2 tiles, each loading half of
+ *                   every weight tile (when the M tiles pair up); 0 = one CTA per tile
  *   "igemm_split_n": mp_conv_igemm halves its N tile when it would launch fewer CTAs than this (default 100)
  *   "wgrad_ctas"  : target CTA count of mp_conv_wgrad (default 148)
- *   "wgrad_taps"  : filter taps accumulated per CTA (default 1)
+ *   "wgrad_halo"  : 1 (default) = up to three row-shifted taps per CTA share the A tile and one halo box of B
  *   "wgrad_kp"    : pixels per pipeline stage of mp_conv_wgrad (default 128)
- *   "wgrad_dbg"   : experiment switches (1 = skip the gradient atomics, 2 = issue MMAs twice, 4 = no MMA) */
+ *   "wgrad_dbg"   : experiment switches (1 = skip the gradient atomics, 4 = no MMA) */
 MP_API int mp_set_tunable(const char* name, int64_t value);
 
 #ifdef __cplusplus

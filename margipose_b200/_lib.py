@@ -93,12 +93,17 @@ def _signatures():
         'mp_euclid_bwd': (I, [P, P, P, P, I, I, P, P]),
         'mp_make_gauss': (I, [P, P, I, D, I, I, I, P]),
         'mp_conv_igemm': (I, [ctypes.POINTER(IgemmArgs), P]),
+        'mp_conv_igemm_grouped': (I, [ctypes.POINTER(IgemmArgs), I, P]),
         'mp_conv_igemm_ctas': (I, [ctypes.POINTER(IgemmArgs)]),
         'mp_conv_wgrad': (I, [ctypes.POINTER(WgradArgs), P]),
+        'mp_conv_wgrad_grouped': (I, [ctypes.POINTER(WgradArgs), I, P]),
         'mp_set_tunable': (I, [ctypes.c_char_p, ctypes.c_int64]),
         'mp_bn_fwd': (I, [ctypes.POINTER(BnArgs), P]),
         'mp_bn_bwd_reduce': (I, [ctypes.POINTER(BnArgs), P]),
         'mp_bn_bwd_apply': (I, [ctypes.POINTER(BnArgs), P]),
+        'mp_bn_fwd_grouped': (I, [ctypes.POINTER(BnArgs), I, P]),
+        'mp_bn_bwd_reduce_grouped': (I, [ctypes.POINTER(BnArgs), I, P]),
+        'mp_bn_bwd_apply_grouped': (I, [ctypes.POINTER(BnArgs), I, P]),
         'mp_maxpool_fwd': (I, [P, P, P, I, I, I, I, P]),
         'mp_maxpool_bwd': (I, [P, P, P, I, I, I, I, P]),
         'mp_axis_permute': (I, [P, P, I, I, I, I, I, P]),

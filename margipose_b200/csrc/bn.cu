@@ -14,6 +14,10 @@
 namespace {
 
 constexpr int MAXT = 256;
+
+struct BnGroup {   // problems of a grouped launch (blockIdx.y): same shapes and flags, different tensors
+  mp_bn_args a[MP_MAX_GROUP];
+};
 constexpr int U = 2;    // pixels per thread per iteration (forward, backward reduce); the NEXT iteration's
 constexpr int UA = 1;   // loads are issued before the current one is consumed (software pipelining)
 
@@ -119,7 +123,8 @@ __device__ __forceinline__ void affine(const mp_bn_args& A, const mp_bn_branch& 
 }
 
 // ------------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const mp_bn_args A) {
+__global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const __grid_constant__ BnGroup GRP) {
+  const mp_bn_args& A = GRP.a[blockIdx.y];
   const int c0 = threadIdx.x * 8;
   const bool has_b = A.b.y != nullptr;
   float sa[8], ha[8], sb[8], hb[8];
@@ -271,7 +276,8 @@ __device__ __forceinline__ void grads_at(const mp_bn_args& A, const LoadsX<NCHW>
 
 // sums layout per replica: [0] sum dz_a, [1] sum dz_a * y_a, [2] sum dz_b, [3] sum dz_b * y_b
 template <bool NCHW>
-__global__ void __launch_bounds__(MAXT, 2) bn_bwd_reduce_kernel(const mp_bn_args A) {
+__global__ void __launch_bounds__(MAXT, 2) bn_bwd_reduce_kernel(const __grid_constant__ BnGroup GRP) {
+  const mp_bn_args& A = GRP.a[blockIdx.y];
   __shared__ float red[32 * MAXT];
   const int cg = threadIdx.x, c0 = cg * 8;
   const bool has_b = A.b.y != nullptr;
@@ -394,7 +400,8 @@ __device__ __forceinline__ void bwd_coefs(const mp_bn_args& A, const mp_bn_branc
 }
 
 template <bool NCHW>
-__global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_kernel(const mp_bn_args A) {
+__global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_kernel(const __grid_constant__ BnGroup GRP) {
+  const mp_bn_args& A = GRP.a[blockIdx.y];
   const int c0 = threadIdx.x * 8;
   const bool has_b = A.b.y != nullptr;
   const bool first = blockIdx.x == 0 && threadIdx.y == 0;
@@ -499,36 +506,65 @@ void launch_dims(const mp_bn_args* a, dim3* grid, dim3* block, int u, int cap) {
 
 }  // namespace
 
+static bool same_shape(const mp_bn_args* x, const mp_bn_args* y) {
+  return x->M == y->M && x->C == y->C && x->Cp == y->Cp && x->HW == y->HW && x->training == y->training &&
+         x->relu_a == y->relu_a && x->relu_out == y->relu_out && x->stat_replicas == y->stat_replicas &&
+         (x->b.y == nullptr) == (y->b.y == nullptr) && (x->res == nullptr) == (y->res == nullptr) &&
+         (x->dout == nullptr) == (y->dout == nullptr) && (x->out_nchw == nullptr) == (y->out_nchw == nullptr);
+}
+
+static int make_group(const mp_bn_args* args, int n, const char* what, bool bwd, BnGroup* g) {
+  MP_CHECK_ARG(args, "%s: null args", what);
+  MP_CHECK_ARG(n >= 1 && n <= MP_MAX_GROUP, "%s: %d problems (1..%d)", what, n, MP_MAX_GROUP);
+  for (int i = 0; i < n; ++i) {
+    int rc = check_args(&args[i], what, bwd);
+    if (rc != MP_OK) return rc;
+    MP_CHECK_ARG(i == 0 || same_shape(&args[0], &args[i]), "%s: problem %d differs in shape", what, i);
+  }
+  for (int i = 0; i < MP_MAX_GROUP; ++i) g->a[i] = args[i < n ? i : 0];
+  return MP_OK;
+}
+
 extern "C" {
 
-int mp_bn_fwd(const mp_bn_args* a, void* stream) {
-  int rc = check_args(a, "mp_bn_fwd", false);
+int mp_bn_fwd(const mp_bn_args* a, void* stream) { return mp_bn_fwd_grouped(a, 1, stream); }
+int mp_bn_bwd_reduce(const mp_bn_args* a, void* stream) { return mp_bn_bwd_reduce_grouped(a, 1, stream); }
+int mp_bn_bwd_apply(const mp_bn_args* a, void* stream) { return mp_bn_bwd_apply_grouped(a, 1, stream); }
+
+int mp_bn_fwd_grouped(const mp_bn_args* args, int n, void* stream) {
+  BnGroup g;
+  int rc = make_group(args, n, "mp_bn_fwd", false, &g);
   if (rc != MP_OK) return rc;
   dim3 grid, block;
-  launch_dims(a, &grid, &block, U, 2 * 148);
-  bn_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*a);
+  launch_dims(args, &grid, &block, U, 2 * 148 / n);
+  grid.y = n;
+  bn_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(g);
   MP_CHECK_LAUNCH("mp_bn_fwd");
   return MP_OK;
 }
 
-int mp_bn_bwd_reduce(const mp_bn_args* a, void* stream) {
-  int rc = check_args(a, "mp_bn_bwd_reduce", true);
+int mp_bn_bwd_reduce_grouped(const mp_bn_args* args, int n, void* stream) {
+  BnGroup g;
+  int rc = make_group(args, n, "mp_bn_bwd_reduce", true, &g);
   if (rc != MP_OK) return rc;
   dim3 grid, block;
-  launch_dims(a, &grid, &block, U, 148);
-  if (a->dout) bn_bwd_reduce_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
-  else bn_bwd_reduce_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
+  launch_dims(args, &grid, &block, U, n > 1 ? 2 * 148 / n : 148);
+  grid.y = n;
+  if (args->dout) bn_bwd_reduce_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(g);
+  else bn_bwd_reduce_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(g);
   MP_CHECK_LAUNCH("mp_bn_bwd_reduce");
   return MP_OK;
 }
 
-int mp_bn_bwd_apply(const mp_bn_args* a, void* stream) {
-  int rc = check_args(a, "mp_bn_bwd_apply", true);
+int mp_bn_bwd_apply_grouped(const mp_bn_args* args, int n, void* stream) {
+  BnGroup g;
+  int rc = make_group(args, n, "mp_bn_bwd_apply", true, &g);
   if (rc != MP_OK) return rc;
   dim3 grid, block;
-  launch_dims(a, &grid, &block, UA, 2 * 148);
-  if (a->dout) bn_bwd_apply_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
-  else bn_bwd_apply_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(*a);
+  launch_dims(args, &grid, &block, UA, 2 * 148 / n);
+  grid.y = n;
+  if (args->dout) bn_bwd_apply_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(g);
+  else bn_bwd_apply_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(g);
   MP_CHECK_LAUNCH("mp_bn_bwd_apply");
   return MP_OK;
 }

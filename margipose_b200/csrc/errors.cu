@@ -21,18 +21,27 @@ const char* mp_last_error(void) { return g_err; }
 #include <string.h>
 void mp_set_igemm_smem(long long v);
 void mp_set_igemm_split_n(long long v);
-void mp_set_igemm_cluster(long long v);
+void mp_set_igemm_halo(long long v);
+void mp_set_igemm_pair(long long v);
+void mp_set_igemm_dbg(long long v);
+void mp_set_igemm_mt(int which, long long v);
 void mp_set_wgrad_tunable(int which, long long v);
 
 extern "C" int mp_set_tunable(const char* name, int64_t value) {
   if (!name) { mp_set_error("mp_set_tunable: null name"); return MP_ERR_ARG; }
   if (!strcmp(name, "igemm_smem")) { mp_set_igemm_smem(value); return MP_OK; }
   if (!strcmp(name, "igemm_split_n")) { mp_set_igemm_split_n(value); return MP_OK; }
-  if (!strcmp(name, "igemm_cluster")) { mp_set_igemm_cluster(value); return MP_OK; }
+  if (!strcmp(name, "igemm_halo")) { mp_set_igemm_halo(value); return MP_OK; }
+  if (!strcmp(name, "igemm_pair")) { mp_set_igemm_pair(value); return MP_OK; }
+  if (!strcmp(name, "igemm_dbg")) { mp_set_igemm_dbg(value); return MP_OK; }
+  if (!strcmp(name, "igemm_mt")) { mp_set_igemm_mt(0, value); return MP_OK; }
+  if (!strcmp(name, "igemm_mt_ctas")) { mp_set_igemm_mt(1, value); return MP_OK; }
+  if (!strcmp(name, "igemm_smem2")) { mp_set_igemm_mt(2, value); return MP_OK; }
   if (!strcmp(name, "wgrad_ctas")) { mp_set_wgrad_tunable(0, value); return MP_OK; }
-  if (!strcmp(name, "wgrad_taps")) { mp_set_wgrad_tunable(1, value); return MP_OK; }
+  if (!strcmp(name, "wgrad_halo")) { mp_set_wgrad_tunable(1, value); return MP_OK; }
   if (!strcmp(name, "wgrad_dbg")) { mp_set_wgrad_tunable(2, value); return MP_OK; }
   if (!strcmp(name, "wgrad_kp")) { mp_set_wgrad_tunable(3, value); return MP_OK; }
+  if (!strcmp(name, "wgrad_slice")) { mp_set_wgrad_tunable(4, value); return MP_OK; }
   mp_set_error("mp_set_tunable: unknown tunable '%s'", name);
   return MP_ERR_ARG;
 }

@@ -16,6 +16,7 @@ module tree are views into the flat buffers, so state_dict()/load_state_dict()/o
 ordinary tensors with the reference's key names and shapes.
 """
 import ctypes
+import os
 
 import torch
 from torch import nn
@@ -310,6 +311,8 @@ class Engine:
         self.bank, self.L = model._bank, model._layers
         self._bufs = []
         self._keep = []
+        # one grouped launch per layer for the three columns of a stage (default) or three stream lanes
+        self.group = os.environ.get('MARGIPOSE_B200_GROUP', '1') != '0'
         self.streams = [torch.cuda.Stream(device=device) for _ in range(3)]
         # one auxiliary stream per lane: weight gradients (nothing downstream waits for them) and the
         # shortcut conv of a block run beside the lane's dependent chain
@@ -367,6 +370,68 @@ class Engine:
         finally:
             C._igemm_launch, C._wgrad_launch = old_i, old_w
         return captured
+
+    # C-ABI entry points with a grouped variant (<name>_grouped(args[], n, stream))
+    GROUPABLE = ('mp_conv_igemm', 'mp_conv_wgrad', 'mp_bn_fwd', 'mp_bn_bwd_reduce', 'mp_bn_bwd_apply')
+
+    def _grouped(self, ops):
+        """One launch for the same op of the three columns (identical geometry, different tensors)."""
+        name = ops[0].name
+        fn = getattr(lib(), name + '_grouped')
+        arr = (type(ops[0].args) * len(ops))()
+        for i, op in enumerate(ops):
+            ctypes.memmove(ctypes.addressof(arr[i]), ctypes.addressof(op.args), ctypes.sizeof(op.args))
+        n, dev = len(ops), self.device
+
+        def run():
+            rc = fn(arr, n, stream_ptr(dev))
+            if rc != 0:
+                check(rc, name + '_grouped')
+        run.name, run.args, run.parts = name, arr, ops     # parts keep the argument structs' referents alive
+        run.flops = sum(op.flops for op in ops)
+        for flag in ('aux', 'join_aux'):
+            if any(getattr(op, flag, False) for op in ops):
+                setattr(run, flag, True)
+        return run
+
+    def _merge_lanes(self, lanes):
+        """The xy / zy / xz columns of a stage (margipose_model.py:196-198) record structurally identical
+        programs; zip them into ONE program whose ops are grouped launches (3x the work per launch:
+        fixed per-launch costs are paid once, tiles of all three columns fill the SMs together).  Ops
+        only some columns have (the axis permutations) keep their own launch."""
+        idx, out = [0] * len(lanes), []
+        while any(i < len(l) for i, l in zip(idx, lanes)):
+            cur = [(k, l[i]) for k, (i, l) in enumerate(zip(idx, lanes)) if i < len(l)]
+            names = [getattr(op, 'name', None) for _k, op in cur]
+            if len(cur) == len(lanes) and len(set(names)) == 1 and names[0] in self.GROUPABLE:
+                out.append(self._grouped([op for _k, op in cur]))
+            elif len(cur) == len(lanes) and all(hasattr(op, 'tail') for _k, op in cur) and \
+                    len(set(op.tail[0] for _k, op in cur)) == 1:
+                out.append(self._tail_op(cur[0][1].tail[0], [op.tail[1:] for _k, op in cur]))
+            else:
+                solo = [(k, op) for k, op in cur if getattr(op, 'name', None) == 'mp_axis_permute'] or cur
+                for k, op in solo:
+                    out.append(op)
+                cur = solo
+            for k, _op in cur:
+                idx[k] += 1
+        return out
+
+    def _tail_op(self, kind, planes_):
+        """Fused-tail launch over up to three planes: ('fwd', logits, prob) / ('bwd', prob, g_in, dlogits)."""
+        cols = [list(c) + [None] * (3 - len(planes_)) for c in zip(*planes_)]
+        if kind == 'fwd':
+            logits, prob = cols
+
+            def op():
+                K._tail_fwd(logits, True, prob=prob)
+        else:
+            prob, g_in, dlogits = cols
+
+            def op():
+                K._tail_bwd(prob, g_in, dlogits, project=True)
+        op.tail = (kind,) + tuple(planes_[0])
+        return op
 
     @staticmethod
     def _on_aux(ops):
@@ -620,13 +685,12 @@ class Engine:
                     blk_b.append(b)
                     self.trace.append(('stage%d.col%d.up%d' % (t, col.mode, i), xcol, rb.bn2.C))
                 prob = torch.zeros(n, J, hf, wf, device=dev)
-                ops.append(lambda logits=logits, prob=prob: K._tail_fwd([logits, None, None], True,
-                                                                          prob=[prob, None, None]))
+                ops.append(self._tail_op('fwd', [(logits, prob)]))
                 lanes.append(ops)
                 lz.append(logits)
                 pr.append(prob)
                 lane_bwd.append((blk_b, perm, len(col.down)))
-            segs.append(('parallel', lanes))
+            segs.append(('serial', self._merge_lanes(lanes)) if self.group else ('parallel', lanes))
             self.probs.append(pr)
             self.logits.append(lz)
             col_bwd.append(lane_bwd)
@@ -650,8 +714,7 @@ class Engine:
                 blk_b, perm, n_down = col_bwd[t][k]
                 prob, g_in = self.probs[t][k], self.gin[t][k]
                 dlogits = torch.zeros(n, J, hf, wf, device=dev)
-                ops.append(lambda prob=prob, g_in=g_in, dlogits=dlogits: K._tail_bwd(
-                    [prob, None, None], [g_in, None, None], [dlogits, None, None], project=True))
+                ops.append(self._tail_op('bwd', [(prob, g_in, dlogits)]))
                 d = None
                 for i in range(len(blk_b) - 1, -1, -1):
                     if i == len(blk_b) - 1:
@@ -666,7 +729,7 @@ class Engine:
                         d = dp
                 lanes.append(ops)
                 dxs.append(d)
-            bsegs.append(('parallel', lanes))
+            bsegs.append(('serial', self._merge_lanes(lanes)) if self.group else ('parallel', lanes))
             d_inp = self.act(*inps[t].shape)
             terms = dxs + ([d_next] if d_next is not None else [])
             arr = (ctypes.c_void_p * 4)(*([x.data_ptr() for x in terms] + [None] * (4 - len(terms))))

@@ -26,15 +26,28 @@ def test_fused_block_dgrad(stride, tr):
     K.check_fused_block_dgrad(stride, tr)
 
 
-@pytest.mark.parametrize('cluster', [2, 4])
-def test_conv_forward_with_multicast_clusters(cluster):
-    """The weight tile can be fetched once per thread-block cluster and TMA-multicast to its CTAs
-    (tunable igemm_cluster); results must not depend on it."""
+DEFAULTS = {'igemm_halo': 1, 'wgrad_halo': 1, 'igemm_pair': 0, 'wgrad_kp': 128, 'igemm_mt': 1,
+            'igemm_mt_ctas': 100, 'wgrad_slice': 256, 'wgrad_ctas': 148}
+
+
+@pytest.mark.parametrize('tunables', [
+    {'igemm_halo': 0, 'wgrad_halo': 0}, {'igemm_pair': 1}, {'igemm_mt': 2, 'igemm_mt_ctas': 1}, {'igemm_mt': 2, 'igemm_mt_ctas': 1, 'igemm_pair': 1},
+    {'wgrad_slice': 64, 'wgrad_ctas': 40, 'wgrad_kp': 64},
+], ids=lambda d: ','.join('%s=%d' % kv for kv in d.items()))
+def test_conv_kernel_variants(tunables):
+    """Row-shifted taps may share one halo box (igemm_halo / wgrad_halo), a CTA may own two 128-pixel
+    accumulators (igemm_mt*), two CTAs may pair up on M=256 tcgen05.mma.cta_group::2 tiles with half a
+    weight tile each (igemm_pair), wgrad may slice its columns / stages differently: results must not
+    depend on any of it."""
     from margipose_b200._lib import lib
     K.DEV = 'cuda'
     try:
-        assert lib().mp_set_tunable(b'igemm_cluster', cluster) == 0
-        K.check_conv_forward_and_stats(K.CASES[0])
-        K.check_conv_dgrad_and_wgrad(K.CASES[1])
+        for k, v in tunables.items():
+            assert lib().mp_set_tunable(k.encode(), v) == 0
+        for case in K.CASES[:2] + K.CASES[7:8] + K.CASES[10:11]:
+            K.check_conv_forward_and_stats(case)
+            K.check_conv_dgrad_and_wgrad(case)
+        K.check_fused_block_dgrad(1, False)
     finally:
-        lib().mp_set_tunable(b'igemm_cluster', 1)
+        for k in tunables:
+            lib().mp_set_tunable(k.encode(), DEFAULTS[k])

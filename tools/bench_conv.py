@@ -15,9 +15,8 @@ SHAPES = [  # cin, cout, k, stride, transposed, n, h, w
     (64, 64, 3, 1, False, 32, 64, 64),
     (128, 17, 3, 1, False, 32, 32, 32),
 ]
-for kv in sys.argv[1:]:
-    k, v = kv.split('=')
-    lib().mp_set_tunable(k.encode(), int(v))
+# tunable sets: "a=1 b=2 / a=0" runs the sweep once per set (later sets keep earlier values unless overridden)
+SETS = [x.split() for x in ' '.join(sys.argv[1:]).split('/')] if len(sys.argv) > 1 else [[]]
 which = os.environ.get('WHICH', 'fwd,dgrad,wgrad').split(',')
 iters = int(os.environ.get('ITERS', '20'))
 only = os.environ.get('ONLY')
@@ -38,29 +37,35 @@ def timeit(fn):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3
 
-for idx, (cin, cout, k, s, tr, n, h, w) in enumerate(SHAPES):
-    if only is not None and idx != int(only): continue
-    g = C.ConvGeom(cin, cout, k, s, tr)
-    ho, wo = g.out_hw(h, w)
-    x = torch.randn(n, h, w, g.cin_p, device='cuda').to(torch.bfloat16)
-    dy = torch.randn(n, ho, wo, g.cout_p, device='cuda').to(torch.bfloat16)
-    master = torch.randn(g.master_shape, device='cuda') * 0.05
-    wf, wb = C.pack_fwd(g, master), C.pack_bwd(g, master)
-    y = torch.zeros(n, ho, wo, g.cout_p, device='cuda', dtype=torch.bfloat16)
-    dx = torch.zeros_like(x)
-    dw = torch.zeros(g.master_shape, device='cuda')
-    stats = torch.zeros(2, g.cout_p, device='cuda')
-    flops = 2.0 * n * (h * w if tr else ho * wo) * g.taps * cin * cout
-    out = '%-28s' % str((cin, cout, k, s, 'T' if tr else '', n, h, w))
-    if 'fwd' in which:
-        t = timeit(lambda: C.conv_forward(g, x, wf, y, stats=(stats[0], stats[1])))
-        out += ' fwd %7.1f us %6.0f TF' % (t, flops / t / 1e6)
-        t = timeit(lambda: C.conv_forward(g, x, wf, y))
-        out += ' (nostat %6.1f us %5.0f TF)' % (t, flops / t / 1e6)
-    if 'dgrad' in which:
-        t = timeit(lambda: C.conv_dgrad(g, dy, wb, dx))
-        out += ' dgrad %7.1f us %6.0f TF' % (t, flops / t / 1e6)
-    if 'wgrad' in which:
-        t = timeit(lambda: C.conv_wgrad(g, x, dy, dw))
-        out += ' wgrad %7.1f us %6.0f TF' % (t, flops / t / 1e6)
-    print(out)
+for tset in SETS:
+    for kv in tset:
+        k_, v_ = kv.split('=')
+        assert lib().mp_set_tunable(k_.encode(), int(v_)) == 0, kv
+    if len(SETS) > 1:
+        print('== ' + ' '.join(tset))
+    for idx, (cin, cout, k, s, tr, n, h, w) in enumerate(SHAPES):
+        if only is not None and idx != int(only): continue
+        g = C.ConvGeom(cin, cout, k, s, tr)
+        ho, wo = g.out_hw(h, w)
+        x = torch.randn(n, h, w, g.cin_p, device='cuda').to(torch.bfloat16)
+        dy = torch.randn(n, ho, wo, g.cout_p, device='cuda').to(torch.bfloat16)
+        master = torch.randn(g.master_shape, device='cuda') * 0.05
+        wf, wb = C.pack_fwd(g, master), C.pack_bwd(g, master)
+        y = torch.zeros(n, ho, wo, g.cout_p, device='cuda', dtype=torch.bfloat16)
+        dx = torch.zeros_like(x)
+        dw = torch.zeros(g.master_shape, device='cuda')
+        stats = torch.zeros(2, g.cout_p, device='cuda')
+        flops = 2.0 * n * (h * w if tr else ho * wo) * g.taps * cin * cout
+        out = '%-28s' % str((cin, cout, k, s, 'T' if tr else '', n, h, w))
+        if 'fwd' in which:
+            t = timeit(lambda: C.conv_forward(g, x, wf, y, stats=(stats[0], stats[1])))
+            out += ' fwd %7.1f us %6.0f TF' % (t, flops / t / 1e6)
+            t = timeit(lambda: C.conv_forward(g, x, wf, y))
+            out += ' (nostat %6.1f us %5.0f TF)' % (t, flops / t / 1e6)
+        if 'dgrad' in which:
+            t = timeit(lambda: C.conv_dgrad(g, dy, wb, dx))
+            out += ' dgrad %7.1f us %6.0f TF' % (t, flops / t / 1e6)
+        if 'wgrad' in which:
+            t = timeit(lambda: C.conv_wgrad(g, x, dy, dw))
+            out += ' wgrad %7.1f us %6.0f TF' % (t, flops / t / 1e6)
+        print(out)
