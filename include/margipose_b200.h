@@ -152,15 +152,15 @@ typedef struct mp_igemm_args {
   float* stat_sq;
   int32_t stat_replicas;           /* >= 1: CTA b adds into replica (b % stat_replicas) ...          */
   int64_t stat_stride;             /* ... at stat_sum/stat_sq + replica * stat_stride (spreads atomics) */
-  /* BatchNorm finalize fused into the conv: the LAST CTA to add its statistics (ticket counter over
-   * bn_total_ctas arrivals, which may span several launches, e.g. the 4 parity classes of a
-   * transposed conv) turns sum/sq into mean / 1/std / scale / shift, saves them and updates the
-   * running buffers -- so the BatchNorm forward kernels start with one small load instead of a
-   * reduction.  bn: HOST pointer to the branch (gamma, beta, running_*, save_*, scale, shift,
-   * conv_bias are used) or NULL.  Requires stat_replicas == 1. */
+  /* BatchNorm finalize fused into the conv: the LAST CTA to add its statistics (ticket counter; the
+   * statistics of one BatchNorm input may come from bn_launches launches of identical geometry, e.g.
+   * the 4 output-parity classes of a transposed conv) turns sum/sq into mean / 1/std / scale / shift,
+   * saves them and updates the running buffers -- so the BatchNorm forward kernels start with one small
+   * load instead of a reduction.  bn: HOST pointer to the branch (gamma, beta, running_*, save_*, scale,
+   * shift, conv_bias are used) or NULL.  Requires stat_replicas == 1. */
   const struct mp_bn_branch* bn;
   uint32_t* bn_counter;            /* device counter, zero before the first contributing launch */
-  int32_t bn_total_ctas;           /* arrivals that complete the statistics (see mp_conv_igemm_ctas) */
+  int32_t bn_launches;             /* launches (of this geometry) that share bn_counter; 0 or 1 = this one only */
   int32_t bn_channels;             /* real channel count C */
   int64_t bn_count;                /* elements per channel (N*H*W of the BatchNorm input) */
   float bn_momentum, bn_eps;
@@ -171,8 +171,6 @@ MP_API int mp_conv_igemm(const mp_igemm_args* args, void* stream);
  * tensors in ONE launch (grid z = problem): the xy / zy / xz HeatmapColumns of a MargiPose stage
  * (models/margipose_model.py:196-198) are three such problems at every layer.  args: contiguous array. */
 MP_API int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, void* stream);
-/* Number of CTAs (statistics arrivals) mp_conv_igemm launches for `args`. */
-MP_API int mp_conv_igemm_ctas(const mp_igemm_args* args);
 
 /* Weight gradient: dw[m][slot][n] += sum over the (n_img, grid_h, grid_w) pixel grid of
  *   a(pix, m) * b[tap](pix + shift, n)
@@ -314,14 +312,19 @@ MP_API int mp_sgd_step(float* param, const float* grad, float* momentum_buf, int
                        int first_step, float grad_scale, void* stream);
 
 /* Tunables for experiments (name -> value); returns MP_ERR_ARG for unknown names.
- *   "igemm_smem"  : shared-memory budget per CTA of mp_conv_igemm in bytes (default 115712)
+ *   "igemm_smem"  : shared-memory budget per (persistent) CTA of mp_conv_igemm in bytes (default 204800)
+ *   "igemm_ctas"  : persistent CTAs per mp_conv_igemm launch (default 0 = the device's SM count)
  *   "igemm_halo"  : 1 (default) = filter taps that differ only by their row shift share one activation box of
  *                   tile_rows + 2 rows (fetched once, read through row-shifted descriptors); 0 = one box per tap
  *   "igemm_pair"  : 1 = two CTAs of a cluster pair up on M=256 tcgen05.mma.cta_group::2 tiles, each loading half of
- *                   every weight tile (when the M tiles pair up); 0 = one CTA per tile
- *   "igemm_split_n": mp_conv_igemm halves its N tile when it would launch fewer CTAs than this (default 100)
+ *                   every weight tile (when the M tiles pair up); 0 (default) = one CTA per tile
+ *   "igemm_mt"    : 2 = two 128-pixel row blocks (TMEM accumulators) per tile share every weight tile when the launch
+ *                   keeps at least "igemm_mt_ctas" tiles (0 = the CTA count); 1 (default) = one
+ *   "igemm_split_n": mp_conv_igemm halves its N tile when a launch has fewer tiles than this (default 0 = the CTA count)
+ *   "igemm_dbg"   : experiment switches (1 = no TMA loads, 2 = no MMA, 4 = no epilogue)
  *   "wgrad_ctas"  : target CTA count of mp_conv_wgrad (default 148)
  *   "wgrad_halo"  : 1 (default) = up to three row-shifted taps per CTA share the A tile and one halo box of B
+ *   "wgrad_slice" : widest column slice of B per CTA when taps are grouped (default 256; 64 or 128 narrow it)
  *   "wgrad_kp"    : pixels per pipeline stage of mp_conv_wgrad (default 128)
  *   "wgrad_dbg"   : experiment switches (1 = skip the gradient atomics, 4 = no MMA) */
 MP_API int mp_set_tunable(const char* name, int64_t value);

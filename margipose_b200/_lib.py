@@ -37,7 +37,7 @@ class IgemmArgs(ctypes.Structure):
                 ('out_sn', ctypes.c_int64), ('out_sh', ctypes.c_int64), ('out_sw', ctypes.c_int64),
                 ('out_c', ctypes.c_int32), ('stat_sum', c_void_p), ('stat_sq', c_void_p),
                 ('stat_replicas', ctypes.c_int32), ('stat_stride', ctypes.c_int64),
-                ('bn', c_void_p), ('bn_counter', c_void_p), ('bn_total_ctas', ctypes.c_int32),
+                ('bn', c_void_p), ('bn_counter', c_void_p), ('bn_launches', ctypes.c_int32),
                 ('bn_channels', ctypes.c_int32), ('bn_count', ctypes.c_int64),
                 ('bn_momentum', ctypes.c_float), ('bn_eps', ctypes.c_float)]
 
@@ -94,7 +94,6 @@ def _signatures():
         'mp_make_gauss': (I, [P, P, I, D, I, I, I, P]),
         'mp_conv_igemm': (I, [ctypes.POINTER(IgemmArgs), P]),
         'mp_conv_igemm_grouped': (I, [ctypes.POINTER(IgemmArgs), I, P]),
-        'mp_conv_igemm_ctas': (I, [ctypes.POINTER(IgemmArgs)]),
         'mp_conv_wgrad': (I, [ctypes.POINTER(WgradArgs), P]),
         'mp_conv_wgrad_grouped': (I, [ctypes.POINTER(WgradArgs), I, P]),
         'mp_set_tunable': (I, [ctypes.c_char_p, ctypes.c_int64]),

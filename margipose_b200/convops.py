@@ -138,7 +138,7 @@ def _igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out
         a.bn = ctypes.addressof(bn['branch'])
         a.bn_counter, a.bn_channels, a.bn_count = bn['counter'], bn['channels'], bn['count']
         a.bn_momentum, a.bn_eps = bn['momentum'], bn['eps']
-        a.bn_total_ctas = 0
+        a.bn_launches = 1
     if defer is not None:
         defer.append((a, out.device))
     else:
@@ -235,9 +235,8 @@ def _scatter_up(k, src, wpack, k_stride, cb, n, h, w, out, c_out_p, stats, res, 
             _igemm(srcs, wpack, taps, cb, n, h, w, out, strides, c_out_p, res=res, stats=stats,
                    out_offset=(ph * wo + pw) * c_out_p, bn=bn, defer=pending)
     if pending:   # the BatchNorm statistics are complete when the CTAs of ALL parity classes have arrived
-        total = sum(lib().mp_conv_igemm_ctas(ctypes.byref(a)) for a, _dev in pending)
         for a, dev in pending:
-            a.bn_total_ctas = total
+            a.bn_launches = len(pending)
             _igemm_launch(a, dev)
 
 

@@ -15,6 +15,12 @@
 // with tcgen05.ld, add the optional residual, round to bf16, store NHWC and reduce the BatchNorm
 // batch statistics of the stored tile.
 //
+// The kernel is PERSISTENT: ~one CTA per SM walks a contiguous range of output tiles; the TMA ring
+// keeps running across tile boundaries and the TMEM accumulator is double-buffered, so the epilogue
+// of tile i (tcgen05.ld, residual, bf16 stores, BatchNorm sums) overlaps the MMAs of tile i + 1 and
+// the per-CTA BatchNorm sums reach global memory once per CTA instead of once per tile.  A grouped
+// launch (grid z = problem) runs the same layer of the three HeatmapColumns of a stage at once.
+//
 // CTA-pair mode (cta_group::2): two CTAs of a cluster own adjacent 128-pixel tiles and each loads
 // only HALF of every weight tile; the leader issues M=256 MMAs that read both halves, so the
 // weight traffic per SM halves too.
@@ -23,8 +29,8 @@
 // (/root/reference/src/margipose/models/margipose_model.py:33,67-68,73-74,79-82 and the
 // torchvision ResNet stem :130-135), forward and dgrad.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2-5 = epilogue (TMEM lane quarter = warp % 4).  Roofline: tensor pipe; algorithmic
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2-9 = epilogue (TMEM lane quarter = warp % 4; the two warps of a quarter split the 32-column chunks).  Roofline: tensor pipe; algorithmic
 // flops per launch = 2 * pixels * n * K.
 #include <string.h>
 #include "tc.cuh"
@@ -32,9 +38,11 @@
 
 namespace {
 
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;     // warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue
+constexpr int EPI_THREADS = 256;
 constexpr int A_TILE_BYTES = 128 * 128;   // 128 pixels x 64 bf16
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_B = 40;        // weight slots (resident mode: one per tap and 64-channel block)
 
 // taps (src, c0, dw, p) with row shifts dh0 .. dh0 + n - 1; n > 1 reads the halo box (tile_rows + 2 rows)
 struct TapGroup {
@@ -49,14 +57,17 @@ struct alignas(64) IgemmMaps {   // TMA descriptors per problem: activation sour
 struct IgemmParams {
   TapGroup groups[MP_MAX_TAPS];
   int n_groups, cblocks;
-  int tile_w, tile_rows, tiles_w, tiles_h;
+  int tile_w, tile_rows, tiles_w, tiles_h;   // tiles_h counts CTA row blocks of mt * tile_rows rows
   int out_h, out_w;
-  int n_tile, tmem_cols;
-  int mt;        // 128-pixel accumulators per CTA (1 or 2): row blocks h0 + i * tile_rows share every weight tile
+  int n_tile, m_tiles, units;   // per problem: m_tiles pixel tiles x (w_rows / n_tile); units = tiles (pair: tile pairs)
+  int tmem_cols, acc_cols;      // acc_cols = mt * n_tile columns per accumulator buffer (two buffers)
+  int mt;        // 128-pixel accumulators per tile (1 or 2): row blocks h0 + i * tile_rows share every weight tile
   int a_stages, b_stages, a_slot_bytes, b_slot_bytes;   // b_slot_bytes: this CTA's share of a weight tile
   int a_tx_plain, a_tx_halo, row_bytes;
+  int resident;  // 1: the CTA's whole weight operand stays in shared memory (one slot per tap and channel block,
+                 // loaded with the first tile); later tiles stream activations only
   int dbg;       // experiment switches (tunable igemm_dbg): 1 = no TMA loads, 2 = no MMA, 4 = no epilogue
-  int pair;      // 1: CTA pair (cluster of 2 along the M tiles), cta_group::2 MMA
+  unsigned long long* trace;   // tunable igemm_trace: device buffer of 64 timestamps written by CTA (0,0,0), or NULL
   long long out_sn, out_sh, out_sw;
   int out_c;
   int stat_replicas;
@@ -77,6 +88,30 @@ struct IgemmParams {
   float fin_momentum, fin_eps;
 };
 
+__device__ __forceinline__ void trace_at(const IgemmParams& P, int slot) {
+  if (P.trace && blockIdx.x == 0 && blockIdx.z == 0 && slot < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.trace[slot] = t;
+  }
+}
+
+struct TileCoord {
+  int n0, img, h0, w0, n_idx;
+};
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
+  TileCoord c;
+  c.n_idx = t / P.m_tiles;
+  int m = t - c.n_idx * P.m_tiles;
+  const int tw = m % P.tiles_w; m /= P.tiles_w;
+  const int th = m % P.tiles_h;
+  c.img = m / P.tiles_h;
+  c.w0 = tw * P.tile_w;
+  c.h0 = th * P.tile_rows * P.mt;
+  c.n0 = c.n_idx * P.n_tile;
+  return c;
+}
+
 template <bool PAIR>
 __global__ void __launch_bounds__(NTHREADS)
 igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ IgemmParams P) {
@@ -85,37 +120,49 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
   const CUtensorMap& tmA1 = TM.a1[blockIdx.z];
   const CUtensorMap& tmB = TM.b[blockIdx.z];
   const IgemmParams::Problem& Q = P.q[blockIdx.z];
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // swizzle atoms need 1024-byte alignment (checked below)
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)P.a_stages * P.a_slot_bytes;
   uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + (size_t)P.b_stages * P.b_slot_bytes);
   uint64_t* emptyA = fullA + MAX_STAGES;
   uint64_t* fullB = emptyA + MAX_STAGES;
-  uint64_t* emptyB = fullB + MAX_STAGES;
-  uint64_t* tmem_full = emptyB + MAX_STAGES;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* emptyB = fullB + MAX_B;
+  uint64_t* tmem_full = emptyB + MAX_B;    // [2]: accumulator buffer written, epilogue may drain it
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]: accumulator buffer drained, MMAs may overwrite it
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_stat = reinterpret_cast<float*>(tmem_holder + 4);   // [2][256] per-CTA channel sums
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_idx_uniform(), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    trace_at(P, 0);
+    if (tc::smem_u32(smem) & 1023u) {
+      printf("margipose_b200: igemm shared memory base not 1024-byte aligned\n");
+      __trap();
+    }
+  }
   if (Q.stat_sum)
     for (int i = threadIdx.x; i < 512; i += NTHREADS) s_stat[i] = 0.f;
-  int t = blockIdx.x;
-  const int tw = t % P.tiles_w; t /= P.tiles_w;
-  const int th = t % P.tiles_h;
-  const int img = t / P.tiles_h;
-  const int w0 = tw * P.tile_w, h0 = th * P.tile_rows * P.mt;
-  const int n0 = blockIdx.y * P.n_tile;
   const uint32_t crank = PAIR ? tc::cluster_ctarank() : 0;
+  // my contiguous range of work units (tiles, or tile pairs for a CTA pair)
+  const int workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int me = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int u_begin = (int)((long long)me * P.units / workers);
+  const int u_end = (int)((long long)(me + 1) * P.units / workers);
+  constexpr int STEP = PAIR ? 2 : 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
       tc::mbar_init(&fullA[s], 1);
       tc::mbar_init(&emptyA[s], 1);
+    }
+    for (int s = 0; s < MAX_B; ++s) {
       tc::mbar_init(&fullB[s], 1);
       tc::mbar_init(&emptyB[s], 1);
     }
-    tc::mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&tmem_full[b], 1);
+      tc::mbar_init(&tmem_empty[b], PAIR ? 16 : 8);   // one arrival per epilogue warp (of both CTAs of a pair)
+    }
     tc::mbar_fence_init();
     tc::prefetch_tmap(&tmA0);
     tc::prefetch_tmap(&tmA0h);
@@ -131,160 +178,209 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
   if (PAIR) tc::cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_holder;
+  if (threadIdx.x == 0) trace_at(P, 1);
 
   if (warp == 0) {
-    if (lane == 0) {   // ---------------------------------------------------------- TMA producer
+    {   // ------------------------------------------- TMA producer: warp-uniform loops, one elected lane issues
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
-      const int b_row0 = n0 + (int)crank * (P.b_slot_bytes >> 7);   // pair: my half of the weight-tile rows
-      for (int g = 0; g < P.n_groups; ++g) {
-        const TapGroup& G = P.groups[g];
-        const bool halo = G.n > 1;
-        const CUtensorMap* tmA = halo ? &tmA0h : (G.src ? &tmA1 : &tmA0);
-        for (int cb = 0; cb < P.cblocks; ++cb) {
-          tc::mbar_wait(&emptyA[sa], pha ^ 1);
-          uint8_t* dstA = sA + (size_t)sa * P.a_slot_bytes;
-          if (P.dbg & 1) {
-            if (crank == 0) tc::mbar_arrive(&fullA[sa]);
-          } else if (PAIR) {   // both CTAs' bytes complete on the leader's barrier
-            if (crank == 0) tc::mbar_arrive_expect_tx(&fullA[sa], 2u * (uint32_t)(halo ? P.a_tx_halo : P.a_tx_plain));
-            tc::tma_load_5d_pair(tmA, &fullA[sa], dstA, G.c0 + cb * 64, w0 + G.dw, G.p, h0 + G.dh0, img);
-          } else {
-            tc::mbar_arrive_expect_tx(&fullA[sa], (uint32_t)(halo ? P.a_tx_halo : P.a_tx_plain));
-            tc::tma_load_5d(tmA, &fullA[sa], dstA, G.c0 + cb * 64, w0 + G.dw, G.p, h0 + G.dh0, img);
-          }
-          if (++sa == P.a_stages) { sa = 0; pha ^= 1; }
-          for (int i = 0; i < G.n; ++i) {
-            tc::mbar_wait(&emptyB[sb], phb ^ 1);
-            uint8_t* dstB = sB + (size_t)sb * P.b_slot_bytes;
-            if (P.dbg & 1) {
-              if (crank == 0) tc::mbar_arrive(&fullB[sb]);
-            } else if (PAIR) {
-              if (crank == 0) tc::mbar_arrive_expect_tx(&fullB[sb], 2u * (uint32_t)P.b_slot_bytes);
-              tc::tma_load_2d_pair(&tmB, &fullB[sb], dstB, G.koff[i] + cb * 64, b_row0);
+      for (int u = u_begin; u < u_end; ++u) {
+        const TileCoord T = decode_tile(P, u * STEP + (int)crank);
+        if (P.resident) { sb = 0; phb = 0; }
+        const bool load_b = !P.resident || u == u_begin;
+        const int b_row0 = T.n0 + (int)crank * (P.b_slot_bytes >> 7);   // pair: my half of the weight-tile rows
+        for (int g = 0; g < P.n_groups; ++g) {
+          const TapGroup& G = P.groups[g];
+          const bool halo = G.n > 1;
+          const CUtensorMap* tmA = halo ? &tmA0h : (G.src ? &tmA1 : &tmA0);
+          for (int cb = 0; cb < P.cblocks; ++cb) {
+            if (!(P.dbg & 16)) tc::mbar_wait(&emptyA[sa], pha ^ 1);
+            uint8_t* dstA = sA + (size_t)sa * P.a_slot_bytes;
+            if (!tc::elect_one()) {
+            } else if (P.dbg & 1) {
+              if (crank == 0) tc::mbar_arrive(&fullA[sa]);
+            } else if (PAIR) {   // both CTAs' bytes complete on the leader's barrier
+              if (crank == 0) tc::mbar_arrive_expect_tx(&fullA[sa], 2u * (uint32_t)(halo ? P.a_tx_halo : P.a_tx_plain));
+              tc::tma_load_5d_pair(tmA, &fullA[sa], dstA, G.c0 + cb * 64, T.w0 + G.dw, G.p, T.h0 + G.dh0, T.img);
             } else {
-              tc::mbar_arrive_expect_tx(&fullB[sb], (uint32_t)P.b_slot_bytes);
-              tc::tma_load_2d(&tmB, &fullB[sb], dstB, G.koff[i] + cb * 64, b_row0);
+              tc::mbar_arrive_expect_tx(&fullA[sa], (uint32_t)(halo ? P.a_tx_halo : P.a_tx_plain));
+              tc::tma_load_5d(tmA, &fullA[sa], dstA, G.c0 + cb * 64, T.w0 + G.dw, G.p, T.h0 + G.dh0, T.img);
             }
-            if (++sb == P.b_stages) { sb = 0; phb ^= 1; }
+            if (++sa == P.a_stages) { sa = 0; pha ^= 1; }
+            for (int i = 0; i < G.n && load_b; ++i) {
+              if (!P.resident && !(P.dbg & 16)) tc::mbar_wait(&emptyB[sb], phb ^ 1);
+              uint8_t* dstB = sB + (size_t)sb * P.b_slot_bytes;
+              if (!tc::elect_one()) {
+              } else if (P.dbg & 1) {
+                if (crank == 0) tc::mbar_arrive(&fullB[sb]);
+              } else if (PAIR) {
+                if (crank == 0) tc::mbar_arrive_expect_tx(&fullB[sb], 2u * (uint32_t)P.b_slot_bytes);
+                tc::tma_load_2d_pair(&tmB, &fullB[sb], dstB, G.koff[i] + cb * 64, b_row0);
+              } else {
+                tc::mbar_arrive_expect_tx(&fullB[sb], (uint32_t)P.b_slot_bytes);
+                tc::tma_load_2d(&tmB, &fullB[sb], dstB, G.koff[i] + cb * 64, b_row0);
+              }
+              if (++sb == P.b_stages) { sb = 0; phb ^= 1; }
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {   // -------------------------------- MMA issuer (pair: the leader only)
+    if (crank == 0) {   // ---------- MMA issuer (pair: the leader only): warp-uniform loops, one elected lane issues
       const uint32_t idesc = tc::idesc_bf16(PAIR ? 256 : 128, P.n_tile, false, false);
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
-      bool first = true;
-      for (int g = 0; g < P.n_groups; ++g) {
-        const int n = P.groups[g].n;
-        for (int cb = 0; cb < P.cblocks; ++cb) {
-          tc::mbar_wait(&fullA[sa], pha);
-          const uint32_t a0 = tc::smem_u32(sA + (size_t)sa * P.a_slot_bytes);
-          for (int i = 0; i < n; ++i) {
-            tc::mbar_wait(&fullB[sb], phb);
-            tc::tc_fence_after();
-            const uint64_t bd = tc::desc_kmajor_sw128(tc::smem_u32(sB + (size_t)sb * P.b_slot_bytes));
-            for (int m = 0; m < P.mt; ++m) {
-              // row-shifted window of the (halo) box: tap i of the group, row block m of the CTA
-              const uint64_t ad = tc::desc_kmajor_sw128(a0 + (uint32_t)((i + m * P.tile_rows) * P.row_bytes));
-              const uint32_t d = tmem + (uint32_t)(m * P.n_tile);
+      int it = 0;
+      for (int u = u_begin; u < u_end; ++u, ++it) {
+        const int buf = it & 1;
+        tc::mbar_wait(&tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));   // epilogue drained this buffer
+        tc::tc_fence_after();
+        const uint32_t acc = tmem + (uint32_t)(buf * P.acc_cols);
+        bool first = true;
+        if (P.resident) { sb = 0; phb = 0; }
+        const bool wait_b = !P.resident || it == 0;
+        for (int g = 0; g < P.n_groups; ++g) {
+          const int n = P.groups[g].n;
+          for (int cb = 0; cb < P.cblocks; ++cb) {
+            if (!(P.dbg & 8)) tc::mbar_wait(&fullA[sa], pha);
+            if (first && lane == 0) trace_at(P, 4 + it * 4);       // first operands of tile `it` have landed
+            const uint32_t a0 = tc::smem_u32(sA + (size_t)sa * P.a_slot_bytes);
+            for (int i = 0; i < n; ++i) {
+              if (wait_b && !(P.dbg & 8)) tc::mbar_wait(&fullB[sb], phb);
+              tc::tc_fence_after();
+              const uint64_t bd = tc::desc_kmajor_sw128(tc::smem_u32(sB + (size_t)sb * P.b_slot_bytes));
+              if (tc::elect_one()) {
+                // row-shifted windows of the (halo) box: tap i of the group, row blocks 0 / 1 of the tile.  With two
+                // row blocks the MMAs alternate between the two accumulators, so an MMA never waits for the one
+                // just issued to the same accumulator.
+                const uint64_t ad0 = tc::desc_kmajor_sw128(a0 + (uint32_t)(i * P.row_bytes));
+                const uint64_t ad1 = tc::desc_kmajor_sw128(a0 + (uint32_t)((i + P.tile_rows) * P.row_bytes));
+                const uint32_t d1 = acc + (uint32_t)P.n_tile;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in the
-                                              // descriptor's 16-byte address field)
-                if (P.dbg & 2) continue;
-                if (PAIR) tc::mma_bf16_pair(d, ad + 2 * k, bd + 2 * k, idesc, !(first && k == 0));
-                else tc::mma_bf16(d, ad + 2 * k, bd + 2 * k, idesc, !(first && k == 0));
+                for (int k = 0; k < 4; ++k) {   // 4 x (K = 16 bf16 = 32 bytes inside the 128B swizzle atom: +2 in
+                                                // the descriptor's 16-byte address field)
+                  if (P.dbg & 2) continue;
+                  if (PAIR) tc::mma_bf16_pair(acc, ad0 + 2 * k, bd + 2 * k, idesc, !(first && k == 0));
+                  else tc::mma_bf16(acc, ad0 + 2 * k, bd + 2 * k, idesc, !(first && k == 0));
+                  if (P.mt > 1) {
+                    if (PAIR) tc::mma_bf16_pair(d1, ad1 + 2 * k, bd + 2 * k, idesc, !(first && k == 0));
+                    else tc::mma_bf16(d1, ad1 + 2 * k, bd + 2 * k, idesc, !(first && k == 0));
+                  }
+                }
+                // frees the weight slot (in both CTAs of a pair) once these MMAs have read it; with the last
+                // tap of the group the activation slot too
+                if (P.resident || (P.dbg & 16)) {} else if (PAIR) tc::mma_commit_pair(&emptyB[sb]); else tc::mma_commit(&emptyB[sb]);
+                if (i == n - 1) {
+                  if (P.dbg & 16) {} else if (PAIR) tc::mma_commit_pair(&emptyA[sa]); else tc::mma_commit(&emptyA[sa]);
+                }
               }
+              first = false;
+              if (++sb == P.b_stages) { sb = 0; phb ^= 1; }
             }
-            first = false;
-            // frees the weight slot (in both CTAs of a pair) once these MMAs have read it
-            if (PAIR) tc::mma_commit_pair(&emptyB[sb]); else tc::mma_commit(&emptyB[sb]);
-            if (++sb == P.b_stages) { sb = 0; phb ^= 1; }
+            if (++sa == P.a_stages) { sa = 0; pha ^= 1; }
           }
-          if (PAIR) tc::mma_commit_pair(&emptyA[sa]); else tc::mma_commit(&emptyA[sa]);
-          if (++sa == P.a_stages) { sa = 0; pha ^= 1; }
         }
+        if (tc::elect_one()) {
+          if (PAIR) tc::mma_commit_pair(&tmem_full[buf]); else tc::mma_commit(&tmem_full[buf]);
+        }
+        if (lane == 0) trace_at(P, 5 + it * 4);                    // all MMAs of tile `it` issued
       }
-      if (PAIR) tc::mma_commit_pair(tmem_full); else tc::mma_commit(tmem_full);
     }
   } else {   // ------------------------------------------------------------------------ epilogue
-    tc::mbar_wait(tmem_full, 0);
-    tc::tc_fence_after();
     const int q = warp & 3;
+    const int et = threadIdx.x - 64;   // 0..255 among the epilogue threads
+    const int half = (warp - 2) >> 2;  // which of the two warps of this TMEM lane quarter
     const int m = q * 32 + lane;
     const int r = m / P.tile_w, wq = m - r * P.tile_w;
     const int nchunks = P.n_tile / 32;
-    for (int mt = 0; mt < ((P.dbg & 4) ? 0 : P.mt); ++mt)
-    for (int c = 0; c < nchunks; ++c) {
-      const int h = h0 + mt * P.tile_rows + r, w = w0 + wq;
-      const bool valid = (r < P.tile_rows) && (h < P.out_h) && (w < P.out_w);
-      const long long pix = (long long)img * P.out_sn + (long long)h * P.out_sh + (long long)w * P.out_sw;
-      const int ch = n0 + c * 32;
-      if (ch >= P.out_c) break;   // warp-uniform
-      float v[32];
-      tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * P.n_tile + c * 32), v);
-      uint32_t packed[16];
-      if (valid) {
-        if (Q.res) {
+    int it = 0;
+    for (int u = u_begin; u < u_end; ++u, ++it) {
+      const TileCoord T = decode_tile(P, u * STEP + (int)crank);
+      const int buf = it & 1;
+      tc::mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
+      tc::tc_fence_after();
+      if (et == 0) trace_at(P, 6 + it * 4);                        // accumulator of tile `it` complete
+      const uint32_t acc = tmem + (uint32_t)(buf * P.acc_cols);
+      const int n0 = T.n0, img = T.img;
+      for (int mt = 0; mt < ((P.dbg & 4) ? 0 : P.mt); ++mt)
+      for (int c = (mt * nchunks + half) & 1; c < nchunks; c += 2) {
+        const int h = T.h0 + mt * P.tile_rows + r, w = T.w0 + wq;
+        const bool valid = (r < P.tile_rows) && (h < P.out_h) && (w < P.out_w);
+        const long long pix = (long long)img * P.out_sn + (long long)h * P.out_sh + (long long)w * P.out_sw;
+        const int ch = n0 + c * 32;
+        if (ch >= P.out_c) break;   // warp-uniform
+        float v[32];
+        tc::tmem_ld32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * P.n_tile + c * 32), v);
+        uint32_t packed[16];
+        if (valid) {
+          if (Q.res) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (ch + i * 8 < P.out_c) {
-              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(Q.res + pix + ch + i * 8));
-              const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+            for (int i = 0; i < 4; ++i) {
+              if (ch + i * 8 < P.out_c) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(Q.res + pix + ch + i * 8));
+                const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2(rr[j]);
-                v[i * 8 + j * 2] += f.x;
-                v[i * 8 + j * 2 + 1] += f.y;
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = unpack_bf16x2(rr[j]);
+                  v[i * 8 + j * 2] += f.x;
+                  v[i * 8 + j * 2 + 1] += f.y;
+                }
               }
             }
           }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (ch + i * 8 < P.out_c)
+              *reinterpret_cast<uint4*>(Q.out + pix + ch + i * 8) =
+                  make_uint4(packed[i * 4], packed[i * 4 + 1], packed[i * 4 + 2], packed[i * 4 + 3]);
+          }
         }
+        if (Q.stat_sum) {   // statistics of the values as stored (bf16-rounded)
+          float s1[32], s2[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (ch + i * 8 < P.out_c)
-            *reinterpret_cast<uint4*>(Q.out + pix + ch + i * 8) =
-                make_uint4(packed[i * 4], packed[i * 4 + 1], packed[i * 4 + 2], packed[i * 4 + 3]);
+          for (int j = 0; j < 16; ++j) {
+            float2 f = make_float2(0.f, 0.f);
+            if (valid) f = unpack_bf16x2(packed[j]);
+            s1[2 * j] = f.x; s1[2 * j + 1] = f.y;
+            s2[2 * j] = f.x * f.x; s2[2 * j + 1] = f.y * f.y;
+          }
+          const float a1 = tc::warp_transpose_sum(s1);
+          const float a2 = tc::warp_transpose_sum(s2);
+          atomicAdd(s_stat + c * 32 + lane, a1);          // the epilogue warps meet in shared memory ...
+          atomicAdd(s_stat + 256 + c * 32 + lane, a2);
         }
       }
-      if (Q.stat_sum) {   // statistics of the values as stored (bf16-rounded)
-        float s1[32], s2[32];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float2 f = make_float2(0.f, 0.f);
-          if (valid) f = unpack_bf16x2(packed[j]);
-          s1[2 * j] = f.x; s1[2 * j + 1] = f.y;
-          s2[2 * j] = f.x * f.x; s2[2 * j + 1] = f.y * f.y;
-        }
-        const float a1 = tc::warp_transpose_sum(s1);
-        const float a2 = tc::warp_transpose_sum(s2);
-        atomicAdd(s_stat + c * 32 + lane, a1);          // 4 epilogue warps meet in shared memory ...
-        atomicAdd(s_stat + 256 + c * 32 + lane, a2);
+      // this warp's share of the buffer is in registers / stored: hand it back to the MMA issuer
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) tc::mbar_arrive_remote(&tmem_empty[buf], 0); else tc::mbar_arrive(&tmem_empty[buf]);
       }
-    }
-    if (Q.stat_sum) {   // ... and the CTA issues ONE global atomic per channel and statistic
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const long long rep = (long long)(blockIdx.x % P.stat_replicas) * P.stat_stride;
-      for (int i = threadIdx.x - 64; i < P.n_tile; i += 128) {
-        if (n0 + i < P.out_c) {
-          atomicAdd(Q.stat_sum + rep + n0 + i, s_stat[i]);
-          atomicAdd(Q.stat_sq + rep + n0 + i, s_stat[256 + i]);
+      if (et == 0) trace_at(P, 7 + it * 4);                        // tile `it` drained (this warp)
+      // BatchNorm sums leave the CTA when its range ends or moves on to other output channels
+      const bool flush = (u + 1 == u_end) || ((u + 1) * STEP / P.m_tiles != T.n_idx);
+      if (Q.stat_sum && flush) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 4 epilogue warps have met in shared memory
+        const long long rep = (long long)(blockIdx.x % P.stat_replicas) * P.stat_stride;
+        for (int i = et; i < P.n_tile; i += EPI_THREADS) {
+          if (n0 + i < P.out_c) {   // ONE global atomic per channel and statistic
+            atomicAdd(Q.stat_sum + rep + n0 + i, s_stat[i]);
+            atomicAdd(Q.stat_sq + rep + n0 + i, s_stat[256 + i]);
+          }
         }
-      }
-      if (Q.fin_counter) {   // last CTA to arrive turns the sums into the BatchNorm coefficients
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        unsigned* s_ticket = reinterpret_cast<unsigned*>(s_stat + 512);
-        if (threadIdx.x == 64) *s_ticket = atomicAdd(Q.fin_counter, 1u);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (*s_ticket == (unsigned)(P.fin_total - 1)) {
+        if (Q.fin_counter) {   // last CTA to arrive turns the sums into the BatchNorm coefficients
           __threadfence();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          unsigned* s_ticket = reinterpret_cast<unsigned*>(s_stat + 512);
+          if (et == 0) *s_ticket = atomicAdd(Q.fin_counter, 1u);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (*s_ticket == (unsigned)(P.fin_total - 1)) {
+            __threadfence();
           const float inv_m = 1.0f / (float)P.fin_count;
-          for (int c = threadIdx.x - 64; c < P.fin_Cp; c += 128) {
+          for (int c = et; c < P.fin_Cp; c += EPI_THREADS) {
             float scale = 0.f, shift = 0.f;
             if (c < P.fin_C) {
               const float mean = __ldcg(Q.stat_sum + c) * inv_m;
@@ -304,12 +400,17 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
             Q.fin_scale[c] = scale;
             Q.fin_shift[c] = shift;
           }
+          }
         }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int i = et; i < 512; i += EPI_THREADS) s_stat[i] = 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_at(P, 2);
   if (PAIR) {
     tc::cluster_sync_all();   // nobody leaves while the pair's MMAs may still read its shared memory / TMEM
     if (warp == 1) tc::tmem_dealloc_pair(tmem, P.tmem_cols);
@@ -318,15 +419,31 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
   }
 }
 
-long long g_igemm_smem = 115712;   // 113 KB: two CTAs share an SM (one's epilogue overlaps the other's main loop)
-long long g_igemm_smem2 = 200 * 1024;   // budget of CTAs with two accumulators (one per SM, deep rings)
-long long g_igemm_mt = 1;          // row blocks (accumulators) per CTA when the launch keeps >= g_igemm_mt_ctas CTAs
-long long g_igemm_mt_ctas = 100;
+long long g_igemm_smem = 227 * 1024;   // per CTA (one persistent CTA per SM): activation ring + weight ring / resident weights
+long long g_igemm_resident = 1;    // keep the weight operand in shared memory across a CTA's tiles when it fits
+long long g_igemm_ctas = 0;        // CTAs per launch (0 = the device's SM count)
 long long g_igemm_halo = 1;        // group taps that differ only in their row shift (one halo box per group)
 long long g_igemm_dbg = 0;
-long long g_igemm_pair = 0;        // CTA pairs (cta_group::2) when the M tiles pair up
-long long g_igemm_split_n = 100;   // split N in two when the launch would have fewer CTAs than this
+long long g_igemm_trace = 0;
+long long g_igemm_pair = 1;        // CTA pairs (cta_group::2) when the M tiles pair up
+long long g_igemm_split_n = 0;     // split N in two when a launch has fewer tiles than this (0 = the CTA count)
+long long g_igemm_mt = 2;          // row blocks (accumulators) per tile when the launch keeps >= g_igemm_mt_ctas tiles
+long long g_igemm_mt_ctas = 0;     // (0 = the CTA count)
 bool g_attr_set = false;
+int g_sm_count = 0;
+
+int cta_budget() {
+  if (g_igemm_ctas > 0) return (int)g_igemm_ctas;
+  if (g_sm_count == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        n > 0)
+      g_sm_count = n;
+    else
+      g_sm_count = 148;
+  }
+  return g_sm_count;
+}
 
 int view_to_tmap(CUtensorMap* tm, const mp_view5& v, const uint32_t box[5], const char* what) {
   uint64_t dims[5], strides[5];
@@ -397,39 +514,43 @@ void mp_set_igemm_smem(long long v) { g_igemm_smem = v; }
 void mp_set_igemm_halo(long long v) { g_igemm_halo = v; }
 void mp_set_igemm_pair(long long v) { g_igemm_pair = v; }
 void mp_set_igemm_dbg(long long v) { g_igemm_dbg = v; }
+void mp_set_igemm_trace(long long v) { g_igemm_trace = v; }
+void mp_set_igemm_resident(long long v) { g_igemm_resident = v; }
 void mp_set_igemm_split_n(long long v) { g_igemm_split_n = v; }
 void mp_set_igemm_mt(int which, long long v) {
   if (which == 0) g_igemm_mt = v;
   else if (which == 1) g_igemm_mt_ctas = v;
-  else g_igemm_smem2 = v;
+  else g_igemm_ctas = v;
 }
 
-static void igemm_grid(const mp_igemm_args* a, int* tile_w, int* tile_rows, int* tiles_w, int* tiles_h, int* n_tile,
-                       int* mt) {
+static void igemm_grid(const mp_igemm_args* a, int n_problems, int* tile_w, int* tile_rows, int* tiles_w, int* tiles_h,
+                       int* n_tile, int* mt) {
   mp_pick_tile(a->out_h, a->out_w, 128, tile_w, tile_rows);
   *tiles_w = (a->out_w + *tile_w - 1) / *tile_w;
-  *n_tile = a->w_rows <= 256 ? (int)a->w_rows : 256;
-  // Two full 128-pixel row blocks per CTA (two TMEM accumulators sharing every weight tile) when that
-  // still leaves enough CTAs: halves the weight traffic per FLOP and amortises the MMA issuer's
-  // barrier handshakes over twice the math.
+  const int budget = cta_budget();
+  // Preferred shape: TWO 128-pixel row blocks per tile, i.e. two TMEM accumulators that share every weight
+  // tile and that the MMAs alternate between (back-to-back MMAs into ONE accumulator run at about half the
+  // tensor rate when N <= 128).  Two accumulators, double-buffered, need 4 * n_tile <= 512 TMEM columns,
+  // so wider outputs are split along N (the activations are then streamed once per part).
   *mt = 1;
+  *n_tile = a->w_rows <= 256 ? (int)a->w_rows : 256;
   if (g_igemm_mt >= 2 && *tile_w * *tile_rows == 128 && a->out_h >= 2 * *tile_rows) {
+    int nt = *n_tile;
+    while (nt > 128 && nt % 2 == 0 && (nt / 2) % 32 == 0) nt /= 2;
     const long long th2 = (a->out_h + 2 * *tile_rows - 1) / (2 * *tile_rows);
-    if ((long long)a->n_img * th2 * *tiles_w * (a->w_rows / *n_tile) >= g_igemm_mt_ctas) *mt = 2;
+    const long long need = g_igemm_mt_ctas > 0 ? g_igemm_mt_ctas : budget / 2;
+    if (nt <= 128 && a->w_rows % nt == 0 &&
+        (long long)n_problems * a->n_img * th2 * *tiles_w * (a->w_rows / nt) >= need) {
+      *mt = 2;
+      *n_tile = nt;
+    }
   }
   *tiles_h = (a->out_h + *tile_rows * *mt - 1) / (*tile_rows * *mt);
-  // Small pixel grids (e.g. 16x16 maps at batch 32 = 64 M-tiles) leave most of the 148 SMs idle:
-  // give each M-tile two CTAs with half the output channels each (the A tile is then fetched twice,
-  // from L2, which is cheaper than idle tensor cores).
-  const long long ctas = (long long)a->n_img * *tiles_h * *tiles_w * (a->w_rows / *n_tile);
-  if (ctas < g_igemm_split_n && *n_tile >= 128 && (*n_tile / 2) % 32 == 0) *n_tile /= 2;
-}
-
-extern "C" int mp_conv_igemm_ctas(const mp_igemm_args* a) {
-  if (!a || a->out_h <= 0 || a->out_w <= 0 || a->w_rows <= 0) return 0;
-  int tw, tr, tsw, tsh, nt, mt;
-  igemm_grid(a, &tw, &tr, &tsw, &tsh, &nt, &mt);
-  return a->n_img * tsh * tsw * (int)(a->w_rows / nt);
+  // Small pixel grids leave SMs idle or badly balanced: give each pixel tile two work units with half the
+  // output channels each.
+  const long long tiles = (long long)n_problems * a->n_img * *tiles_h * *tiles_w * (a->w_rows / *n_tile);
+  const long long want = g_igemm_split_n > 0 ? g_igemm_split_n : budget;
+  if (*mt == 1 && tiles < want && *n_tile >= 128 && (*n_tile / 2) % 32 == 0) *n_tile /= 2;
 }
 
 static int check_one(const mp_igemm_args* a, bool* use_src1) {
@@ -474,7 +595,7 @@ static bool same_geometry(const mp_igemm_args* x, const mp_igemm_args* y) {
       x->stat_stride != y->stat_stride || !same_view(x->src[0], y->src[0]) ||
       (x->src[1].ptr == nullptr) != (y->src[1].ptr == nullptr) || (x->src[1].ptr && !same_view(x->src[1], y->src[1])))
     return false;
-  if (x->bn && (x->bn_total_ctas != y->bn_total_ctas || x->bn_channels != y->bn_channels || x->bn_count != y->bn_count ||
+  if (x->bn && (x->bn_launches != y->bn_launches || x->bn_channels != y->bn_channels || x->bn_count != y->bn_count ||
                 x->bn_momentum != y->bn_momentum || x->bn_eps != y->bn_eps))
     return false;
   return memcmp(x->taps, y->taps, sizeof(mp_tap) * x->n_taps) == 0;
@@ -497,7 +618,7 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
   }
 
   IgemmParams P;
-  igemm_grid(a, &P.tile_w, &P.tile_rows, &P.tiles_w, &P.tiles_h, &P.n_tile, &P.mt);
+  igemm_grid(a, n_problems, &P.tile_w, &P.tile_rows, &P.tiles_w, &P.tiles_h, &P.n_tile, &P.mt);
   P.cblocks = a->cblocks;
   P.out_h = a->out_h;
   P.out_w = a->out_w;
@@ -513,37 +634,65 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
   P.a_tx_halo = P.tile_w * (P.tile_rows * P.mt + 2) * 128;
   P.a_slot_bytes = (P.mt - 1) * P.tile_rows * P.row_bytes + A_TILE_BYTES + (any_halo ? 2 * P.row_bytes : 0);
 
-  // CTA pairs: adjacent M tiles, each CTA holds half of the weight-tile rows
-  const long long m_tiles = (long long)a->n_img * P.tiles_h * P.tiles_w;
-  P.pair = (g_igemm_pair != 0 && m_tiles % 2 == 0 && P.n_tile % 16 == 0 && (P.n_tile / 2) % 8 == 0) ? 1 : 0;
-  P.b_slot_bytes = (P.n_tile / (P.pair ? 2 : 1)) * 128;
+  // CTA pairs: adjacent pixel tiles, each CTA holds half of the weight-tile rows
+  P.m_tiles = a->n_img * P.tiles_h * P.tiles_w;
+  auto pair_ok = [&](int n_tile) {
+    return g_igemm_pair != 0 && P.m_tiles % 2 == 0 && n_tile % 16 == 0 && (n_tile / 2) % 8 == 0;
+  };
+  // Resident weights: when this CTA's share of the whole weight operand fits beside two activation slots it
+  // is loaded once (with the first tile) and later tiles stream activations only.
+  const int overhead = 3072;   // barriers + TMEM address + per-CTA channel sums + ticket
+  const long long budget = g_igemm_smem - overhead;
+  const int b_slots = a->n_taps * a->cblocks;
+  auto fits = [&](int n_tile) {
+    const long long bytes = (long long)b_slots * (n_tile / (pair_ok(n_tile) ? 2 : 1)) * 128;
+    return b_slots <= MAX_B && 2LL * P.a_slot_bytes + bytes <= budget;
+  };
+  P.resident = 0;
+  if (g_igemm_resident) {
+    if (fits(P.n_tile)) P.resident = 1;
+  }
+  const int pair = pair_ok(P.n_tile) ? 1 : 0;
+  const int n_tiles = (int)(a->w_rows / P.n_tile);
+  P.acc_cols = P.mt * P.n_tile;
+  {
+    const int cols = 2 * P.acc_cols;   // double-buffered accumulator
+    MP_CHECK_ARG(cols <= 512, "mp_conv_igemm: %d TMEM columns needed", cols);
+    P.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+  }
+
+  // work units and CTAs: every problem gets the same number of persistent CTAs, each a contiguous range
+  P.units = P.m_tiles * n_tiles / (pair ? 2 : 1);
+  int workers = cta_budget() / n_problems / (pair ? 2 : 1);
+  if (workers < 1) workers = 1;
+  if (workers > P.units) workers = P.units;
+  if (P.resident && n_tiles > 1) {   // a CTA's range must stay within one output-channel block
+    if (workers >= n_tiles) workers -= workers % n_tiles;
+    else P.resident = 0;
+  }
+  P.b_slot_bytes = (P.n_tile / (pair ? 2 : 1)) * 128;
   P.dbg = (int)g_igemm_dbg;
+  P.trace = reinterpret_cast<unsigned long long*>(g_igemm_trace);
 
   // shared-memory rings: with halo groups each activation box feeds up to three weight tiles
-  const int overhead = 1024 + 512 + 2048 + 64;   // alignment slack + barriers + per-CTA channel sums + ticket
-  const long long budget = (P.mt > 1 ? g_igemm_smem2 : g_igemm_smem) - overhead;
-  const int a_loads = P.n_groups * a->cblocks, b_loads = a->n_taps * a->cblocks;
   int a_stages, b_stages;
-  if (any_halo) {
-    a_stages = 2;
+  if (P.resident) {
+    b_stages = b_slots;
+    a_stages = (int)((budget - (long long)b_slots * P.b_slot_bytes) / P.a_slot_bytes);
+  } else if (any_halo) {
+    a_stages = 3;
+    if (budget - 3LL * P.a_slot_bytes < 4LL * P.b_slot_bytes) a_stages = 2;
     b_stages = (int)((budget - (long long)a_stages * P.a_slot_bytes) / P.b_slot_bytes);
-    if (b_stages > 6 && budget - 3LL * P.a_slot_bytes - 6LL * P.b_slot_bytes >= 0) a_stages = 3;
-    b_stages = (int)((budget - (long long)a_stages * P.a_slot_bytes) / P.b_slot_bytes);
+    if (b_stages > MAX_STAGES) b_stages = MAX_STAGES;
   } else {
     a_stages = b_stages = (int)(budget / (P.a_slot_bytes + P.b_slot_bytes));
+    if (b_stages > MAX_STAGES) b_stages = MAX_STAGES;
   }
   if (a_stages < 2) a_stages = 2;
   if (b_stages < 2) b_stages = 2;
   if (a_stages > MAX_STAGES) a_stages = MAX_STAGES;
-  if (b_stages > MAX_STAGES) b_stages = MAX_STAGES;
-  if (a_stages > a_loads) a_stages = a_loads < 2 ? 2 : a_loads;
-  if (b_stages > b_loads) b_stages = b_loads < 2 ? 2 : b_loads;
   P.a_stages = a_stages;
   P.b_stages = b_stages;
-  {
-    const int cols = P.n_tile * P.mt;
-    P.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-  }
   P.out_sn = a->out_sn; P.out_sh = a->out_sh; P.out_sw = a->out_sw;
   P.out_c = a->out_c;
   P.stat_replicas = a->stat_replicas > 1 ? a->stat_replicas : 1;
@@ -554,8 +703,14 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
                  "mp_conv_igemm: incomplete BatchNorm finalize arguments");
     P.fin_C = a->bn_channels; P.fin_Cp = a->out_c;
     P.fin_count = a->bn_count; P.fin_momentum = a->bn_momentum; P.fin_eps = a->bn_eps;
-    P.fin_total = a->bn_total_ctas > 0 ? a->bn_total_ctas
-                                       : a->n_img * P.tiles_h * P.tiles_w * (int)(a->w_rows / P.n_tile);
+    // arrivals per problem and launch: one per CTA and run of tiles with the same output-channel block
+    long long arrivals = 0;
+    const int step = pair ? 2 : 1;
+    for (int w = 0; w < workers; ++w) {
+      const long long ub = (long long)w * P.units / workers, ue = (long long)(w + 1) * P.units / workers;
+      if (ue > ub) arrivals += ((ue - 1) * step / P.m_tiles - ub * step / P.m_tiles + 1) * step;
+    }
+    P.fin_total = (int)(arrivals * (a->bn_launches > 1 ? a->bn_launches : 1));
   }
 
   IgemmMaps TM;
@@ -609,7 +764,7 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
     MP_CUDA(cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr_set = true;
   }
-  dim3 grid((unsigned)m_tiles, (unsigned)(a->w_rows / P.n_tile), (unsigned)n_problems);
+  dim3 grid((unsigned)(workers * (pair ? 2 : 1)), 1, (unsigned)n_problems);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(NTHREADS);
@@ -617,12 +772,12 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = P.pair ? 2 : 1;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (P.pair) MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<true>, TM, P));
+  if (pair) MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<true>, TM, P));
   else MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<false>, TM, P));
   MP_CHECK_LAUNCH("mp_conv_igemm");
   return MP_OK;

@@ -65,7 +65,7 @@ wgrad_kernel(const __grid_constant__ WgradMaps TM, const __grid_constant__ Wgrad
   uint64_t* tmem_full = empty + stages;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_idx_uniform(), lane = threadIdx.x & 31;
   const TapGroup& G = P.groups[blockIdx.x / P.n_slices];
   const int slice = blockIdx.x % P.n_slices;
   const int n_off = P.n_off + P.slice_off[slice], n_cols = P.slice_cols[slice];
@@ -94,7 +94,7 @@ wgrad_kernel(const __grid_constant__ WgradMaps TM, const __grid_constant__ Wgrad
   const uint32_t tmem = *tmem_holder;
 
   if (warp == 0) {
-    if (lane == 0) {   // ---------------------------------------------------------- TMA producer
+    {   // --------------------------------------------- TMA producer: warp-uniform loop, one elected lane issues
       int s = 0;
       uint32_t ph = 0;
       const int per_img = P.chunks_w * P.chunks_h;
@@ -107,18 +107,20 @@ wgrad_kernel(const __grid_constant__ WgradMaps TM, const __grid_constant__ Wgrad
         const int h0 = ch * P.kp_rows, w0 = cw * P.kp_w;
         uint8_t* st = smem + (size_t)s * P.stage_bytes;
         tc::mbar_wait(&empty[s], ph ^ 1);
-        tc::mbar_arrive_expect_tx(&full[s], tx);
-        for (int j = 0; j < 2; ++j)
-          tc::tma_load_5d(&tmA, &full[s], st + (size_t)j * P.a_box_bytes, m0 + j * 64, w0, 0, h0, img);
-        uint8_t* sb = st + 2 * (size_t)P.a_box_bytes;
-        for (int j = 0; j < b_boxes; ++j)
-          tc::tma_load_5d(halo ? &tmBh : &tmB, &full[s], sb + (size_t)j * b_box_bytes, G.c0 + n_off + j * 64,
-                          w0 + G.dw, G.p, h0 + G.dh0, img);
+        if (tc::elect_one()) {
+          tc::mbar_arrive_expect_tx(&full[s], tx);
+          for (int j = 0; j < 2; ++j)
+            tc::tma_load_5d(&tmA, &full[s], st + (size_t)j * P.a_box_bytes, m0 + j * 64, w0, 0, h0, img);
+          uint8_t* sb = st + 2 * (size_t)P.a_box_bytes;
+          for (int j = 0; j < b_boxes; ++j)
+            tc::tma_load_5d(halo ? &tmBh : &tmB, &full[s], sb + (size_t)j * b_box_bytes, G.c0 + n_off + j * 64,
+                            w0 + G.dw, G.p, h0 + G.dh0, img);
+        }
         if (++s == stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ------------------------------------------------------------ MMA issuer
+    {   // ----------------------------------------------- MMA issuer: warp-uniform loop, one elected lane issues
       const uint32_t idesc = tc::idesc_bf16(128, n_cols, true, true);
       int s = 0;
       uint32_t ph = 0;
@@ -127,17 +129,20 @@ wgrad_kernel(const __grid_constant__ WgradMaps TM, const __grid_constant__ Wgrad
         tc::tc_fence_after();
         const uint32_t st = tc::smem_u32(smem + (size_t)s * P.stage_bytes);
         const uint32_t sb = st + 2u * (uint32_t)P.a_box_bytes;
-        for (int t = 0; t < G.n; ++t) {
-          const uint32_t bbase = sb + (uint32_t)(t * P.row_bytes);   // row-shifted window of the halo box
-          for (int ks = 0; ks < P.ksteps; ++ks)   // 16 pixels = 16 lines of 128 B per step
-            if (!(P.dbg & 4) || (i | ks) == 0)
-              tc::mma_bf16(tmem + (uint32_t)(t * n_cols), tc::desc_mnmajor_sw128(st + ks * 2048, P.a_box_bytes),
-                           tc::desc_mnmajor_sw128(bbase + ks * 2048, b_box_bytes), idesc, (i | ks) != 0);
+        if (tc::elect_one()) {
+          for (int t = 0; t < G.n; ++t) {
+            const uint32_t bbase = sb + (uint32_t)(t * P.row_bytes);   // row-shifted window of the halo box
+            const uint64_t ad = tc::desc_mnmajor_sw128(st, P.a_box_bytes);
+            const uint64_t bd = tc::desc_mnmajor_sw128(bbase, b_box_bytes);
+            for (int ks = 0; ks < P.ksteps; ++ks)   // 16 pixels = 16 lines of 128 B (2048 B -> +128 in the address field)
+              if (!(P.dbg & 4) || (i | ks) == 0)
+                tc::mma_bf16(tmem + (uint32_t)(t * n_cols), ad + 128 * ks, bd + 128 * ks, idesc, (i | ks) != 0);
+          }
+          tc::mma_commit(&empty[s]);
         }
-        tc::mma_commit(&empty[s]);
         if (++s == stages) { s = 0; ph ^= 1; }
       }
-      tc::mma_commit(tmem_full);
+      if (tc::elect_one()) tc::mma_commit(tmem_full);
     }
   } else {   // ------------------------------------------------------------------------ epilogue
     tc::mbar_wait(tmem_full, 0);
