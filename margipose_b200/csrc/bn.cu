@@ -124,6 +124,8 @@ __device__ __forceinline__ void affine(const mp_bn_args& A, const mp_bn_branch& 
 
 // ------------------------------------------------------------------------------------- forward
 __global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const __grid_constant__ BnGroup GRP) {
+  pdl_trigger();
+  pdl_wait();
   const mp_bn_args& A = GRP.a[blockIdx.y];
   const int c0 = threadIdx.x * 8;
   const bool has_b = A.b.y != nullptr;
@@ -277,6 +279,8 @@ __device__ __forceinline__ void grads_at(const mp_bn_args& A, const LoadsX<NCHW>
 // sums layout per replica: [0] sum dz_a, [1] sum dz_a * y_a, [2] sum dz_b, [3] sum dz_b * y_b
 template <bool NCHW>
 __global__ void __launch_bounds__(MAXT, 2) bn_bwd_reduce_kernel(const __grid_constant__ BnGroup GRP) {
+  pdl_trigger();
+  pdl_wait();
   const mp_bn_args& A = GRP.a[blockIdx.y];
   __shared__ float red[32 * MAXT];
   const int cg = threadIdx.x, c0 = cg * 8;
@@ -401,6 +405,8 @@ __device__ __forceinline__ void bwd_coefs(const mp_bn_args& A, const mp_bn_branc
 
 template <bool NCHW>
 __global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_kernel(const __grid_constant__ BnGroup GRP) {
+  pdl_trigger();
+  pdl_wait();
   const mp_bn_args& A = GRP.a[blockIdx.y];
   const int c0 = threadIdx.x * 8;
   const bool has_b = A.b.y != nullptr;
@@ -538,7 +544,7 @@ int mp_bn_fwd_grouped(const mp_bn_args* args, int n, void* stream) {
   dim3 grid, block;
   launch_dims(args, &grid, &block, U, 2 * 148 / n);
   grid.y = n;
-  bn_fwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(g);
+  MP_CUDA(mp_launch(bn_fwd_kernel, grid, block, 0, (cudaStream_t)stream, g));
   MP_CHECK_LAUNCH("mp_bn_fwd");
   return MP_OK;
 }
@@ -550,8 +556,8 @@ int mp_bn_bwd_reduce_grouped(const mp_bn_args* args, int n, void* stream) {
   dim3 grid, block;
   launch_dims(args, &grid, &block, U, n > 1 ? 2 * 148 / n : 148);
   grid.y = n;
-  if (args->dout) bn_bwd_reduce_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(g);
-  else bn_bwd_reduce_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(g);
+  if (args->dout) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<false>, grid, block, 0, (cudaStream_t)stream, g));
+  else MP_CUDA(mp_launch(bn_bwd_reduce_kernel<true>, grid, block, 0, (cudaStream_t)stream, g));
   MP_CHECK_LAUNCH("mp_bn_bwd_reduce");
   return MP_OK;
 }
@@ -563,8 +569,8 @@ int mp_bn_bwd_apply_grouped(const mp_bn_args* args, int n, void* stream) {
   dim3 grid, block;
   launch_dims(args, &grid, &block, UA, 2 * 148 / n);
   grid.y = n;
-  if (args->dout) bn_bwd_apply_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(g);
-  else bn_bwd_apply_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(g);
+  if (args->dout) MP_CUDA(mp_launch(bn_bwd_apply_kernel<false>, grid, block, 0, (cudaStream_t)stream, g));
+  else MP_CUDA(mp_launch(bn_bwd_apply_kernel<true>, grid, block, 0, (cudaStream_t)stream, g));
   MP_CHECK_LAUNCH("mp_bn_bwd_apply");
   return MP_OK;
 }

@@ -38,6 +38,31 @@ void mp_set_error(const char* fmt, ...);
     }                                                                          \
   } while (0)
 
+// Programmatic dependent launch (tunable "pdl", default on): a kernel launched through mp_launch may
+// be scheduled while its stream predecessor is still running -- its CTAs become resident and run their
+// prologue early -- and must call pdl_wait() before it touches memory the predecessor writes or reads;
+// pdl_trigger() lets the NEXT kernel do the same.  Both are no-ops in a normally launched kernel.
+int mp_pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mp_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = mp_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline bool mp_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -173,11 +173,13 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
     if (PAIR) tc::tmem_alloc_pair(tmem_holder, P.tmem_cols);
     else tc::tmem_alloc(tmem_holder, P.tmem_cols);
   }
+  pdl_trigger();
   tc::tc_fence_before();
   __syncthreads();
   if (PAIR) tc::cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_holder;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
   if (threadIdx.x == 0) trace_at(P, 1);
 
   if (warp == 0) {
@@ -770,13 +772,15 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = pair ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = mp_pdl_enabled() ? 2 : 1;
   if (pair) MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<true>, TM, P));
   else MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<false>, TM, P));
   MP_CHECK_LAUNCH("mp_conv_igemm");

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) combiner_fwd_kernel(const float* __restri
 // dp_k[n, j, pix] = sum_c w[c, k*J + j] * dout[pix, c];  dw[c, kk] += sum_pix dout[pix, c] * p[kk, pix]
 // One block walks CMB_TILES tiles of 32 pixels of one image; the weight-gradient partial sums stay in
 // registers across the tiles, so the block issues one atomic per weight at the end.
-constexpr int CMB_TILES = 8;
+constexpr int CMB_TILES = 2;   // few tiles per block: 4 blocks (32 warps) per SM hide the shared-memory latency of the FMA loops
 constexpr int CMB_WPT = 26;   // weights per thread: ceil(128 * 51 / 256)
 __global__ void __launch_bounds__(256) combiner_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
                                                          const float* __restrict__ p0, const float* __restrict__ p1,

@@ -88,10 +88,12 @@ wgrad_kernel(const __grid_constant__ WgradMaps TM, const __grid_constant__ Wgrad
     tc::prefetch_tmap(&tmBh);
   }
   if (warp == 1) tc::tmem_alloc(tmem_holder, P.tmem_cols);
+  pdl_trigger();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_holder;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     {   // --------------------------------------------- TMA producer: warp-uniform loop, one elected lane issues
@@ -360,7 +362,7 @@ extern "C" int mp_conv_wgrad_grouped(const mp_wgrad_args* args, int n_problems, 
     g_attr_set = true;
   }
   dim3 grid((unsigned)gx, (unsigned)split, (unsigned)(m_tiles * n_problems));
-  wgrad_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(TM, P);
+  MP_CUDA(mp_launch(wgrad_kernel, grid, dim3(NTHREADS), smem, (cudaStream_t)stream, TM, P));
   MP_CHECK_LAUNCH("mp_conv_wgrad");
   return MP_OK;
 }
