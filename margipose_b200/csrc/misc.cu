@@ -25,6 +25,8 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 // ------------------------------------------------------------------ maxpool 3x3 / stride 2 / pad 1
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                    uint8_t* __restrict__ idx, int N, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2, G = C / 8;
   const long long total = (long long)N * Ho * Wo * G;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,6 +63,8 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                                    __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2, G = C / 8;
   const long long total = (long long)N * H * W * G;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -100,6 +104,8 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const u
 // out[n, c', w, g*S + h] = in[n, h, w, g*S + c']  (mode 2)
 __global__ void axis_permute_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                     int mode, int N, int S, int C, int Cp) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)N * S * S * Cp;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -128,6 +134,8 @@ __global__ void __launch_bounds__(256) combiner_fwd_kernel(const float* __restri
                                                          const float* __restrict__ p2, const float* __restrict__ w,
                                                          const __nv_bfloat16* __restrict__ inp,
                                                          __nv_bfloat16* __restrict__ out, int J, int HW, int C) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int K = 3 * J;
   float* sp = sm;                 // [K][CMB_PIX]
@@ -175,6 +183,8 @@ __global__ void __launch_bounds__(256) combiner_bwd_kernel(const __nv_bfloat16* 
                                                          float* __restrict__ dp0, float* __restrict__ dp1,
                                                          float* __restrict__ dp2, float* __restrict__ dw,
                                                          int accumulate, int J, int HW, int C) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int K = 3 * J;
   float* sd = sm;                    // [CMB_PIX][C + 1]
@@ -232,6 +242,8 @@ __global__ void __launch_bounds__(256) combiner_bwd_kernel(const __nv_bfloat16* 
 // patches[n, ho, wo, (r*7+s)*3 + c] = x[n, c, 2*ho + r - 3, 2*wo + s - 3]; 192 columns per row.
 __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
                                    int W) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)N * Ho * Wo * 24;   // 24 groups of 8 columns
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -260,6 +272,8 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* _
 // -------------------------------------------------------------------------------------- add_n
 __global__ void add_bf16_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, const __nv_bfloat16* c,
                                 const __nv_bfloat16* d, int n, __nv_bfloat16* out, long long groups) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= groups) return;
   float acc[8], v[8];
@@ -334,8 +348,8 @@ int mp_maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, in
   MP_CHECK_ARG(x && y && idx && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0,
                "mp_maxpool_fwd: bad arguments");
   const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
-  maxpool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, idx, N, H, W, C);
+  MP_CUDA(mp_launch(maxpool_fwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, idx, N, H, W, C));
   MP_CHECK_LAUNCH("mp_maxpool_fwd");
   return MP_OK;
 }
@@ -343,8 +357,8 @@ int mp_maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, in
 int mp_maxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int N, int H, int W, int C, void* stream) {
   MP_CHECK_ARG(dy && dx && idx && N > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "mp_maxpool_bwd: bad arguments");
   const long long total = (long long)N * H * W * (C / 8);
-  maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dy, idx, (__nv_bfloat16*)dx, N, H, W, C);
+  MP_CUDA(mp_launch(maxpool_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)dy, idx, (__nv_bfloat16*)dx, N, H, W, C));
   MP_CHECK_LAUNCH("mp_maxpool_bwd");
   return MP_OK;
 }
@@ -353,8 +367,8 @@ int mp_axis_permute(const void* in, void* out, int mode, int N, int S, int C, in
   MP_CHECK_ARG(in && out && in != out && (mode == 1 || mode == 2) && N > 0 && S > 0 && C % S == 0 && Cp >= C,
                "mp_axis_permute: bad arguments (the spatial size must divide the channel count)");
   const long long total = (long long)N * S * S * Cp;
-  axis_permute_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)in, (__nv_bfloat16*)out, mode, N, S, C, Cp);
+  MP_CUDA(mp_launch(axis_permute_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
+      (const __nv_bfloat16*)in, (__nv_bfloat16*)out, mode, N, S, C, Cp));
   MP_CHECK_LAUNCH("mp_axis_permute");
   return MP_OK;
 }
@@ -366,8 +380,8 @@ int mp_combiner_fwd(const float* const p[3], const float* w, const void* inp, vo
   const size_t smem = (size_t)(3 * J * CMB_PIX + C * 3 * J) * sizeof(float);
   MP_CHECK_ARG(smem <= 48 * 1024, "mp_combiner_fwd: J*C too large");
   dim3 grid((HW + CMB_PIX - 1) / CMB_PIX, N);
-  combiner_fwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p[0], p[1], p[2], w, (const __nv_bfloat16*)inp,
-                                                                 (__nv_bfloat16*)out, J, HW, C);
+  MP_CUDA(mp_launch(combiner_fwd_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, p[0], p[1], p[2], w, (const __nv_bfloat16*)inp,
+                                                                 (__nv_bfloat16*)out, J, HW, C));
   MP_CHECK_LAUNCH("mp_combiner_fwd");
   return MP_OK;
 }
@@ -385,8 +399,8 @@ int mp_combiner_bwd(const void* dout, const float* const p[3], const float* w, f
     attr_set = true;
   }
   dim3 grid((HW + CMB_PIX * CMB_TILES - 1) / (CMB_PIX * CMB_TILES), N);
-  combiner_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)dout, p[0], p[1], p[2], w,
-                                                                 dp[0], dp[1], dp[2], dw, accumulate, J, HW, C);
+  MP_CUDA(mp_launch(combiner_bwd_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const __nv_bfloat16*)dout, p[0], p[1], p[2], w,
+                                                                 dp[0], dp[1], dp[2], dw, accumulate, J, HW, C));
   MP_CHECK_LAUNCH("mp_combiner_bwd");
   return MP_OK;
 }
@@ -394,8 +408,8 @@ int mp_combiner_bwd(const void* dout, const float* const p[3], const float* w, f
 int mp_stem_im2col(const float* x, void* patches, int N, int H, int W, void* stream) {
   MP_CHECK_ARG(x && patches && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "mp_stem_im2col: bad arguments");
   const long long total = (long long)N * (H / 2) * (W / 2) * 24;
-  stem_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      x, (__nv_bfloat16*)patches, N, H, W);
+  MP_CUDA(mp_launch(stem_im2col_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
+      x, (__nv_bfloat16*)patches, N, H, W));
   MP_CHECK_LAUNCH("mp_stem_im2col");
   return MP_OK;
 }
@@ -404,10 +418,10 @@ int mp_add_bf16(const void* const in[4], int n, void* out, int64_t count, void* 
   MP_CHECK_ARG(in && out && n >= 1 && n <= 4 && count > 0 && count % 8 == 0, "mp_add_bf16: bad arguments");
   for (int i = 0; i < n; ++i) MP_CHECK_ARG(in[i] && mp_aligned16(in[i]), "mp_add_bf16: bad input %d", i);
   const long long groups = count / 8;
-  add_bf16_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  MP_CUDA(mp_launch(add_bf16_kernel, dim3((unsigned)((groups + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)in[0], (const __nv_bfloat16*)(n > 1 ? in[1] : nullptr),
       (const __nv_bfloat16*)(n > 2 ? in[2] : nullptr), (const __nv_bfloat16*)(n > 3 ? in[3] : nullptr), n,
-      (__nv_bfloat16*)out, groups);
+      (__nv_bfloat16*)out, groups));
   MP_CHECK_LAUNCH("mp_add_bf16");
   return MP_OK;
 }

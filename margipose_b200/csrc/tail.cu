@@ -241,6 +241,8 @@ __device__ __forceinline__ void plane_forward(float (&x)[V * VEC], const Geom& g
 
 template <int VEC, int V, bool FROM_LOGITS>
 __global__ void __launch_bounds__(NT) tail_fwd_kernel(const FwdArgs A) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_ecol[MAX_DIM];
   __shared__ float s_erow[MAX_DIM];
   __shared__ float red[NW * 3];
@@ -319,6 +321,8 @@ __global__ void __launch_bounds__(NT) tail_fwd_kernel(const FwdArgs A) {
 //   D = G + w_js * dJS/dp + c_col * c_w + c_row * c_h ;  out = PROJECT ? p * (D - sum(p*D)) : D
 template <int VEC, int V, bool PROJECT>
 __global__ void __launch_bounds__(NT) tail_bwd_kernel(const BwdArgs A) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_ecol[MAX_DIM];
   __shared__ float s_erow[MAX_DIM];
   __shared__ float red[NW * 3];
@@ -489,6 +493,8 @@ struct WarpPlan {
 
 template <int NV, bool FROM_LOGITS>
 __global__ void __launch_bounds__(512, 2) tail_fwd_warp_kernel(const FwdArgs A, const WarpPlan P) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int W = A.g.W, H = A.g.H, HW = A.g.HW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -679,6 +685,8 @@ __global__ void __launch_bounds__(512, 2) tail_fwd_warp_kernel(const FwdArgs A, 
 
 template <int NV, bool PROJECT>
 __global__ void __launch_bounds__(512, 2) tail_bwd_warp_kernel(const BwdArgs A, const WarpPlan P) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int W = A.g.W, H = A.g.H, HW = A.g.HW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -855,14 +863,14 @@ int launch_fwd(const FwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
       const int threads = (P.seq ? 1 : P.groups * P.np) * P.wpp * 32;
       const int blocks = (BJ + P.groups - 1) / P.groups;
       const size_t smem = warp_smem(P, A.g.H, A.g.W, true);
-#define MP_FWDW(NV) tail_fwd_warp_kernel<NV, FROM_LOGITS><<<blocks, threads, smem, st>>>(A, P)
+#define MP_FWDW(NV) mp_launch(tail_fwd_warp_kernel<NV, FROM_LOGITS>, dim3(blocks), dim3(threads), smem, st, A, P)
       if (nv == 1) MP_FWDW(1); else if (nv == 2) MP_FWDW(2); else if (nv == 4) MP_FWDW(4);
       else if (nv == 6) MP_FWDW(6); else MP_FWDW(8);
 #undef MP_FWDW
       return MP_OK;
     }
   }
-#define MP_FWD(VEC, V) tail_fwd_kernel<VEC, V, FROM_LOGITS><<<BJ, NT, 0, st>>>(A)
+#define MP_FWD(VEC, V) mp_launch(tail_fwd_kernel<VEC, V, FROM_LOGITS>, dim3(BJ), dim3(NT), 0, st, A)
   if (vec4) {
     const int v = (HW / 4 + NT - 1) / NT;
     if (v <= 1) MP_FWD(4, 1);
@@ -895,14 +903,14 @@ int launch_bwd(const BwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
       const int threads = (P.seq ? 1 : P.groups * P.np) * P.wpp * 32;
       const int blocks = (BJ + P.groups - 1) / P.groups;
       const size_t smem = warp_smem(P, A.g.H, A.g.W, false);
-#define MP_BWDW(NV) tail_bwd_warp_kernel<NV, PROJECT><<<blocks, threads, smem, st>>>(A, P)
+#define MP_BWDW(NV) mp_launch(tail_bwd_warp_kernel<NV, PROJECT>, dim3(blocks), dim3(threads), smem, st, A, P)
       if (nv == 1) MP_BWDW(1); else if (nv == 2) MP_BWDW(2); else if (nv == 4) MP_BWDW(4);
       else if (nv == 6) MP_BWDW(6); else MP_BWDW(8);
 #undef MP_BWDW
       return MP_OK;
     }
   }
-#define MP_BWD(VEC, V) tail_bwd_kernel<VEC, V, PROJECT><<<BJ, NT, 0, st>>>(A)
+#define MP_BWD(VEC, V) mp_launch(tail_bwd_kernel<VEC, V, PROJECT>, dim3(BJ), dim3(NT), 0, st, A)
   if (vec4) {
     const int v = (HW / 4 + NT - 1) / NT;
     if (v <= 1) MP_BWD(4, 1);
