@@ -129,6 +129,173 @@ __global__ void axis_permute_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
 // ------------------------------------------------------------------------------------ combiner
 // One block = 32 pixels of one image: probabilities staged in shared memory, each thread owns
 // 8 consecutive output channels of 2 pixels... kept simple: thread = (pixel, 8 channels).
+// ---- register-tiled combiner kernels (C <= 128): 64 pixels per tile, 128-bit shared-memory loads, ~10 FMA per load
+constexpr int CT_PIX = 64;
+
+// out[pix, c] = inp[pix, c] + sum_k w[c, k] * p_k[pix]; thread = 8 channels x 4 pixels.
+__global__ void __launch_bounds__(256) combiner_fwd_tiled_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
+                                                               const float* __restrict__ p2, const float* __restrict__ w,
+                                                               const __nv_bfloat16* __restrict__ inp,
+                                                               __nv_bfloat16* __restrict__ out, int J, int HW, int C) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float smt[];
+  const int K = 3 * J, CS = C + 4, G = C / 8;
+  float* swT = smt;              // [K][C + 4]: k-major so a thread's 8 channels are two 128-bit loads
+  float* sp = smt + K * CS;      // [K][64]
+  const int n = blockIdx.y, pix0 = blockIdx.x * CT_PIX;
+  for (int i = threadIdx.x; i < C * K; i += blockDim.x) {
+    const int c = i / K, k = i - c * K;
+    swT[k * CS + c] = w[i];
+  }
+  for (int i = threadIdx.x; i < K * CT_PIX; i += blockDim.x) {
+    const int k = i / CT_PIX, px = i - k * CT_PIX;
+    const float* src = k < J ? p0 : (k < 2 * J ? p1 : p2);
+    sp[i] = (pix0 + px < HW) ? src[((long long)n * J + (k % J)) * HW + pix0 + px] : 0.f;
+  }
+  __syncthreads();
+  const int g = threadIdx.x % G, q = threadIdx.x / G;   // 16 pixel quads x G channel groups
+  if (q >= CT_PIX / 4) return;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float4 wa = *reinterpret_cast<const float4*>(swT + k * CS + g * 8);
+    const float4 wb = *reinterpret_cast<const float4*>(swT + k * CS + g * 8 + 4);
+    const float4 pv = *reinterpret_cast<const float4*>(sp + k * CT_PIX + q * 4);
+    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+    const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv[j], pp[i], acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int px = pix0 + q * 4 + i;
+    if (px >= HW) break;
+    const long long o = ((long long)n * HW + px) * C + g * 8;
+    float base[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(inp + o)), base);
+    // fp32 weights, fp32 probabilities, fp32 accumulate; the new stage input is rounded to bf16 once
+#pragma unroll
+    for (int j = 0; j < 8; ++j) base[j] += acc[i][j];
+    *reinterpret_cast<uint4*>(out + o) = pack8(base);
+  }
+}
+
+// dp_k[n, j, pix] = sum_c w[c, k] * dout[pix, c]  (thread = 4 pixels x 4 k);
+// dw[c, k] += sum_pix dout[pix, c] * p_k[pix]      (thread = 8 channels x 4 k, kept in registers over the block's tiles)
+constexpr int CT_TILES = 2;
+__global__ void __launch_bounds__(256) combiner_bwd_tiled_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                               const float* __restrict__ p0, const float* __restrict__ p1,
+                                                               const float* __restrict__ p2, const float* __restrict__ w,
+                                                               float* __restrict__ dp0, float* __restrict__ dp1,
+                                                               float* __restrict__ dp2, float* __restrict__ dw,
+                                                               int accumulate, int J, int HW, int C) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float smt[];
+  const int K = 3 * J, KP = (K + 3) & ~3, CS = C + 4, G = C / 8, KG = KP / 4;
+  float* sdT = smt;                    // [64][C + 4] upstream gradient tile, fp32
+  float* sw = sdT + CT_PIX * CS;       // [C][KP]
+  float* spT = sw + C * KP;            // [64][KP] probabilities, pixel-major
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < C * KP; i += blockDim.x) {
+    const int c = i / KP, k = i - c * KP;
+    sw[i] = k < K ? w[c * K + k] : 0.f;
+  }
+  const int kq = threadIdx.x % 16, q = threadIdx.x / 16;      // dp role: k group (4 k) x pixel quad
+  const int cg = threadIdx.x % G, kg = threadIdx.x / G;       // dw role: channel group (8 c) x k group (4 k)
+  const bool dw_active = kg < KG;
+  float wacc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wacc[i][j] = 0.f;
+  for (int tile = 0; tile < CT_TILES; ++tile) {
+    const int pix0 = (blockIdx.x * CT_TILES + tile) * CT_PIX;
+    if (pix0 >= HW) break;
+    __syncthreads();
+    for (int i = threadIdx.x; i < CT_PIX * G; i += blockDim.x) {
+      const int px = i / G, g = i - px * G;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      if (pix0 + px < HW) unpack8(__ldg(reinterpret_cast<const uint4*>(dout + ((long long)n * HW + pix0 + px) * C + g * 8)), v);
+      *reinterpret_cast<float4*>(sdT + px * CS + g * 8) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(sdT + px * CS + g * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    for (int i = threadIdx.x; i < KP * CT_PIX; i += blockDim.x) {
+      const int k = i / CT_PIX, px = i - k * CT_PIX;
+      float v = 0.f;
+      if (k < K && pix0 + px < HW) {
+        const float* src = k < J ? p0 : (k < 2 * J ? p1 : p2);
+        v = src[((long long)n * J + (k % J)) * HW + pix0 + px];
+      }
+      spT[px * KP + k] = v;
+    }
+    __syncthreads();
+    if (kq * 4 < K) {   // ---- dp: 4 pixels x 4 k per thread
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int c = 0; c < C; c += 4) {
+        float d[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 t = *reinterpret_cast<const float4*>(sdT + (q * 4 + i) * CS + c);
+          d[i][0] = t.x; d[i][1] = t.y; d[i][2] = t.z; d[i][3] = t.w;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float4 t = *reinterpret_cast<const float4*>(sw + (c + cc) * KP + kq * 4);
+          const float wv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[j], d[i][cc], acc[i][j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = kq * 4 + j;
+        if (k >= K) break;
+        float* dst = (k < J ? dp0 : (k < 2 * J ? dp1 : dp2)) + ((long long)n * J + (k % J)) * HW + pix0 + q * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (pix0 + q * 4 + i < HW) dst[i] = accumulate ? dst[i] + acc[i][j] : acc[i][j];
+      }
+    }
+    if (dw_active) {   // ---- dw: 8 channels x 4 k per thread over the tile's pixels
+      for (int px = 0; px < CT_PIX; ++px) {
+        const float4 da = *reinterpret_cast<const float4*>(sdT + px * CS + cg * 8);
+        const float4 db = *reinterpret_cast<const float4*>(sdT + px * CS + cg * 8 + 4);
+        const float4 pv = *reinterpret_cast<const float4*>(spT + px * KP + kg * 4);
+        const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+        const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) wacc[i][j] = fmaf(dv[i], pp[j], wacc[i][j]);
+      }
+    }
+  }
+  if (dw_active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = kg * 4 + j;
+        if (k < K) atomicAdd(dw + (cg * 8 + i) * K + k, wacc[i][j]);
+      }
+  }
+}
+
 constexpr int CMB_PIX = 32;
 __global__ void __launch_bounds__(256) combiner_fwd_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
                                                          const float* __restrict__ p2, const float* __restrict__ w,
@@ -324,20 +491,40 @@ __global__ void pack_weights_kernel(const float* __restrict__ master, __nv_bfloa
 }
 
 // ------------------------------------------------------------------------------------------ SGD
-__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
-                           long long n, float lr, float mom, float damp, float wd, int nesterov, int first,
-                           float gscale) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float grad = g[i] * gscale;
-  const float w = p[i];
+__device__ __forceinline__ float sgd_one(float w, float grad, float& b, float lr, float mom, float damp, float wd,
+                                        int nesterov, int first) {
   if (wd != 0.f) grad = fmaf(wd, w, grad);
   if (mom != 0.f) {
-    const float b = first ? grad : fmaf(mom, buf[i], (1.f - damp) * grad);
-    buf[i] = b;
+    b = first ? grad : fmaf(mom, b, (1.f - damp) * grad);
     grad = nesterov ? fmaf(mom, b, grad) : b;
   }
-  p[i] = fmaf(-lr, grad, w);
+  return fmaf(-lr, grad, w);
+}
+
+// 4 parameters per thread (128-bit accesses), grid-stride; the scalar tail goes to the last few threads.
+__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                  float* __restrict__ buf, long long n, float lr, float mom, float damp,
+                                                  float wd, int nesterov, int first, float gscale) {
+  const long long n4 = n >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 w = reinterpret_cast<float4*>(p)[i];
+    const float4 gr = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mom != 0.f && !first) b = reinterpret_cast<float4*>(buf)[i];
+    w.x = sgd_one(w.x, gr.x * gscale, b.x, lr, mom, damp, wd, nesterov, first);
+    w.y = sgd_one(w.y, gr.y * gscale, b.y, lr, mom, damp, wd, nesterov, first);
+    w.z = sgd_one(w.z, gr.z * gscale, b.z, lr, mom, damp, wd, nesterov, first);
+    w.w = sgd_one(w.w, gr.w * gscale, b.w, lr, mom, damp, wd, nesterov, first);
+    if (mom != 0.f) reinterpret_cast<float4*>(buf)[i] = b;
+    reinterpret_cast<float4*>(p)[i] = w;
+  }
+  const long long t = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    float b = (mom != 0.f && !first) ? buf[t] : 0.f;
+    p[t] = sgd_one(p[t], g[t] * gscale, b, lr, mom, damp, wd, nesterov, first);
+    if (mom != 0.f) buf[t] = b;
+  }
 }
 
 }  // namespace
@@ -377,6 +564,19 @@ int mp_combiner_fwd(const float* const p[3], const float* w, const void* inp, vo
                     int C, void* stream) {
   MP_CHECK_ARG(p && p[0] && p[1] && p[2] && w && inp && out && N > 0 && J > 0 && HW > 0 && C % 8 == 0,
                "mp_combiner_fwd: bad arguments");
+  if (C <= 128 && 3 * J <= 64 && 256 % (C / 8) == 0) {   // register-tiled kernel (the MargiPose shape: C = 128, J = 17)
+    const size_t smem_t = (size_t)(3 * J * (C + 4) + 3 * J * CT_PIX) * sizeof(float);
+    static bool attr_f = false;
+    if (!attr_f) {
+      MP_CUDA(cudaFuncSetAttribute(combiner_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_f = true;
+    }
+    dim3 grid_t((HW + CT_PIX - 1) / CT_PIX, N);
+    MP_CUDA(mp_launch(combiner_fwd_tiled_kernel, grid_t, dim3(256), smem_t, (cudaStream_t)stream, p[0], p[1], p[2], w,
+                      (const __nv_bfloat16*)inp, (__nv_bfloat16*)out, J, HW, C));
+    MP_CHECK_LAUNCH("mp_combiner_fwd");
+    return MP_OK;
+  }
   const size_t smem = (size_t)(3 * J * CMB_PIX + C * 3 * J) * sizeof(float);
   MP_CHECK_ARG(smem <= 48 * 1024, "mp_combiner_fwd: J*C too large");
   dim3 grid((HW + CMB_PIX - 1) / CMB_PIX, N);
@@ -391,6 +591,20 @@ int mp_combiner_bwd(const void* dout, const float* const p[3], const float* w, f
   MP_CHECK_ARG(dout && p && p[0] && p[1] && p[2] && w && dp && dp[0] && dp[1] && dp[2] && dw && N > 0 && J > 0 &&
                    HW > 0 && C > 0,
                "mp_combiner_bwd: bad arguments");
+  if (C % 8 == 0 && C <= 128 && 3 * J <= 64 && 256 % (C / 8) == 0 && (256 / (C / 8)) * 4 >= ((3 * J + 3) & ~3)) {
+    const int KP = (3 * J + 3) & ~3;
+    const size_t smem_t = (size_t)(CT_PIX * (C + 4) + C * KP + CT_PIX * KP) * sizeof(float);
+    static bool attr_b = false;
+    if (!attr_b) {
+      MP_CUDA(cudaFuncSetAttribute(combiner_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_b = true;
+    }
+    dim3 grid_t((HW + CT_PIX * CT_TILES - 1) / (CT_PIX * CT_TILES), N);
+    MP_CUDA(mp_launch(combiner_bwd_tiled_kernel, grid_t, dim3(256), smem_t, (cudaStream_t)stream,
+                      (const __nv_bfloat16*)dout, p[0], p[1], p[2], w, dp[0], dp[1], dp[2], dw, accumulate, J, HW, C));
+    MP_CHECK_LAUNCH("mp_combiner_bwd");
+    return MP_OK;
+  }
   const size_t smem = (size_t)(CMB_PIX * (C + 1) + C * 3 * J + 3 * J * (CMB_PIX + 1)) * sizeof(float);
   MP_CHECK_ARG(smem <= 96 * 1024 && (long long)C * 3 * J <= 256 * CMB_WPT, "mp_combiner_bwd: J*C too large");
   static bool attr_set = false;
@@ -441,7 +655,12 @@ int mp_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n,
                 float dampening, float weight_decay, int nesterov, int first_step, float grad_scale,
                 void* stream) {
   MP_CHECK_ARG(param && grad && n > 0 && (momentum == 0.f || momentum_buf), "mp_sgd_step: bad arguments");
-  sgd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  MP_CHECK_ARG(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
+                 reinterpret_cast<uintptr_t>(momentum_buf)) & 15) == 0, "mp_sgd_step: buffers must be 16-byte aligned");
+  long long blocks = ((n >> 2) + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  sgd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       param, grad, momentum_buf, n, lr, momentum, dampening, weight_decay, nesterov, first_step, grad_scale);
   MP_CHECK_LAUNCH("mp_sgd_step");
   return MP_OK;

@@ -132,14 +132,17 @@ wgrad_kernel(const __grid_constant__ WgradMaps TM, const __grid_constant__ Wgrad
         const uint32_t st = tc::smem_u32(smem + (size_t)s * P.stage_bytes);
         const uint32_t sb = st + 2u * (uint32_t)P.a_box_bytes;
         if (tc::elect_one()) {
-          for (int t = 0; t < G.n; ++t) {
-            const uint32_t bbase = sb + (uint32_t)(t * P.row_bytes);   // row-shifted window of the halo box
-            const uint64_t ad = tc::desc_mnmajor_sw128(st, P.a_box_bytes);
-            const uint64_t bd = tc::desc_mnmajor_sw128(bbase, b_box_bytes);
-            for (int ks = 0; ks < P.ksteps; ++ks)   // 16 pixels = 16 lines of 128 B (2048 B -> +128 in the address field)
+          // 16 pixels = 16 lines of 128 B per K step (2048 B -> +128 in the descriptor's address field); tap t reads the
+          // row-shifted window t of the halo box.  (Taking turns between the taps' accumulators per K step measured
+          // slower here than finishing one tap's K steps first.)
+          const uint64_t ad = tc::desc_mnmajor_sw128(st, P.a_box_bytes);
+          const uint64_t bd0 = tc::desc_mnmajor_sw128(sb, b_box_bytes);
+          const uint32_t tap_step = (uint32_t)P.row_bytes >> 4;
+          for (int t = 0; t < G.n; ++t)
+            for (int ks = 0; ks < P.ksteps; ++ks)
               if (!(P.dbg & 4) || (i | ks) == 0)
-                tc::mma_bf16(tmem + (uint32_t)(t * n_cols), ad + 128 * ks, bd + 128 * ks, idesc, (i | ks) != 0);
-          }
+                tc::mma_bf16(tmem + (uint32_t)(t * n_cols), ad + 128 * ks, bd0 + (uint64_t)(t * tap_step) + 128 * ks, idesc,
+                             (i | ks) != 0);
           tc::mma_commit(&empty[s]);
         }
         if (++s == stages) { s = 0; ph ^= 1; }
