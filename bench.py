@@ -11,8 +11,9 @@ seeded random-init weights (no network for datasets / checkpoints).
   value : steps run from device-resident inputs (CUDA events, max over ranks)
   e2e   : the same step through the public API (margipose_b200.train.TrainStep.__call__) fed from
           pinned HOST buffers each step, loss read back to the host each step
-  roofline : the tcgen05 implicit-GEMM conv kernel (mp_conv_igemm: fprop + dgrad launches of
-          one step), algorithmic FLOPs / CUDA-event time per launch vs the measured bf16 peak
+  roofline : the tcgen05 implicit-GEMM conv kernel (mp_conv_igemm: the grouped fprop + dgrad launches
+          of one step, each alone on the GPU, replayed from a CUDA graph), algorithmic FLOPs / CUDA-event
+          time per launch vs the measured sustained bf16 peak
   cpu_baseline / --impl reference : the reference algorithm's CPU path (the fp32 oracle port
           of /root/reference/src/margipose, the unmodified reference cannot travel to the GPU box)
           on the host cores, on a bounded sample of the same workload
@@ -249,7 +250,9 @@ def run_b200(args):
         wn, wt, wf = classes['mp_conv_wgrad']
         roof = {'bound': 'tensor', 'kernel': 'igemm_kernel (mp_conv_igemm: conv fprop + dgrad)', 'achieved': achieved,
                 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': traffic,
-                'traffic_note': 'DRAM bytes of the 128->128 3x3 @32x32 launch (profiles/r01_igemm_ncu.md)',
+                'traffic_note': 'DRAM bytes (read + write) of the dominant grouped launch, 3 x (128->128 3x3 @32x32) forward + BN '
+                                'statistics, ncu --set full (profiles/r01_igemm_ncu.md launch 0); algorithmic bytes 51.2 MB, the '
+                                'bf16 outputs stay in the 126 MB L2',
                 'peak_source': src + ' bf16 sustained (MEASURED_PEAKS.json)', 'launches_per_step': n,
                 'avg_launch_us': 1e3 * t_ms / n, 'flops_per_launch': fl / n,
                 'serial_ms_per_step': {k: v[1] for k, v in classes.items()},
