@@ -305,17 +305,24 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
       if (et == 0) trace_at(P, 6 + it * 4);                        // accumulator of tile `it` complete
       const uint32_t acc = tmem + (uint32_t)(buf * P.acc_cols);
       const int n0 = T.n0, img = T.img;
-      for (int mt = 0; mt < ((P.dbg & 4) ? 0 : P.mt); ++mt)
-      for (int c = (mt * nchunks + half) & 1; c < nchunks; c += 2) {
-        const int h = T.h0 + mt * P.tile_rows + r, w = T.w0 + wq;
-        const bool valid = (r < P.tile_rows) && (h < P.out_h) && (w < P.out_w);
-        const long long pix = (long long)img * P.out_sn + (long long)h * P.out_sh + (long long)w * P.out_sw;
+      // The two warps of a TMEM lane quarter split the 32-column chunks by parity; a warp drains its chunk for
+      // BOTH row blocks of the tile, so the BatchNorm sums of the two blocks are added per thread before the
+      // (expensive) cross-lane transpose-reduction.
+      for (int c = half; c < ((P.dbg & 4) ? 0 : nchunks); c += 2) {
         const int ch = n0 + c * 32;
         if (ch >= P.out_c) break;   // warp-uniform
-        float v[32];
-        tc::tmem_ld32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * P.n_tile + c * 32), v);
-        uint32_t packed[16];
-        if (valid) {
+        float s1[32], s2[32];
+        if (Q.stat_sum) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+        }
+        for (int mt = 0; mt < P.mt; ++mt) {
+          const int h = T.h0 + mt * P.tile_rows + r, w = T.w0 + wq;
+          const bool valid = (r < P.tile_rows) && (h < P.out_h) && (w < P.out_w);
+          const long long pix = (long long)img * P.out_sn + (long long)h * P.out_sh + (long long)w * P.out_sw;
+          float v[32];
+          tc::tmem_ld32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * P.n_tile + c * 32), v);
+          if (!valid) continue;
           if (Q.res) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -331,6 +338,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
               }
             }
           }
+          uint32_t packed[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) packed[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
 #pragma unroll
@@ -339,16 +347,16 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
               *reinterpret_cast<uint4*>(Q.out + pix + ch + i * 8) =
                   make_uint4(packed[i * 4], packed[i * 4 + 1], packed[i * 4 + 2], packed[i * 4 + 3]);
           }
-        }
-        if (Q.stat_sum) {   // statistics of the values as stored (bf16-rounded)
-          float s1[32], s2[32];
+          if (Q.stat_sum) {   // statistics of the values as stored (bf16-rounded)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float2 f = make_float2(0.f, 0.f);
-            if (valid) f = unpack_bf16x2(packed[j]);
-            s1[2 * j] = f.x; s1[2 * j + 1] = f.y;
-            s2[2 * j] = f.x * f.x; s2[2 * j + 1] = f.y * f.y;
+            for (int j = 0; j < 16; ++j) {
+              const float2 f = unpack_bf16x2(packed[j]);
+              s1[2 * j] += f.x; s1[2 * j + 1] += f.y;
+              s2[2 * j] = fmaf(f.x, f.x, s2[2 * j]); s2[2 * j + 1] = fmaf(f.y, f.y, s2[2 * j + 1]);
+            }
           }
+        }
+        if (Q.stat_sum) {
           const float a1 = tc::warp_transpose_sum(s1);
           const float a2 = tc::warp_transpose_sum(s2);
           atomicAdd(s_stat + c * 32 + lane, a1);          // the epilogue warps meet in shared memory ...
