@@ -310,6 +310,13 @@ MP_API int mp_pack_weights(const float* master, void* packed, const mp_pack_entr
 MP_API int mp_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr,
                        float momentum, float dampening, float weight_decay, int nesterov,
                        int first_step, float grad_scale, void* stream);
+/* Same, but when `hyper` (device pointer to 5 floats: lr, momentum, dampening, weight_decay, grad_scale) is given
+ * the kernel reads the hyperparameters from it at run time, so a step captured in a CUDA graph follows LR /
+ * momentum schedules (the reference's 1-cycle schedule, hyperparam_scheduler.py:24-42; momentum_buf is then
+ * required).  nesterov / first_step stay launch-time constants. */
+MP_API int mp_sgd_step_hp(float* param, const float* grad, float* momentum_buf, int64_t n, float lr,
+                          float momentum, float dampening, float weight_decay, int nesterov,
+                          int first_step, float grad_scale, const float* hyper, void* stream);
 
 /* Tunables for experiments (name -> value); returns MP_ERR_ARG for unknown names.
  *   "igemm_smem"  : shared-memory budget per (persistent) CTA of mp_conv_igemm in bytes (default 204800)
@@ -323,7 +330,7 @@ MP_API int mp_sgd_step(float* param, const float* grad, float* momentum_buf, int
  *   "igemm_split_n": mp_conv_igemm halves its N tile when a launch has fewer tiles than this (default 0 = the CTA count)
  *   "igemm_dbg"   : experiment switches (1 = no TMA loads, 2 = no MMA, 4 = no epilogue)
  *   "wgrad_ctas"  : target CTA count of mp_conv_wgrad (default 148)
- *   "wgrad_halo"  : 1 (default) = up to three row-shifted taps per CTA share the A tile and one halo box of B
+ *   "wgrad_halo"  : 1 = up to three row-shifted taps per CTA share the A tile and one halo box of B; 0 (default) = one tap per CTA
  *   "wgrad_slice" : widest column slice of B per CTA when taps are grouped (default 256; 64 or 128 narrow it)
  *   "wgrad_kp"    : pixels per pipeline stage of mp_conv_wgrad (default 128)
  *   "wgrad_dbg"   : experiment switches (1 = skip the gradient atomics, 4 = no MMA) */

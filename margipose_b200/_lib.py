@@ -113,6 +113,8 @@ def _signatures():
         'mp_pack_weights': (I, [P, P, P, I, ctypes.c_int64, P]),
         'mp_sgd_step': (I, [P, P, P, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                             ctypes.c_float, I, I, ctypes.c_float, P]),
+        'mp_sgd_step_hp': (I, [P, P, P, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                               ctypes.c_float, I, I, ctypes.c_float, P, P]),
     }
 
 

@@ -415,9 +415,11 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* _
   const long long total = (long long)N * Ho * Wo * 24;   // 24 groups of 8 columns
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int g = (int)(i % 24);
-  long long t = i / 24;
-  const int wo = (int)(t % Wo); t /= Wo;
+  // consecutive threads = consecutive output columns of one 8-column group: the image reads of a warp are
+  // one stride-2 run per (tap, channel) instead of 24 scattered runs per pixel
+  const int wo = (int)(i % Wo);
+  long long t = i / Wo;
+  const int g = (int)(t % 24); t /= 24;
   const int ho = (int)(t % Ho);
   const int n = (int)(t / Ho);
   float v[8];
@@ -504,7 +506,11 @@ __device__ __forceinline__ float sgd_one(float w, float grad, float& b, float lr
 // 4 parameters per thread (128-bit accesses), grid-stride; the scalar tail goes to the last few threads.
 __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                   float* __restrict__ buf, long long n, float lr, float mom, float damp,
-                                                  float wd, int nesterov, int first, float gscale) {
+                                                  float wd, int nesterov, int first, float gscale,
+                                                  const float* __restrict__ hyper) {
+  if (hyper) {   // hyperparameters live in device memory: schedulers keep working when the step is a replayed CUDA graph
+    lr = hyper[0]; mom = hyper[1]; damp = hyper[2]; wd = hyper[3]; gscale = hyper[4];
+  }
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -654,14 +660,21 @@ int mp_pack_weights(const float* master, void* packed, const mp_pack_entry* tabl
 int mp_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
                 float dampening, float weight_decay, int nesterov, int first_step, float grad_scale,
                 void* stream) {
-  MP_CHECK_ARG(param && grad && n > 0 && (momentum == 0.f || momentum_buf), "mp_sgd_step: bad arguments");
+  return mp_sgd_step_hp(param, grad, momentum_buf, n, lr, momentum, dampening, weight_decay, nesterov, first_step,
+                        grad_scale, nullptr, stream);
+}
+
+int mp_sgd_step_hp(float* param, const float* grad, float* momentum_buf, int64_t n, float lr, float momentum,
+                   float dampening, float weight_decay, int nesterov, int first_step, float grad_scale,
+                   const float* hyper, void* stream) {
+  MP_CHECK_ARG(param && grad && n > 0 && ((momentum == 0.f && !hyper) || momentum_buf), "mp_sgd_step: bad arguments");
   MP_CHECK_ARG(((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
                  reinterpret_cast<uintptr_t>(momentum_buf)) & 15) == 0, "mp_sgd_step: buffers must be 16-byte aligned");
   long long blocks = ((n >> 2) + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
   sgd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      param, grad, momentum_buf, n, lr, momentum, dampening, weight_decay, nesterov, first_step, grad_scale);
+      param, grad, momentum_buf, n, lr, momentum, dampening, weight_decay, nesterov, first_step, grad_scale, hyper);
   MP_CHECK_LAUNCH("mp_sgd_step");
   return MP_OK;
 }

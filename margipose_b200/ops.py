@@ -115,7 +115,9 @@ def add_bf16(tensors):
 
 
 def sgd_step(param, grad, buf, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False,
-             first_step=False, grad_scale=1.0):
-    check(lib().mp_sgd_step(param.data_ptr(), grad.data_ptr(), _p(buf), param.numel(), lr, momentum, dampening,
-                            weight_decay, int(nesterov), int(first_step), grad_scale,
-                            stream_ptr(param.device)), 'mp_sgd_step')
+             first_step=False, grad_scale=1.0, hyper=None):
+    """hyper: optional device tensor (lr, momentum, dampening, weight_decay, grad_scale) read by the kernel
+    at run time instead of the launch-time scalars (CUDA-graph-safe schedules)."""
+    check(lib().mp_sgd_step_hp(param.data_ptr(), grad.data_ptr(), _p(buf), param.numel(), lr, momentum, dampening,
+                               weight_decay, int(nesterov), int(first_step), grad_scale, _p(hyper),
+                               stream_ptr(param.device)), 'mp_sgd_step')

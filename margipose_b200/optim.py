@@ -26,6 +26,18 @@ class FlatSGD(torch.optim.Optimizer):
         self.momentum_buf = torch.zeros_like(self.bank.flat)
         self._steps = 0
         self.grad_scale = 1.0     # e.g. 1 / world_size after a summing all-reduce
+        # (lr, momentum, dampening, weight_decay, grad_scale) as the kernel reads them: a pinned host mirror that
+        # refresh_hyper() fills from param_groups and an async copy into device memory in front of every step.
+        # The copy is part of a captured step, so a replayed CUDA graph picks up whatever a scheduler wrote.
+        self._hyper_host = torch.zeros(8).pin_memory()
+        self._hyper = torch.zeros(8, device=device)
+
+    def refresh_hyper(self):
+        """Host side only: publish the current param_groups hyperparameters to the pinned mirror (call before
+        replaying a CUDA graph that contains step(); step() itself does it when run eagerly)."""
+        g = self.param_groups[0]
+        h = self._hyper_host
+        h[0], h[1], h[2], h[3], h[4] = g['lr'], g['momentum'], g['dampening'], g['weight_decay'], self.grad_scale
 
     def zero_grad(self, set_to_none=False):
         self.bank.flat_grad.zero_()
@@ -43,9 +55,11 @@ class FlatSGD(torch.optim.Optimizer):
             raise RuntimeError('the model was re-materialised (moved / re-created) after this optimiser '
                                'was built; create the optimiser after model.cuda()')
         g = self.param_groups[0]
+        self.refresh_hyper()
+        self._hyper.copy_(self._hyper_host, non_blocking=True)
         ops.sgd_step(self.bank.flat, self.bank.flat_grad, self.momentum_buf, g['lr'], g['momentum'],
                      g['dampening'], g['weight_decay'], g['nesterov'], first_step=(self._steps == 0),
-                     grad_scale=self.grad_scale)
+                     grad_scale=self.grad_scale, hyper=self._hyper)
         self._steps += 1
         self.model.mark_params_dirty()
         return loss

@@ -60,6 +60,8 @@ class TrainStep:
         if self._graphs is not None:
             self._graphs[0].replay()
             self._allreduce()
+            if hasattr(self.opt, 'refresh_hyper'):
+                self.opt.refresh_hyper()   # LR / momentum schedules reach the captured optimiser step
             self._graphs[1].replay()
         else:
             self._fwd_bwd()

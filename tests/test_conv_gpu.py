@@ -26,12 +26,12 @@ def test_fused_block_dgrad(stride, tr):
     K.check_fused_block_dgrad(stride, tr)
 
 
-DEFAULTS = {'igemm_halo': 1, 'wgrad_halo': 1, 'igemm_pair': 1, 'igemm_resident': 1, 'wgrad_kp': 128, 'igemm_mt': 2,
+DEFAULTS = {'igemm_halo': 1, 'wgrad_halo': 0, 'igemm_pair': 1, 'igemm_resident': 1, 'wgrad_kp': 128, 'igemm_mt': 2,
             'igemm_mt_ctas': 0, 'wgrad_slice': 256, 'wgrad_ctas': 148}
 
 
 @pytest.mark.parametrize('tunables', [
-    {'igemm_halo': 0, 'wgrad_halo': 0}, {'igemm_pair': 0}, {'igemm_resident': 0}, {'igemm_pair': 0, 'igemm_resident': 0},
+    {'igemm_halo': 0, 'wgrad_halo': 1}, {'igemm_pair': 0}, {'igemm_resident': 0}, {'igemm_pair': 0, 'igemm_resident': 0},
     {'igemm_mt_ctas': 1}, {'igemm_mt_ctas': 1, 'igemm_pair': 0}, {'igemm_mt': 1}, {'igemm_mt_ctas': 1, 'igemm_resident': 0},
     {'wgrad_slice': 64, 'wgrad_ctas': 40, 'wgrad_kp': 64},
 ], ids=lambda d: ','.join('%s=%d' % kv for kv in d.items()))

@@ -243,3 +243,31 @@ def test_optimizer_step_changes_output_and_flat_sgd_matches_torch_sgd():
     for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         if p1.dim() == 4:      # conv weights; near-zero BatchNorm biases have no meaningful relative error
             assert rel(p1.detach(), p2.detach()) < 0.05, k
+
+
+def test_train_step_cuda_graph_follows_lr_schedule():
+    """The optimiser step is captured in a CUDA graph; its hyperparameters must still follow param_groups
+    (the reference drives LR and momentum with a 1-cycle schedule, hyperparam_scheduler.py:24-42)."""
+    from margipose_b200.models import create_model
+    from margipose_b200.optim import FlatSGD
+    from margipose_b200.train import TrainStep
+    desc = {'type': 'margipose', 'version': '6.0.1',
+            'settings': dict(n_stages=1, feature_extractor='resnet18')}
+    torch.manual_seed(7)
+    model = create_model(desc).cuda().train()
+    opt = FlatSGD(model, lr=1e-2, momentum=0.9)
+    step = TrainStep(model, opt, batch=2, warmup=1)
+    x, target, mask = model_inputs(8, 2)
+    for _ in range(3):
+        step(x, target, mask)
+    assert step._graphs is not None, 'the step should be replaying CUDA graphs by now'
+    flat = model._bank.flat
+    for g in opt.param_groups:
+        g['lr'] = 0.0
+    before = flat.clone()
+    step(x, target, mask)
+    assert torch.equal(before, flat), 'lr = 0 must freeze the parameters, graph or not'
+    for g in opt.param_groups:
+        g['lr'] = 1e-2
+    step(x, target, mask)
+    assert not torch.equal(before, flat)
