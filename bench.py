@@ -159,6 +159,58 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def tail_sweep(peak_bw, sizes=(32, 64, 128), batch=128):
+    """BASELINE.json configs[3]: the fused flat_softmax + dsnt (+ xyz combination) kernel, and the full fused tail
+    (+ Gaussian targets, JS divergences, Euclidean loss), forward and backward, three planes, 17 joints, batch 128:
+    achieved HBM GB/s = algorithmic bytes (8 per heatmap element forward: logit in, probability out; 12 backward:
+    probability + upstream gradient in, d logit out) / CUDA-event time, inputs rotated through > 126 MB (L2)."""
+    import torch
+    from margipose_b200 import dsntnn as K
+    B, J = batch, JOINTS
+    out = []
+    for S in sizes:
+        n_sets = max(2, int(300e6 // (3 * B * J * S * S * 4)) + 1)
+        sets = [[torch.randn(B, J, S, S, device='cuda') for _ in range(3)] for _ in range(n_sets)]
+        probs = [[torch.empty_like(t) for t in s] for s in sets]
+        gup = [[torch.randn(B, J, S, S, device='cuda') * 1e-3 for _ in range(3)] for _ in range(n_sets)]
+        dz = [[torch.empty_like(t) for t in s] for s in sets]
+        target = torch.rand(B, J, 3, device='cuda') * 1.6 - 0.8
+        coords = torch.empty(B, J, 3, device='cuda')
+        loss = torch.empty(B, J, device='cuda')
+        w = torch.full((B, J), 1.0 / (B * J), device='cuda')
+        modes = {
+            'softmax_dsnt_fwd': (lambda i: K._tail_fwd(sets[i], True, prob=probs[i], coords=coords), 8),
+            'full_tail_fwd': (lambda i: K._tail_fwd(sets[i], True, prob=probs[i], target=target, coords=coords,
+                                                    loss=loss), 8),
+            'full_tail_bwd': (lambda i: K._tail_bwd(probs[i], gup[i], dz[i], target=target, coords=coords, w=w,
+                                                    project=True), 12),
+        }
+        row = {'heatmap': S}
+        for name, (fn, bpe) in modes.items():
+            for i in range(n_sets):
+                fn(i)
+            torch.cuda.synchronize()
+            reps = 5 * n_sets
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for r in range(reps):
+                    fn(r % n_sets)
+            graph.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / reps * 1e3
+            gbs = 3 * B * J * S * S * bpe / us / 1e3
+            row[name] = {'us': us, 'GB/s': gbs, 'frac': gbs / peak_bw}
+        out.append(row)
+        del sets, probs, gup, dz
+        torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def run_b200(args):
     import torch
@@ -262,6 +314,11 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    tail = None
+    if world == 1 and not args.skip_tail:
+        tail = {'bound': 'hbm', 'unit': 'GB/s', 'peak': peak_bw, 'peak_source': src + ' copy bandwidth (MEASURED_PEAKS.json)',
+                'workload': 'configs[3]: heatmap 32/64/128, 17 joints, batch 128, three planes',
+                'sweep': tail_sweep(peak_bw)}
     cpu = None
     if world == 1 and not args.skip_cpu:
         cpu = cpu_reference(batch=4, steps=2, warmup=1, budget_s=60.0)
@@ -277,7 +334,7 @@ def run_b200(args):
                        'l2': 'per-step working set (~10 GB of activations) exceeds the 126 MB L2; 4 input sets rotate'},
             'conv_flops_per_image': FLOPS_PER_IMAGE,
             'conv_tflops_whole_step': value / world * FLOPS_PER_IMAGE / 1e12,
-            'roofline': roof, 'cpu_baseline': cpu,
+            'roofline': roof, 'tail_roofline': tail, 'cpu_baseline': cpu,
             'e2e': {'value': B * world * K / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'last_loss': last},
             'gpu_launches': step.launches_per_step() * K * 2, 'clocks': clocks}
@@ -295,6 +352,7 @@ def main():
     ap.add_argument('--batch', type=int, default=32, help='images per GPU per step')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-tail', action='store_true', help='skip the soft-argmax fusion HBM sweep (configs[3])')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
