@@ -13,7 +13,11 @@
  *  - returns 0 on success, a negative MP_ERR_* code otherwise; never throws;
  *    mp_last_error() returns a thread-local description of the last failure;
  *  - tensors: heatmaps / logits are fp32 NCHW-contiguous (B, J, H, W) as in the reference;
- *    network activations are bf16 NHWC (see DESIGN.md "Data layout").
+ *    network activations are bf16 NHWC (see DESIGN.md "Data layout");
+ *  - `_grouped` entry points run 1..MP_MAX_GROUP problems of identical geometry (the xy / zy / xz
+ *    HeatmapColumns of a stage) in one launch; the plain entry point is the 1-problem case;
+ *  - the kernels of the network chain are launched with programmatic stream serialization (tunable "pdl"):
+ *    on one stream a kernel's prologue may overlap its predecessor's tail, results are identical.
  */
 #ifndef MARGIPOSE_B200_H
 #define MARGIPOSE_B200_H
@@ -328,7 +332,10 @@ MP_API int mp_sgd_step_hp(float* param, const float* grad, float* momentum_buf, 
  *   "igemm_mt"    : 2 = two 128-pixel row blocks (TMEM accumulators) per tile share every weight tile when the launch
  *                   keeps at least "igemm_mt_ctas" tiles (0 = the CTA count); 1 (default) = one
  *   "igemm_split_n": mp_conv_igemm halves its N tile when a launch has fewer tiles than this (default 0 = the CTA count)
- *   "igemm_dbg"   : experiment switches (1 = no TMA loads, 2 = no MMA, 4 = no epilogue)
+ *   "igemm_resident": 1 (default) = a CTA keeps its whole weight operand in shared memory across its tiles when it fits
+ *   "igemm_dbg"   : experiment switches, timing only -- results are garbage (1 = no TMA loads, 2 = no MMA, 4 = no epilogue)
+ *   "igemm_trace" : device pointer to 64 uint64: CTA (0,0,0) stamps %globaltimer at its phase boundaries (tools/trace_igemm.py)
+ *   "pdl"         : 1 (default) = programmatic dependent launch for the kernels of the network chain
  *   "wgrad_ctas"  : target CTA count of mp_conv_wgrad (default 148)
  *   "wgrad_halo"  : 1 = up to three row-shifted taps per CTA share the A tile and one halo box of B; 0 (default) = one tap per CTA
  *   "wgrad_slice" : widest column slice of B per CTA when taps are grouped (default 256; 64 or 128 narrow it)

@@ -196,7 +196,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
           const bool halo = G.n > 1;
           const CUtensorMap* tmA = halo ? &tmA0h : (G.src ? &tmA1 : &tmA0);
           for (int cb = 0; cb < P.cblocks; ++cb) {
-            if (!(P.dbg & 16)) tc::mbar_wait(&emptyA[sa], pha ^ 1);
+            tc::mbar_wait(&emptyA[sa], pha ^ 1);
             uint8_t* dstA = sA + (size_t)sa * P.a_slot_bytes;
             if (!tc::elect_one()) {
             } else if (P.dbg & 1) {
@@ -210,7 +210,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
             }
             if (++sa == P.a_stages) { sa = 0; pha ^= 1; }
             for (int i = 0; i < G.n && load_b; ++i) {
-              if (!P.resident && !(P.dbg & 16)) tc::mbar_wait(&emptyB[sb], phb ^ 1);
+              if (!P.resident) tc::mbar_wait(&emptyB[sb], phb ^ 1);
               uint8_t* dstB = sB + (size_t)sb * P.b_slot_bytes;
               if (!tc::elect_one()) {
               } else if (P.dbg & 1) {
@@ -245,11 +245,11 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
         for (int g = 0; g < P.n_groups; ++g) {
           const int n = P.groups[g].n;
           for (int cb = 0; cb < P.cblocks; ++cb) {
-            if (!(P.dbg & 8)) tc::mbar_wait(&fullA[sa], pha);
+            tc::mbar_wait(&fullA[sa], pha);
             if (first && lane == 0) trace_at(P, 4 + it * 4);       // first operands of tile `it` have landed
             const uint32_t a0 = tc::smem_u32(sA + (size_t)sa * P.a_slot_bytes);
             for (int i = 0; i < n; ++i) {
-              if (wait_b && !(P.dbg & 8)) tc::mbar_wait(&fullB[sb], phb);
+              if (wait_b) tc::mbar_wait(&fullB[sb], phb);
               tc::tc_fence_after();
               const uint64_t bd = tc::desc_kmajor_sw128(tc::smem_u32(sB + (size_t)sb * P.b_slot_bytes));
               if (tc::elect_one()) {
@@ -272,9 +272,9 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
                 }
                 // frees the weight slot (in both CTAs of a pair) once these MMAs have read it; with the last
                 // tap of the group the activation slot too
-                if (P.resident || (P.dbg & 16)) {} else if (PAIR) tc::mma_commit_pair(&emptyB[sb]); else tc::mma_commit(&emptyB[sb]);
+                if (P.resident) {} else if (PAIR) tc::mma_commit_pair(&emptyB[sb]); else tc::mma_commit(&emptyB[sb]);
                 if (i == n - 1) {
-                  if (P.dbg & 16) {} else if (PAIR) tc::mma_commit_pair(&emptyA[sa]); else tc::mma_commit(&emptyA[sa]);
+                  if (PAIR) tc::mma_commit_pair(&emptyA[sa]); else tc::mma_commit(&emptyA[sa]);
                 }
               }
               first = false;
