@@ -50,6 +50,7 @@ extern "C" int mp_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "wgrad_dbg")) { mp_set_wgrad_tunable(2, value); return MP_OK; }
   if (!strcmp(name, "wgrad_kp")) { mp_set_wgrad_tunable(3, value); return MP_OK; }
   if (!strcmp(name, "wgrad_slice")) { mp_set_wgrad_tunable(4, value); return MP_OK; }
+  if (!strcmp(name, "wgrad_smem")) { mp_set_wgrad_tunable(5, value); return MP_OK; }
   mp_set_error("mp_set_tunable: unknown tunable '%s'", name);
   return MP_ERR_ARG;
 }

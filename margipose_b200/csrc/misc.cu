@@ -471,11 +471,20 @@ __global__ void pack_weights_kernel(const float* __restrict__ master, __nv_bfloa
     if (table[mid].work_end > e0) hi = mid; else lo = mid + 1;
   }
   const mp_pack_entry E = table[lo];
-  const long long local = e0 - E.work_off;
-  const int c0 = (int)(local % E.cols_p);
-  const long long rt = local / E.cols_p;
-  const int t = (int)(rt % E.taps);
-  const int r = (int)(rt / E.taps);
+  const unsigned local = (unsigned)((e0 - E.work_off) >> 3);   // this thread's 8-column group within the entry
+  const unsigned cgroups = (unsigned)E.cols_p >> 3;
+  int c0, t, r;
+  if (!E.transpose) {   // groups ordered (r, t, c-group): source rows are read along c, contiguously
+    c0 = (int)(local % cgroups) * 8;
+    const unsigned rt = local / cgroups;
+    t = (int)(rt % (unsigned)E.taps);
+    r = (int)(rt / (unsigned)E.taps);
+  } else {              // groups ordered (c-group, t, r): consecutive threads read consecutive r of the source
+    r = (int)(local % (unsigned)E.rows_p);
+    const unsigned ct = local / (unsigned)E.rows_p;
+    t = (int)(ct % (unsigned)E.taps);
+    c0 = (int)(ct / (unsigned)E.taps) * 8;
+  }
   float v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {

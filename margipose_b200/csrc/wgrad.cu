@@ -186,6 +186,7 @@ long long g_wgrad_halo = 0;   // measured in the grouped step: one tap per CTA (
 long long g_wgrad_dbg = 0;
 long long g_wgrad_kp = 128;
 long long g_wgrad_slice = 256;
+long long g_wgrad_smem = 200 * 1024;   // shared-memory budget for the pipeline stages
 bool g_attr_set = false;
 
 int view_to_tmap(CUtensorMap* tm, const mp_view5& v, const uint32_t box[5], const char* what) {
@@ -240,7 +241,8 @@ void mp_set_wgrad_tunable(int which, long long v) {
   else if (which == 1) g_wgrad_halo = v;
   else if (which == 2) g_wgrad_dbg = v;
   else if (which == 3) g_wgrad_kp = v;
-  else g_wgrad_slice = v;
+  else if (which == 4) g_wgrad_slice = v;
+  else g_wgrad_smem = v;
 }
 
 static int check_one(const mp_wgrad_args* a) {
@@ -318,7 +320,7 @@ extern "C" int mp_conv_wgrad_grouped(const mp_wgrad_args* args, int n_problems, 
   const int b_box_plain = kp * 128, b_box_halo = (P.kp_rows + 2) * P.row_bytes;
   P.stage_bytes = 2 * P.a_box_bytes + (max_cols / 64) * (max_n > 1 ? b_box_halo : b_box_plain);
   const int overhead = 1024 + 256;
-  int stages = (200 * 1024 - overhead) / P.stage_bytes;
+  int stages = (int)((g_wgrad_smem - overhead) / P.stage_bytes);
   MP_CHECK_ARG(stages >= 1, "mp_conv_wgrad: stage of %d bytes does not fit", P.stage_bytes);
   if (stages < 2) stages = 2;
   if (stages > 8) stages = 8;
