@@ -17,6 +17,7 @@ reference's own response to a 1e-6 input perturbation at the same storage precis
                              total gradient norm within 25 %, conv-weight gradient norms within 60 %
 Index bookkeeping (state_dict keys, joint order, num_batches_tracked) is exact.
 """
+import math
 import os
 
 import pytest
@@ -271,3 +272,71 @@ def test_train_step_cuda_graph_follows_lr_schedule():
         g['lr'] = 1e-2
     step(x, target, mask)
     assert not torch.equal(before, flat)
+
+
+def test_full_size_properties_of_the_bench_workload():
+    """BASELINE.json configs[1] at full size (4-stage ResNet-34, 256x256, 17 joints, batch 32): the grouped /
+    two-accumulator / CTA-pair conv paths that small batches never select, checked through size-independent
+    properties instead of the (too slow) CPU oracle:
+      * every heatmap is a probability distribution and the returned coordinates are the DSNT expectations of
+        the last stage's heatmaps (recomputed here with plain torch, dsntnn.py:84-96 + margipose_model.py:254-261);
+      * in eval mode samples are independent, so the batch of 32 must agree with its two halves run as batches
+        of 16 (which take a different tile shape / CTA count) up to bf16 accumulation-order noise;
+      * one training step: finite loss, every parameter receives a finite gradient, BatchNorm counters advance
+        by exactly one, and the step is made of grouped launches (3 columns per launch)."""
+    from margipose_b200.models import create_model
+    from margipose_b200 import dsntnn as K
+    desc = {'type': 'margipose', 'version': '6.0.1',
+            'settings': dict(n_stages=4, axis_permutation=True, feature_extractor='resnet34', pixelwise_loss='jsd')}
+    torch.manual_seed(11)
+    model = create_model(desc).cuda()
+    x, target, mask = model_inputs(12, 32)
+    xc = x.cuda()
+    # give the BatchNorm layers meaningful running statistics (a randomly initialised net is not usable in
+    # eval mode otherwise): one training-mode forward with momentum 1 copies this batch's statistics
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.momentum = 1.0
+    model.train()
+    with torch.no_grad():
+        model(xc)
+
+    model.eval()
+    with torch.no_grad():
+        full = model(xc).clone()
+        hms = [[h.clone() for h in model.xy_heatmaps], [h.clone() for h in model.zy_heatmaps],
+               [h.clone() for h in model.xz_heatmaps]]
+        halves = torch.cat([model(xc[:16]).clone(), model(xc[16:]).clone()])
+    for plane in hms:
+        assert len(plane) == 4
+        for h in plane:
+            assert h.shape == (32, 17, 32, 32) and bool((h >= 0).all())
+            torch.testing.assert_close(h.sum((-1, -2)), torch.ones(32, 17, device='cuda'), rtol=0, atol=1e-4)
+    c = (2 * torch.arange(32, device='cuda', dtype=torch.float32) + 1) / 32 - 1
+
+    def expect(h):   # (last-dim coordinate, row coordinate)
+        return (h.sum(-2) * c).sum(-1), (h.sum(-1) * c).sum(-1)
+    (ax, by), (azy, _), (_, bxz) = expect(hms[0][-1]), expect(hms[1][-1]), expect(hms[2][-1])
+    want = torch.stack([ax, by, 0.5 * (azy + bxz)], -1)
+    torch.testing.assert_close(full, want, rtol=0, atol=1e-5)
+    assert bool((full.abs() <= 1).all())
+    # batch 32 vs 2 x batch 16: same math, different tiling (observed max difference ~1e-3)
+    print('batch-32 vs 2 x batch-16 max coordinate difference', (full - halves).abs().max().item())
+    assert (full - halves).abs().max().item() < 2e-2
+    assert (full - halves).abs().mean().item() < 2e-3
+
+    model.train()
+    counters0 = {k: int(b) for k, b in model.named_buffers() if b.dtype == torch.int64}
+    model.zero_grad()
+    out = model(xc)
+    loss = K.average_loss(model.forward_3d_losses(out, target.cuda()), mask.cuda())
+    loss.backward()
+    assert math.isfinite(loss.item()) and loss.item() > 0
+    for k, p in model.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), k
+    assert model.flat_grads.norm().item() > 0
+    for k, b in model.named_buffers():
+        if b.dtype == torch.int64:
+            assert int(b) == counters0[k] + 1, k
+    eng = model.engine_for(32, 256, 256, True)
+    assert eng.group and eng.launches() < 900, 'the three columns of a stage should share grouped launches'
