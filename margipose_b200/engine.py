@@ -7,7 +7,9 @@ up front (bf16 NHWC, channels padded to 64), and records the forward and backwar
 lists of C-ABI launches with pre-built argument structs.  Running a pass is then a loop of ctypes
 calls -- no allocation, no autograd graph, no host synchronisation -- which is also what makes
 the whole training step capturable in one CUDA graph.  The three HeatmapColumns of a stage are
-independent (margipose_model.py:196-198) and run on three streams.
+independent (margipose_model.py:196-198) and structurally identical: their programs are zipped into
+ONE program of grouped launches (three problems per kernel launch); MARGIPOSE_B200_GROUP=0 runs
+them on three streams instead.
 
 Parameters live in ONE flat fp32 buffer (conv weights in channels-last memory = the GEMM's
 [rows][taps][cols] order), gradients in a second flat buffer with the same layout, and the bf16

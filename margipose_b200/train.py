@@ -5,7 +5,7 @@ reference's `do_training_pass` (/root/reference/src/margipose/bin/train_3d.py:15
     step = TrainStep(model, optimizer, batch=32)
     loss = step(images, targets, joint_mask)        # host or device tensors
 
-All device buffers are static, so after a few eager iterations the whole step (≈3000 kernel
+All device buffers are static, so after a few eager iterations the whole step (≈730 kernel
 launches for the 4-stage ResNet-34 model) is captured once into a CUDA graph and replayed; the
 per-step host work is then two async H2D copies, one graph launch and one 4-byte loss read-back.
 With torch.distributed initialised, gradients are averaged across ranks with ONE all-reduce over
