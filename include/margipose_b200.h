@@ -333,6 +333,7 @@ MP_API int mp_sgd_step_hp(float* param, const float* grad, float* momentum_buf, 
  *                   keeps at least "igemm_mt_ctas" tiles (0 = the CTA count); 1 (default) = one
  *   "igemm_split_n": mp_conv_igemm halves its N tile when a launch has fewer tiles than this (default 0 = the CTA count)
  *   "igemm_resident": 1 (default) = a CTA keeps its whole weight operand in shared memory across its tiles when it fits
+ *   "igemm_astages": activation (halo box) slots in flight when the weights stream (default 3)
  *   "igemm_dbg"   : experiment switches, timing only -- results are garbage (1 = no TMA loads, 2 = no MMA, 4 = no epilogue)
  *   "igemm_trace" : device pointer to 64 uint64: CTA (0,0,0) stamps %globaltimer at its phase boundaries (tools/trace_igemm.py)
  *   "pdl"         : 1 (default) = programmatic dependent launch for the kernels of the network chain
@@ -340,6 +341,7 @@ MP_API int mp_sgd_step_hp(float* param, const float* grad, float* momentum_buf, 
  *   "wgrad_halo"  : 1 = up to three row-shifted taps per CTA share the A tile and one halo box of B; 0 (default) = one tap per CTA
  *   "wgrad_slice" : widest column slice of B per CTA when taps are grouped (default 256; 64 or 128 narrow it)
  *   "wgrad_kp"    : pixels per pipeline stage of mp_conv_wgrad (default 128)
+ *   "wgrad_smem"  : shared-memory budget of mp_conv_wgrad's pipeline stages in bytes (default 204800)
  *   "wgrad_dbg"   : experiment switches (1 = skip the gradient atomics, 4 = no MMA) */
 MP_API int mp_set_tunable(const char* name, int64_t value);
 

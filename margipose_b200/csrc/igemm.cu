@@ -430,6 +430,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
 }
 
 long long g_igemm_smem = 227 * 1024;   // per CTA (one persistent CTA per SM): activation ring + weight ring / resident weights
+long long g_igemm_astages = 3;     // activation (halo box) slots when the weights stream
 long long g_igemm_resident = 1;    // keep the weight operand in shared memory across a CTA's tiles when it fits
 long long g_igemm_ctas = 0;        // CTAs per launch (0 = the device's SM count)
 long long g_igemm_halo = 1;        // group taps that differ only in their row shift (one halo box per group)
@@ -526,6 +527,7 @@ void mp_set_igemm_pair(long long v) { g_igemm_pair = v; }
 void mp_set_igemm_dbg(long long v) { g_igemm_dbg = v; }
 void mp_set_igemm_trace(long long v) { g_igemm_trace = v; }
 void mp_set_igemm_resident(long long v) { g_igemm_resident = v; }
+void mp_set_igemm_astages(long long v) { g_igemm_astages = v < 2 ? 2 : v; }
 void mp_set_igemm_split_n(long long v) { g_igemm_split_n = v; }
 void mp_set_igemm_mt(int which, long long v) {
   if (which == 0) g_igemm_mt = v;
@@ -690,8 +692,8 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
     b_stages = b_slots;
     a_stages = (int)((budget - (long long)b_slots * P.b_slot_bytes) / P.a_slot_bytes);
   } else if (any_halo) {
-    a_stages = 3;
-    if (budget - 3LL * P.a_slot_bytes < 4LL * P.b_slot_bytes) a_stages = 2;
+    a_stages = (int)g_igemm_astages;   // activation boxes in flight; the weight ring gets the rest
+    while (a_stages > 2 && budget - (long long)a_stages * P.a_slot_bytes < 4LL * P.b_slot_bytes) --a_stages;
     b_stages = (int)((budget - (long long)a_stages * P.a_slot_bytes) / P.b_slot_bytes);
     if (b_stages > MAX_STAGES) b_stages = MAX_STAGES;
   } else {
