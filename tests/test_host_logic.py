@@ -119,3 +119,43 @@ def test_no_cpu_fallback():
         K.flat_softmax(torch.randn(1, 17, 32, 32))
     with pytest.raises(MargiposeB200Error):
         K.dsnt(torch.rand(1, 17, 32, 32))
+
+
+def test_engine_zips_the_three_column_programs_into_grouped_launches():
+    """engine.Engine._merge_lanes (host logic, no GPU): the xy / zy / xz columns record structurally identical
+    launch programs (models/margipose_model.py:196-198); ops with a grouped C-ABI variant become ONE launch over
+    a contiguous array of the three argument structs, ops only some columns have (the axis permutations of the
+    zy / xz columns) keep their own launch, and per-column order is preserved."""
+    from margipose_b200 import engine as E
+    from margipose_b200._lib import IgemmArgs, BnArgs
+
+    def op(name, args, flops=0.0, **flags):
+        f = lambda: None
+        f.name, f.args, f.flops = name, args, flops
+        for k, v in flags.items():
+            setattr(f, k, v)
+        return f
+
+    def lane(k, permute):
+        a, b, c = IgemmArgs(), BnArgs(), IgemmArgs()
+        a.n_img, c.n_img, b.C = 10 + k, 20 + k, 30 + k
+        ops = [op('mp_conv_igemm', a, flops=1.0), op('mp_bn_fwd', b, join_aux=True)]
+        if permute:
+            ops.append(op('mp_axis_permute', None))
+        ops.append(op('mp_conv_igemm', c, flops=2.0, aux=True))
+        return ops
+
+    eng = E.Engine.__new__(E.Engine)
+    eng.device = torch.device('cpu')
+    lanes = [lane(0, False), lane(1, True), lane(2, True)]
+    merged = eng._merge_lanes(lanes)
+    assert [m.name for m in merged] == ['mp_conv_igemm', 'mp_bn_fwd', 'mp_axis_permute', 'mp_axis_permute',
+                                        'mp_conv_igemm']
+    first, bn, p1, p2, last = merged
+    assert len(first.parts) == 3 and [first.args[i].n_img for i in range(3)] == [10, 11, 12]
+    assert [bn.args[i].C for i in range(3)] == [30, 31, 32] and bn.join_aux
+    assert p1 is lanes[1][2] and p2 is lanes[2][2]
+    assert [last.args[i].n_img for i in range(3)] == [20, 21, 22] and last.aux and last.flops == 6.0
+    assert first.flops == 3.0 and not getattr(first, 'aux', False)
+    # the grouped argument array is contiguous memory of the C struct (what mp_*_grouped expects)
+    assert ctypes.sizeof(first.args) == 3 * ctypes.sizeof(IgemmArgs)
