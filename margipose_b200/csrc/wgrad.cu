@@ -8,12 +8,14 @@
 // [pixels][64 channels] lines of 128 bytes in shared memory and the UMMA descriptors walk it with
 // K = pixel (8-pixel groups 1024 B apart) and M/N = channel (64-channel groups one box apart).
 // Each CTA owns one 128-row slice of m, one TAP GROUP, one slice of the n columns and a strided
-// share of the pixel chunks (split-K).  A tap group is up to three taps that differ only by their
-// row shift dh (a 3x3 filter column): their B tiles are row-shifted windows of ONE box of
-// kp_rows + 2 rows, fetched once, and each tap's descriptor starts dh * kp_w * 128 bytes further (a
-// whole number of swizzle atoms); the A tile is shared as well -- the kernel is bound by
-// L2 -> shared-memory delivery and this cuts it ~2.4x for 3x3 filters.  One TMEM accumulator per
-// tap; the epilogue adds the partial sums into the fp32 gradient with vector red.global.add.
+// share of the pixel chunks (split-K).  By default a tap group is a single tap.  With the tunable
+// wgrad_halo it is up to three taps that differ only by their row shift dh (a 3x3 filter column):
+// their B tiles are row-shifted windows of ONE box of kp_rows + 2 rows, fetched once, each tap's
+// descriptor starts dh * kp_w * 128 bytes further (a whole number of swizzle atoms) and the A tile
+// is shared as well -- 2.4x less L2 -> shared-memory traffic for 3x3 filters, but three times the
+// split-K atomics: measured 1.5 % slower in the training step, hence optional.  One TMEM accumulator
+// per tap; the epilogue adds the partial sums into the fp32 gradient with vector red.global.add.
+// A grouped launch (grid z = problem x m-tile) runs the three HeatmapColumns of a stage at once.
 //
 // Replaces the cuDNN wgrad calls autograd issues for the nn.Conv2d / nn.ConvTranspose2d sites
 // of /root/reference/src/margipose/models/margipose_model.py:33,67-68,73-74,79-82 (SURVEY.md
