@@ -168,6 +168,13 @@ typedef struct mp_igemm_args {
   int32_t bn_channels;             /* real channel count C */
   int64_t bn_count;                /* elements per channel (N*H*W of the BatchNorm input) */
   float bn_momentum, bn_eps;
+  /* Epilogue affine (inference: eval-mode BatchNorm folded into the conv, bin/infer_single.py:58-66):
+   *   out = relu2?( relu1?(acc * ep_scale[c] + ep_shift[c]) + res )
+   * ep_scale / ep_shift: fp32, w_rows entries (zeros beyond the real channels), 16-byte aligned, or both NULL;
+   * ep_relu: 0 = no ReLU, 1 = ReLU before the residual add (MargiPose ResidualBlock), 2 = after it (ResNet blocks). */
+  const float* ep_scale;
+  const float* ep_shift;
+  int32_t ep_relu;
 } mp_igemm_args;
 
 MP_API int mp_conv_igemm(const mp_igemm_args* args, void* stream);
@@ -260,6 +267,24 @@ MP_API int mp_bn_fwd_grouped(const mp_bn_args* args, int n_problems, void* strea
 MP_API int mp_bn_bwd_reduce_grouped(const mp_bn_args* args, int n_problems, void* stream);
 MP_API int mp_bn_bwd_apply_grouped(const mp_bn_args* args, int n_problems, void* stream);
 
+/* Inference: eval-mode BatchNorm (running statistics) of n layers as per-channel affines
+ *   scale[c] = gamma[c] / sqrt(running_var[c] + eps),  shift[c] = beta[c] - (running_mean[c] - conv_bias[c]) * scale[c]
+ * (zeros for C <= c < Cp), which mp_conv_igemm applies in its epilogue (ep_scale / ep_shift) -- BatchNorm folded
+ * into the conv, bin/infer_single.py:58-66 / bin/eval_3d.py:60-62.  `table` is a DEVICE array of n entries. */
+typedef struct mp_bn_fold_entry {
+  const float* gamma;
+  const float* beta;
+  const float* running_mean;
+  const float* running_var;
+  const float* conv_bias;   /* or NULL */
+  float* scale;             /* (Cp) */
+  float* shift;             /* (Cp) */
+  int32_t C, Cp;
+  float eps;
+  int32_t reserved;
+} mp_bn_fold_entry;
+MP_API int mp_bn_fold_eval(const mp_bn_fold_entry* table, int n, void* stream);
+
 /* nn.MaxPool2d(3, 2, 1) of the ResNet stem on bf16 NHWC; idx (N, H/2, W/2, C) uint8 records the
  * arg-max tap (first maximum in row-major window order, as ATen does) for the backward. */
 MP_API int mp_maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, void* stream);
@@ -314,10 +339,10 @@ MP_API int mp_pack_weights(const float* master, void* packed, const mp_pack_entr
 MP_API int mp_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr,
                        float momentum, float dampening, float weight_decay, int nesterov,
                        int first_step, float grad_scale, void* stream);
-/* Same, but when `hyper` (device pointer to 5 floats: lr, momentum, dampening, weight_decay, grad_scale) is given
- * the kernel reads the hyperparameters from it at run time, so a step captured in a CUDA graph follows LR /
- * momentum schedules (the reference's 1-cycle schedule, hyperparam_scheduler.py:24-42; momentum_buf is then
- * required).  nesterov / first_step stay launch-time constants. */
+/* Same, but when `hyper` (device pointer to 6 floats: lr, momentum, dampening, weight_decay, grad_scale,
+ * first_step as 0/1) is given the kernel reads them from it at run time, so a step captured in a CUDA graph
+ * follows LR / momentum schedules (the reference's 1-cycle schedule, hyperparam_scheduler.py:24-42;
+ * momentum_buf is then required).  nesterov stays a launch-time constant. */
 MP_API int mp_sgd_step_hp(float* param, const float* grad, float* momentum_buf, int64_t n, float lr,
                           float momentum, float dampening, float weight_decay, int nesterov,
                           int first_step, float grad_scale, const float* hyper, void* stream);

@@ -39,7 +39,8 @@ class IgemmArgs(ctypes.Structure):
                 ('stat_replicas', ctypes.c_int32), ('stat_stride', ctypes.c_int64),
                 ('bn', c_void_p), ('bn_counter', c_void_p), ('bn_launches', ctypes.c_int32),
                 ('bn_channels', ctypes.c_int32), ('bn_count', ctypes.c_int64),
-                ('bn_momentum', ctypes.c_float), ('bn_eps', ctypes.c_float)]
+                ('bn_momentum', ctypes.c_float), ('bn_eps', ctypes.c_float),
+                ('ep_scale', c_void_p), ('ep_shift', c_void_p), ('ep_relu', ctypes.c_int32)]
 
 
 class WgradArgs(ctypes.Structure):
@@ -63,6 +64,13 @@ class BnArgs(ctypes.Structure):
                 ('M', ctypes.c_int64), ('C', ctypes.c_int32), ('Cp', ctypes.c_int32),
                 ('HW', ctypes.c_int32), ('training', ctypes.c_int32), ('momentum', ctypes.c_float),
                 ('eps', ctypes.c_float)]
+
+
+class BnFoldEntry(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ('gamma', 'beta', 'running_mean', 'running_var', 'conv_bias',
+                                        'scale', 'shift')] + \
+               [('C', ctypes.c_int32), ('Cp', ctypes.c_int32), ('eps', ctypes.c_float),
+                ('reserved', ctypes.c_int32)]
 
 
 class PackEntry(ctypes.Structure):
@@ -97,6 +105,7 @@ def _signatures():
         'mp_conv_wgrad': (I, [ctypes.POINTER(WgradArgs), P]),
         'mp_conv_wgrad_grouped': (I, [ctypes.POINTER(WgradArgs), I, P]),
         'mp_set_tunable': (I, [ctypes.c_char_p, ctypes.c_int64]),
+        'mp_bn_fold_eval': (I, [P, I, P]),
         'mp_bn_fwd': (I, [ctypes.POINTER(BnArgs), P]),
         'mp_bn_bwd_reduce': (I, [ctypes.POINTER(BnArgs), P]),
         'mp_bn_bwd_apply': (I, [ctypes.POINTER(BnArgs), P]),

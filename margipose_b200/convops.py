@@ -112,11 +112,12 @@ def _fill_taps(args, taps):
 
 
 def _igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_c, res=None,
-           stats=None, out_offset=0, bn=None, defer=None):
+           stats=None, out_offset=0, bn=None, defer=None, ep=None):
     """srcs: list of (tensor, parity) pairs; see mp_conv_igemm in include/margipose_b200.h.
     bn = dict(branch=BnBranch, counter=ptr, channels=C, count=M, momentum=, eps=): fuse the BatchNorm
     finalize into the launch(es); defer = list collecting the argument structs of a multi-launch
-    conv so the caller can set the shared arrival total before launching."""
+    conv so the caller can set the shared arrival total before launching.
+    ep = (scale ptr, shift ptr, relu mode): per-channel affine + ReLU in the epilogue (eval-mode BatchNorm)."""
     a = IgemmArgs()
     for i, (t, parity) in enumerate(srcs):
         a.src[i] = _view(t, parity)
@@ -139,6 +140,8 @@ def _igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out
         a.bn_counter, a.bn_channels, a.bn_count = bn['counter'], bn['channels'], bn['count']
         a.bn_momentum, a.bn_eps = bn['momentum'], bn['eps']
         a.bn_launches = 1
+    if ep is not None:
+        a.ep_scale, a.ep_shift, a.ep_relu = ep
     if defer is not None:
         defer.append((a, out.device))
     else:
@@ -192,7 +195,7 @@ def _s1_taps(k, k_stride, sign, src=0, koff0=0):
     return taps
 
 
-def conv_forward(g, x, wpack, out, stats=None, res=None, bn=None):
+def conv_forward(g, x, wpack, out, stats=None, res=None, bn=None, ep=None):
     """y = conv(x) (or conv_transpose(x)); x (N,H,W,cin_p), out (N,Ho,Wo,cout_p), both bf16 NHWC.
     stats = (sum, sumsq[, replicas, stride]) fp32 (cout_p) accumulators for the BatchNorm batch
     statistics (optionally `replicas` copies `stride` floats apart to spread the atomics)."""
@@ -207,12 +210,15 @@ def conv_forward(g, x, wpack, out, stats=None, res=None, bn=None):
         else:
             taps, src = _down_taps(g.k, g.cin_p, g.cin_p), (x, True)
         _igemm([src], wpack, taps, cb, n, ho, wo, out, (ho * wo * g.cout_p, wo * g.cout_p, g.cout_p),
-               g.cout_p, res=res, stats=stats, bn=bn)
+               g.cout_p, res=res, stats=stats, bn=bn, ep=ep)
     else:
-        _scatter_up(g.k, (x, False), wpack, g.cin_p, cb, n, h, w, out, g.cout_p, stats, res, bn=bn)
+        if ep is not None and g.k == 1:
+            raise ValueError('an epilogue affine cannot be fused into a 1x1 transposed conv: three of its four '
+                             'output parity classes are not written by any launch')
+        _scatter_up(g.k, (x, False), wpack, g.cin_p, cb, n, h, w, out, g.cout_p, stats, res, bn=bn, ep=ep)
 
 
-def _scatter_up(k, src, wpack, k_stride, cb, n, h, w, out, c_out_p, stats, res, extra=None, bn=None):
+def _scatter_up(k, src, wpack, k_stride, cb, n, h, w, out, c_out_p, stats, res, extra=None, bn=None, ep=None):
     """The stride-2 'up' relation out[2a+ph, 2b+pw] = sum of taps over in[a+dh, b+dw]: one launch
     per output parity class, scattered into the (N, 2h, 2w, C) output.  Classes no tap reaches
     (1x1 kernels) stay zero in `out` (the buffer is zero-initialised once by its owner).
@@ -233,7 +239,7 @@ def _scatter_up(k, src, wpack, k_stride, cb, n, h, w, out, c_out_p, stats, res, 
             if not taps:
                 continue
             _igemm(srcs, wpack, taps, cb, n, h, w, out, strides, c_out_p, res=res, stats=stats,
-                   out_offset=(ph * wo + pw) * c_out_p, bn=bn, defer=pending)
+                   out_offset=(ph * wo + pw) * c_out_p, bn=bn, defer=pending, ep=ep)
     if pending:   # the BatchNorm statistics are complete when the CTAs of ALL parity classes have arrived
         for a, dev in pending:
             a.bn_launches = len(pending)

@@ -466,6 +466,24 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_kernel(const __grid_cons
   }
 }
 
+// Eval-mode BatchNorm as a per-channel affine (folded into the producing conv's epilogue, igemm.cu): one block
+// per BatchNorm of the network.
+__global__ void bn_fold_eval_kernel(const mp_bn_fold_entry* __restrict__ table) {
+  pdl_trigger();
+  pdl_wait();
+  const mp_bn_fold_entry E = table[blockIdx.x];
+  for (int c = threadIdx.x; c < E.Cp; c += blockDim.x) {
+    float scale = 0.f, shift = 0.f;
+    if (c < E.C) {
+      scale = E.gamma[c] * rsqrtf(E.running_var[c] + E.eps);
+      const float mean = E.running_mean[c] - (E.conv_bias ? E.conv_bias[c] : 0.f);
+      shift = fmaf(-mean, scale, E.beta[c]);
+    }
+    E.scale[c] = scale;
+    E.shift[c] = shift;
+  }
+}
+
 int check_args(const mp_bn_args* a, const char* what, bool bwd) {
   MP_CHECK_ARG(a, "%s: null args", what);
   MP_CHECK_ARG(a->a.y && a->M > 0 && a->C > 0 && a->Cp >= a->C && a->Cp % 8 == 0 && a->Cp / 8 <= MAXT,
@@ -536,6 +554,13 @@ extern "C" {
 int mp_bn_fwd(const mp_bn_args* a, void* stream) { return mp_bn_fwd_grouped(a, 1, stream); }
 int mp_bn_bwd_reduce(const mp_bn_args* a, void* stream) { return mp_bn_bwd_reduce_grouped(a, 1, stream); }
 int mp_bn_bwd_apply(const mp_bn_args* a, void* stream) { return mp_bn_bwd_apply_grouped(a, 1, stream); }
+
+int mp_bn_fold_eval(const mp_bn_fold_entry* table, int n, void* stream) {
+  MP_CHECK_ARG(table && n > 0, "mp_bn_fold_eval: bad arguments");
+  MP_CUDA(mp_launch(bn_fold_eval_kernel, dim3((unsigned)n), dim3(64), 0, (cudaStream_t)stream, table));
+  MP_CHECK_LAUNCH("mp_bn_fold_eval");
+  return MP_OK;
+}
 
 int mp_bn_fwd_grouped(const mp_bn_args* args, int n, void* stream) {
   BnGroup g;

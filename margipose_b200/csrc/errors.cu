@@ -13,7 +13,7 @@ void mp_set_error(const char* fmt, ...) {
 }
 
 extern "C" {
-int mp_abi_version(void) { return 2; }   // 2: grouped entry points, bn_launches, mp_sgd_step_hp
+int mp_abi_version(void) { return 3; }   // 3: epilogue affine (ep_*), mp_bn_fold_eval, deterministic mode, hyper[5]
 const char* mp_last_error(void) { return g_err; }
 }
 

@@ -82,7 +82,10 @@ struct IgemmParams {
     const float* fin_gamma; const float* fin_beta; const float* fin_bias;
     float* fin_rmean; float* fin_rvar; float* fin_smean; float* fin_sinvstd; float* fin_scale; float* fin_shift;
     unsigned* fin_counter;
+    // per-channel affine on the accumulator (eval-mode BatchNorm folded into the conv), see mp_igemm_args.ep_scale
+    const float* ep_scale; const float* ep_shift;
   } q[MP_MAX_GROUP];
+  int ep_relu;   // 0 = none, 1 = ReLU before the residual add, 2 = ReLU after it
   int fin_total, fin_C, fin_Cp;
   long long fin_count;
   float fin_momentum, fin_eps;
@@ -112,7 +115,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
   return c;
 }
 
-template <bool PAIR>
+template <bool PAIR, bool AFFINE>
 __global__ void __launch_bounds__(NTHREADS)
 igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ IgemmParams P) {
   const CUtensorMap& tmA0 = TM.a0[blockIdx.z];
@@ -323,6 +326,21 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
           float v[32];
           tc::tmem_ld32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * P.n_tile + c * 32), v);
           if (!valid) continue;
+          if (AFFINE) {   // y = relu?(acc * scale[c] + shift[c]): warp-uniform addresses, 128-bit broadcast loads
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(Q.ep_scale + ch) + i);
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(Q.ep_shift + ch) + i);
+              v[i * 4 + 0] = fmaf(v[i * 4 + 0], sc.x, sh.x);
+              v[i * 4 + 1] = fmaf(v[i * 4 + 1], sc.y, sh.y);
+              v[i * 4 + 2] = fmaf(v[i * 4 + 2], sc.z, sh.z);
+              v[i * 4 + 3] = fmaf(v[i * 4 + 3], sc.w, sh.w);
+            }
+            if (P.ep_relu == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+          }
           if (Q.res) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -337,6 +355,10 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
                 }
               }
             }
+          }
+          if (AFFINE && P.ep_relu == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           uint32_t packed[16];
 #pragma unroll
@@ -604,6 +626,7 @@ static bool same_geometry(const mp_igemm_args* x, const mp_igemm_args* y) {
       x->out_sh != y->out_sh || x->out_sw != y->out_sw || x->out_c != y->out_c ||
       (x->res == nullptr) != (y->res == nullptr) || (x->stat_sum == nullptr) != (y->stat_sum == nullptr) ||
       (x->bn == nullptr) != (y->bn == nullptr) || x->stat_replicas != y->stat_replicas ||
+      (x->ep_scale == nullptr) != (y->ep_scale == nullptr) || x->ep_relu != y->ep_relu ||
       x->stat_stride != y->stat_stride || !same_view(x->src[0], y->src[0]) ||
       (x->src[1].ptr == nullptr) != (y->src[1].ptr == nullptr) || (x->src[1].ptr && !same_view(x->src[1], y->src[1])))
     return false;
@@ -709,6 +732,8 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
   P.out_c = a->out_c;
   P.stat_replicas = a->stat_replicas > 1 ? a->stat_replicas : 1;
   P.stat_stride = a->stat_stride;
+  P.ep_relu = a->ep_relu;
+  MP_CHECK_ARG(a->ep_relu >= 0 && a->ep_relu <= 2, "mp_conv_igemm: ep_relu %d out of range", a->ep_relu);
   P.fin_total = 0; P.fin_C = 0; P.fin_Cp = 0; P.fin_count = 0; P.fin_momentum = 0.f; P.fin_eps = 0.f;
   if (a->bn) {
     MP_CHECK_ARG(a->bn_count > 0 && a->bn_channels > 0 && a->bn_channels <= a->out_c,
@@ -738,6 +763,11 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
     Q.fin_gamma = Q.fin_beta = Q.fin_bias = nullptr;
     Q.fin_rmean = Q.fin_rvar = Q.fin_smean = Q.fin_sinvstd = Q.fin_scale = Q.fin_shift = nullptr;
     Q.fin_counter = nullptr;
+    Q.ep_scale = x->ep_scale;
+    Q.ep_shift = x->ep_shift;
+    MP_CHECK_ARG((x->ep_scale == nullptr) == (x->ep_shift == nullptr) &&
+                     (!x->ep_scale || (mp_aligned16(x->ep_scale) && mp_aligned16(x->ep_shift))),
+                 "mp_conv_igemm: ep_scale / ep_shift go together and must be 16-byte aligned");
     if (x->bn) {
       const mp_bn_branch* b = x->bn;
       MP_CHECK_ARG(x->stat_sum && P.stat_replicas == 1, "mp_conv_igemm: BatchNorm finalize needs un-replicated statistics");
@@ -772,8 +802,10 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
   const size_t smem = (size_t)a_stages * P.a_slot_bytes + (size_t)b_stages * P.b_slot_bytes + overhead;
   MP_CHECK_ARG(smem <= 227 * 1024, "mp_conv_igemm: %zu bytes of shared memory needed", smem);
   if (!g_attr_set) {
-    MP_CUDA(cudaFuncSetAttribute(igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    MP_CUDA(cudaFuncSetAttribute(igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MP_CUDA(cudaFuncSetAttribute(igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MP_CUDA(cudaFuncSetAttribute(igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MP_CUDA(cudaFuncSetAttribute(igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MP_CUDA(cudaFuncSetAttribute(igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr_set = true;
   }
   dim3 grid((unsigned)(workers * (pair ? 2 : 1)), 1, (unsigned)n_problems);
@@ -791,8 +823,12 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = mp_pdl_enabled() ? 2 : 1;
-  if (pair) MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<true>, TM, P));
-  else MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<false>, TM, P));
+  const bool affine = a->ep_scale != nullptr;
+  MP_CHECK_ARG(affine || a->ep_relu == 0, "mp_conv_igemm: ep_relu needs ep_scale / ep_shift");
+  if (pair && affine) MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<true, true>, TM, P));
+  else if (pair) MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<true, false>, TM, P));
+  else if (affine) MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<false, true>, TM, P));
+  else MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<false, false>, TM, P));
   MP_CHECK_LAUNCH("mp_conv_igemm");
   return MP_OK;
 }

@@ -519,6 +519,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
                                                   const float* __restrict__ hyper) {
   if (hyper) {   // hyperparameters live in device memory: schedulers keep working when the step is a replayed CUDA graph
     lr = hyper[0]; mom = hyper[1]; damp = hyper[2]; wd = hyper[3]; gscale = hyper[4];
+    first = hyper[5] != 0.f;   // "first step initialises the momentum buffer" follows the host's step count too
   }
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;

@@ -128,7 +128,7 @@ class ParamBank:
                 view.copy_(p.detach().to(device=device, dtype=torch.float32))
             p.data = view
             p.grad = None
-            s.view, s.gview = view, gview
+            s.view, s.gview, s.ptr = view, gview, view.data_ptr()
         for s in self.buffers:
             b = getattr(s.mod, s.name)
             s.data = self.flat_buf[s.off:s.off + s.numel]
@@ -152,9 +152,19 @@ class ParamBank:
         self.device = device
 
     def linked(self):
-        """True while every nn.Parameter still aliases its slice of the flat buffer."""
-        return all(getattr(s.mod, s.name).data_ptr() == s.view.data_ptr() for s in self.params[:4]) and \
-            all(getattr(s.mod, s.name).data_ptr() == s.view.data_ptr() for s in self.params[-4:])
+        """True while every nn.Parameter still aliases its slice of the flat buffer (a rebound parameter,
+        e.g. `m.weight = nn.Parameter(...)` or `m.weight.data = pretrained`, makes the model re-materialise)."""
+        for s in self.params:
+            p = s.mod._parameters.get(s.name)
+            if p is None or p.data_ptr() != s.ptr:
+                return False
+        return True
+
+    def param_version(self):
+        """Changes whenever any parameter is written in place through its nn.Parameter (load_state_dict,
+        torch.optim steps, p.add_): the Parameters carry their own version counters -- `p.data = view` in
+        finalize() detaches them from the flat buffer's -- so the bf16 weight-pack cache keys on their sum."""
+        return self.flat._version + sum(s.mod._parameters[s.name]._version for s in self.params)
 
     def pack(self):
         if not self.pack_entries:
@@ -288,8 +298,10 @@ def build_layers(model, bank):
         return r
 
     L.columns = []
+    L.stage_ranges = []      # [lo, hi) of stage t's parameters in the flat buffers (all-reduce buckets)
     for t in range(L.n_stages):
         row = []
+        lo = bank.n_param
         for cols in (inner.xy_hm_cnns, inner.zy_hm_cnns, inner.xz_hm_cnns):
             col = cols[t]
             c = _NS()
@@ -299,6 +311,7 @@ def build_layers(model, bank):
             c.mid_channels = c.down[-1].conv2.g.cout
             row.append(c)
         L.columns.append(row)
+        L.stage_ranges.append((lo, bank.n_param))
     L.combiners = [bank.add_param(cmb.conv, 'weight', master_shape=(cmb.conv.out_channels, 1,
                                                                     cmb.conv.in_channels), conv_k=1)
                    for cmb in inner.hm_combiners]
@@ -334,7 +347,12 @@ class Engine:
         self.affine = torch.zeros(max(self.L.bn_floats, 8), device=device)    # scale, shift
         self.coefs = torch.zeros(max(3 * self.L.bn_floats, 8), device=device)  # backward (3, Cp) per branch
         self._stat_n = self.R * self.L.bn_floats
+        self._stat_fwd_n = self._stat_n       # [0, _stat_fwd_n): forward sums; [.., _counter_base): backward sums
         self.fwd, self.bwd = [], []
+        self.generation = 0    # bumped by every forward(): a backward belongs to exactly one forward
+        self.loss_ctx = None   # set by enable_fused_loss(): buffers of the fused loss path
+        self._fused = False    # this forward / backward runs the fused loss path (forward(x, fused=True))
+        self.bwd_marks = []    # index into self.bwd after which stage t's parameter gradients are complete
         self.trace = []        # (name, buffer, real channels) of every block output, in forward order
         self._record()
 
@@ -408,8 +426,9 @@ class Engine:
             if len(cur) == len(lanes) and len(set(names)) == 1 and names[0] in self.GROUPABLE:
                 out.append(self._grouped([op for _k, op in cur]))
             elif len(cur) == len(lanes) and all(hasattr(op, 'tail') for _k, op in cur) and \
-                    len(set(op.tail[0] for _k, op in cur)) == 1:
-                out.append(self._tail_op(cur[0][1].tail[0], [op.tail[1:] for _k, op in cur]))
+                    len(set(op.tail for _k, op in cur)) == 1:
+                kind, stage = cur[0][1].tail
+                out.append(self._tail_op(kind, [op.planes for _k, op in cur], stage))
             else:
                 solo = [(k, op) for k, op in cur if getattr(op, 'name', None) == 'mp_axis_permute'] or cur
                 for k, op in solo:
@@ -419,20 +438,85 @@ class Engine:
                 idx[k] += 1
         return out
 
-    def _tail_op(self, kind, planes_):
-        """Fused-tail launch over up to three planes: ('fwd', logits, prob) / ('bwd', prob, g_in, dlogits)."""
+    def _tail_op(self, kind, planes_, stage):
+        """Fused-tail launch over up to three planes: ('fwd', logits, prob) / ('bwd', prob, g_in, dlogits).
+        With a loss context (enable_fused_loss) and all three planes in the launch this is THE fusion of
+        SURVEY.md section 2b (K4 / K5): softmax + expectations + xyz + Gaussian + JS x3 + Euclid, the stage's
+        loss accumulated in place; backward = loss gradient + combiner gradient + softmax backward."""
         cols = [list(c) + [None] * (3 - len(planes_)) for c in zip(*planes_)]
+        last = stage == self.L.n_stages - 1
         if kind == 'fwd':
             logits, prob = cols
 
             def op():
-                K._tail_fwd(logits, True, prob=prob)
+                L = self.loss_ctx if self._fused else None
+                if L is None or len(planes_) < 3:
+                    K._tail_fwd(logits, True, prob=prob)
+                else:
+                    K._tail_fwd(logits, True, prob=prob, target=L.target, valid_depth=L.valid_depth,
+                                coords=L.coords[stage], loss=L.loss_bj, accumulate=stage > 0,
+                                pixelwise=L.pixelwise, sigma=L.sigma)
         else:
             prob, g_in, dlogits = cols
 
             def op():
-                K._tail_bwd(prob, g_in, dlogits, project=True)
-        op.tail = (kind,) + tuple(planes_[0])
+                L = self.loss_ctx if self._fused else None
+                if L is None or len(planes_) < 3:
+                    K._tail_bwd(prob, g_in, dlogits, project=True)
+                else:   # the last stage has no combiner behind it: no upstream gradient to read
+                    K._tail_bwd(prob, None if last else g_in, dlogits, target=L.target, coords=L.coords[stage],
+                                w=L.w, valid_depth=L.valid_depth, project=True, pixelwise=L.pixelwise,
+                                sigma=L.sigma)
+        op.tail = (kind, stage)
+        op.planes = tuple(planes_[0])
+        return op
+
+    def enable_fused_loss(self, pixelwise=True, sigma=1.0):
+        """Static buffers for the fused loss path (train.TrainStep): xyz targets, per-sample valid_depth flags
+        (1 = 3D loss, 0 = 2D loss -- the mixed batches of bin/train_3d.py:126-142), joint mask; outputs: the
+        per-joint loss summed over stages (margipose_model.py:236-252), per-stage coordinates, the masked
+        mean (dsntnn.py:99-121) and its gradient weights."""
+        if not self.group:
+            raise MargiposeB200Error('the fused loss path needs grouped launches (MARGIPOSE_B200_GROUP=1)')
+        n, J, dev = self.n, self.L.n_joints, self.device
+        L = _NS()
+        L.pixelwise, L.sigma = bool(pixelwise), float(sigma)
+        L.target = torch.zeros(n, J, 3, device=dev)
+        L.valid_depth = torch.ones(n, dtype=torch.int32, device=dev)
+        L.mask = torch.ones(n, J, device=dev)
+        L.loss_bj = torch.zeros(n, J, device=dev)
+        L.coords = [torch.zeros(n, J, 3, device=dev) for _ in range(self.L.n_stages)]
+        L.out2 = torch.zeros(2, device=dev)       # (masked mean, its denominator)
+        L.w = torch.zeros(n, J, device=dev)       # d mean / d loss[b, j]
+        L.one = torch.ones(1, device=dev)
+        self.loss_ctx = L
+        return L
+
+    def loss_reduce(self):
+        """average_loss over the accumulated per-joint losses and its gradient (two tiny launches)."""
+        L, dev = self.loss_ctx, self.device
+        nel = L.loss_bj.numel()
+        check(lib().mp_masked_mean_fwd(L.loss_bj.data_ptr(), L.mask.data_ptr(), nel, L.out2.data_ptr(),
+                                       stream_ptr(dev)), 'mp_masked_mean_fwd')
+        if self.training:
+            check(lib().mp_masked_mean_bwd(L.one.data_ptr(), L.mask.data_ptr(), L.out2.data_ptr(), nel,
+                                           L.w.data_ptr(), stream_ptr(dev)), 'mp_masked_mean_bwd')
+        return L.out2[0]
+
+    def _combiner_bwd_op(self, d_next, prev, wc, gin, n, J, hw, cf):
+        """HeatmapCombiner backward into the stage's upstream-gradient planes: added to the loss gradients
+        the autograd path copied there, or overwriting them on the fused loss path (the tail backward adds
+        the loss terms itself)."""
+        fn, dev = lib().mp_combiner_bwd, self.device
+        pp, gp = planes(prev), planes(gin)
+
+        def op():
+            rc = fn(d_next.data_ptr(), pp, wc.data.data_ptr(), gp, wc.grad.data_ptr(),
+                    0 if self._fused else 1, n, J, hw, cf, stream_ptr(dev))
+            if rc != 0:
+                check(rc, 'mp_combiner_bwd')
+        op.name = 'mp_combiner_bwd'
+        op._keep = (pp, gp)
         return op
 
     @staticmethod
@@ -483,7 +567,10 @@ class Engine:
         args.C, args.Cp, args.HW = a.C, a.Cp, hw
         args.training = int(self.training)
         args.stat_replicas, args.stat_stride = self.R, self.L.bn_floats
-        args.momentum = a.mod.momentum if a.mod.momentum is not None else 0.1
+        if a.mod.momentum is None:
+            raise MargiposeB200Error('BatchNorm2d(momentum=None) (cumulative moving average) is not on the hot '
+                                     'path; the reference uses the default momentum 0.1')
+        args.momentum = a.mod.momentum
         args.eps = a.mod.eps
         return args
 
@@ -687,7 +774,7 @@ class Engine:
                     blk_b.append(b)
                     self.trace.append(('stage%d.col%d.up%d' % (t, col.mode, i), xcol, rb.bn2.C))
                 prob = torch.zeros(n, J, hf, wf, device=dev)
-                ops.append(self._tail_op('fwd', [(logits, prob)]))
+                ops.append(self._tail_op('fwd', [(logits, prob)], t))
                 lanes.append(ops)
                 lz.append(logits)
                 pr.append(prob)
@@ -707,16 +794,14 @@ class Engine:
         for t in range(L.n_stages - 1, -1, -1):
             if t < L.n_stages - 1:
                 prev, wc = comb[t]
-                bsegs.append(('serial', [self._call(
-                    'mp_combiner_bwd', d_next.data_ptr(), planes(prev), wc.data.data_ptr(), planes(self.gin[t]),
-                    wc.grad.data_ptr(), 1, n, J, hf * wf, cf)]))
+                bsegs.append(('serial', [self._combiner_bwd_op(d_next, prev, wc, self.gin[t], n, J, hf * wf, cf)]))
             lanes, dxs = [], []
             for k in range(3):
                 ops = []
                 blk_b, perm, n_down = col_bwd[t][k]
                 prob, g_in = self.probs[t][k], self.gin[t][k]
                 dlogits = torch.zeros(n, J, hf, wf, device=dev)
-                ops.append(self._tail_op('bwd', [(prob, g_in, dlogits)]))
+                ops.append(self._tail_op('bwd', [(prob, g_in, dlogits)], t))
                 d = None
                 for i in range(len(blk_b) - 1, -1, -1):
                     if i == len(blk_b) - 1:
@@ -739,6 +824,7 @@ class Engine:
                                                 d_inp.numel())]))
             self._keep.append(arr)
             d_next = d_inp
+            self.bwd_marks.append(len(bsegs))    # stage t's (and combiner t's) parameter gradients are complete
         # ---- stem backward
         ops = []
         d = d_next
@@ -827,21 +913,38 @@ class Engine:
                 out += len(body) if kind == 'serial' else sum(len(o) for o in body)
         return out
 
-    def forward(self, x):
-        """x: fp32 (N, 3, H, W) on the device.  Returns probs[t][k], fp32 (N, J, h, w)."""
-        self.x_in.copy_(x)
+    def forward(self, x, fused=False):
+        """x: fp32 (N, 3, H, W) on the device.  Returns probs[t][k], fp32 (N, J, h, w).  fused=True (after
+        enable_fused_loss): the stage tails also compute the losses of the loss context.  The returned
+        tensors (and everything a backward reads) are the engine's static buffers: the next forward of this
+        engine overwrites them, and a backward is only valid for the most recent forward (checked through
+        `generation`)."""
+        if x.data_ptr() != self.x_in.data_ptr():
+            self.x_in.copy_(x)
+        self.generation += 1
+        self._fused = bool(fused)
+        if fused and self.loss_ctx is None:
+            raise MargiposeB200Error('forward(fused=True) needs enable_fused_loss() first')
         if self.training:
-            self.stats.zero_()
+            self.stats[:self._stat_fwd_n].zero_()       # forward BatchNorm sums
+            self.stats[self._counter_base:].zero_()     # ticket counters
             self.bank.flat_cnt.add_(1)
         self._run(self.fwd)
         return self.probs
 
-    def backward(self, grads):
-        """grads[t][k]: fp32 (N, J, h, w) gradient w.r.t. the stage-t plane-k heatmap, or None."""
-        for t, row in enumerate(self.gin):
-            for k, g in enumerate(row):
-                if grads[t][k] is None:
-                    g.zero_()
-                else:
-                    g.copy_(grads[t][k])
-        self._run(self.bwd)
+    def backward(self, grads=None, lo=0, hi=None):
+        """grads[t][k]: fp32 (N, J, h, w) gradient w.r.t. the stage-t plane-k heatmap, or None; grads=None on
+        the fused loss path (the tail backward derives the loss gradient itself).  [lo, hi) selects a slice of
+        the backward program (see bwd_marks) so a caller can start all-reducing finished parameter ranges."""
+        if lo == 0:
+            # backward reductions are atomically accumulated: zero them per backward (a second backward over
+            # the same forward -- retain_graph, separate 2D / 3D loss backwards -- must not see the first's sums)
+            self.stats[self._stat_fwd_n:self._counter_base].zero_()
+            if not self._fused:
+                for t, row in enumerate(self.gin):
+                    for k, g in enumerate(row):
+                        if grads is None or grads[t][k] is None:
+                            g.zero_()
+                        else:
+                            g.copy_(grads[t][k])
+        self._run(self.bwd[lo:hi])

@@ -29,8 +29,11 @@ def create_model(model_desc):
     return model
 
 
-def load_model(model_file):
-    details = torch.load(model_file, map_location='cpu', weights_only=False)
+def load_model(model_file, allow_pickle=False):
+    """models/__init__.py:30-34.  A reference checkpoint is a dict of plain containers and tensors
+    ({'state_dict', 'model_desc', 'train_datasets', 'optimizer', 'epoch'}, bin/train_3d.py:374-382), so
+    it loads under `weights_only=True`; full unpickling (arbitrary code execution) is an explicit opt-in."""
+    details = torch.load(model_file, map_location='cpu', weights_only=not allow_pickle)
     model = create_model(details['model_desc'])
     model.load_state_dict(details['state_dict'])
     return model

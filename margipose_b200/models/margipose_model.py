@@ -227,13 +227,20 @@ class _Body(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eng, x, _anchor):
         probs = eng.forward(x)
-        ctx.eng = eng
+        ctx.eng, ctx.generation = eng, eng.generation
         ctx.set_materialize_grads(False)
         return tuple(p.detach() for row in probs for p in row)
 
     @staticmethod
     def backward(ctx, *grads):
         eng = ctx.eng
+        if eng.generation != ctx.generation:
+            # one set of activation buffers per (batch, resolution, mode): a later forward of the same shape
+            # has overwritten what this backward needs (and the heatmaps this forward returned)
+            raise MargiposeB200Error(
+                'backward through a MargiPose forward whose activations were overwritten by a later forward '
+                'of the same shape; call backward before the next forward (gradient accumulation: one '
+                'forward + backward per micro-batch)')
         eng.bank.attach_grads()
         eng.backward([[grads[3 * t + k] for k in range(3)] for t in range(len(grads) // 3)])
         return None, None, None
@@ -283,8 +290,15 @@ class MargiPoseModel(nn.Module):
         self._packed_version = None
 
     def _refresh_packs(self):
-        v = self._bank.flat._version
-        if self.training or self._packed_version != v:
+        """bf16 GEMM operands follow the fp32 master weights: every training forward repacks (one launch);
+        in eval mode the packs are reused until a parameter is written -- through the flat buffer (FlatSGD
+        calls mark_params_dirty) or through any nn.Parameter (load_state_dict, torch.optim, p.add_)."""
+        if self.training:
+            self._bank.pack()
+            self._packed_version = None
+            return
+        v = self._bank.param_version()
+        if self._packed_version != v:
             self._bank.pack()
             self._packed_version = v
 
@@ -345,6 +359,19 @@ class MargiPoseModel(nn.Module):
         losses = 0
         for xy_hm, zy_hm, xz_hm in zip(self.xy_heatmaps, self.zy_heatmaps, self.xz_heatmaps):
             l, _ = K.fused_tail_losses(xy_hm, zy_hm, xz_hm, target_xyz, pixelwise=pixelwise, sigma=1.0)
+            losses = losses + l
+        return losses
+
+    def forward_mixed_losses(self, out_var, target_var, valid_depth):
+        """The mixed branch of bin/train_3d.py:134-140 without its per-sample Python loop: sample b gets the
+        3D loss where valid_depth[b] == 1 and the 2D loss (xy plane and x, y only) where it is 0."""
+        pixelwise = self._pixelwise_flag()
+        target_xyz = target_var.narrow(-1, 0, 3)
+        flags = torch.as_tensor(valid_depth).to(device=target_xyz.device, dtype=torch.int32)
+        losses = 0
+        for xy_hm, zy_hm, xz_hm in zip(self.xy_heatmaps, self.zy_heatmaps, self.xz_heatmaps):
+            l, _ = K.fused_tail_losses(xy_hm, zy_hm, xz_hm, target_xyz, valid_depth=flags,
+                                       pixelwise=pixelwise, sigma=1.0)
             losses = losses + l
         return losses
 

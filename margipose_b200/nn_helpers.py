@@ -1,8 +1,7 @@
 """Parameter initialisation of the heatmap columns / combiners (mirror of
 /root/reference/src/margipose/nn_helpers.py:7-21): Kaiming-normal (fan_out) convolutions,
-BatchNorm gamma = 1, beta = 0.  Host-side, runs once at model construction."""
-from math import sqrt
-
+BatchNorm gamma = 1, beta = 0 (the reference's nn.Linear branch has no module to act on here).
+Host-side, runs once at model construction."""
 from torch import nn
 from torch.nn import init
 from torch.nn.modules.conv import _ConvNd
@@ -14,10 +13,6 @@ def init_parameters(net):
             init.kaiming_normal_(m.weight, 0, 'fan_out')
             if m.bias is not None:
                 init.constant_(m.bias, 0)
-        elif isinstance(m, nn.Linear):
-            init.normal_(m.weight, 0, sqrt(2.0 / m.weight.size(0)))
-            if m.bias is not None:
-                init.normal_(m.bias, 0, sqrt(2.0 / m.bias.size(0)))
         elif isinstance(m, nn.BatchNorm2d):
             init.constant_(m.weight, 1)
             if m.bias is not None:

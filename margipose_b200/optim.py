@@ -2,8 +2,10 @@
 with, /root/reference/src/margipose/bin/train_3d.py:338-340 + train_helpers.py:70-75) as ONE
 kernel launch over the flat parameter / gradient buffers instead of ~1100 per-tensor updates.
 
-It is a torch.optim.Optimizer, so LR / momentum schedulers that write `param_groups[i][name]`
-(the reference's 1-cycle HyperparameterScheduler, hyperparam_scheduler.py:24-42) keep working.
+It is a torch.optim.Optimizer, so LR / momentum schedulers that write `param_groups[0][name]`
+(the reference's 1-cycle HyperparameterScheduler, hyperparam_scheduler.py:24-42) keep working,
+and `state_dict()` / `load_state_dict()` carry the momentum buffer and the step count (the
+reference saves `optimizer.state_dict()` in its checkpoints, train_3d.py:374-382).
 """
 import torch
 
@@ -20,17 +22,28 @@ class FlatSGD(torch.optim.Optimizer):
         model._ensure(device)
         self.model = model
         self.bank = model._bank
+        frozen = [k for k, p in model.named_parameters() if not p.requires_grad]
+        if frozen:
+            raise ValueError('FlatSGD updates the whole flat parameter buffer; frozen parameters are not '
+                             'supported (%s, ...)' % frozen[0])
         defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay,
                         nesterov=nesterov)
         super().__init__(list(model.parameters()), defaults)
         self.momentum_buf = torch.zeros_like(self.bank.flat)
         self._steps = 0
         self.grad_scale = 1.0     # e.g. 1 / world_size after a summing all-reduce
-        # (lr, momentum, dampening, weight_decay, grad_scale) as the kernel reads them: a pinned host mirror that
-        # refresh_hyper() fills from param_groups and an async copy into device memory in front of every step.
-        # The copy is part of a captured step, so a replayed CUDA graph picks up whatever a scheduler wrote.
+        # (lr, momentum, dampening, weight_decay, grad_scale, first_step) as the kernel reads them: a pinned host
+        # mirror that refresh_hyper() fills from param_groups and an async copy into device memory in front of
+        # every step.  The copy is part of a captured step, so a replayed CUDA graph picks up whatever a
+        # scheduler wrote -- including the "first step initialises the momentum buffer" flag.
         self._hyper_host = torch.zeros(8).pin_memory()
         self._hyper = torch.zeros(8, device=device)
+
+    def add_param_group(self, param_group):
+        if getattr(self, 'param_groups', None):
+            raise ValueError('FlatSGD supports exactly one parameter group (one flat buffer, one set of '
+                             'hyperparameters)')
+        super().add_param_group(param_group)
 
     def refresh_hyper(self):
         """Host side only: publish the current param_groups hyperparameters to the pinned mirror (call before
@@ -38,12 +51,31 @@ class FlatSGD(torch.optim.Optimizer):
         g = self.param_groups[0]
         h = self._hyper_host
         h[0], h[1], h[2], h[3], h[4] = g['lr'], g['momentum'], g['dampening'], g['weight_decay'], self.grad_scale
+        h[5] = 1.0 if self._steps == 0 else 0.0
 
     def zero_grad(self, set_to_none=False):
         self.bank.flat_grad.zero_()
         if set_to_none:
             for s in self.bank.params:
                 getattr(s.mod, s.name).grad = None
+
+    def state_dict(self):
+        sd = super().state_dict()
+        sd['flat'] = {'momentum_buf': self.momentum_buf.detach().clone(), 'steps': self._steps}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        flat = state_dict.pop('flat', None)
+        super().load_state_dict(state_dict)
+        if flat is not None:
+            self.momentum_buf.copy_(flat['momentum_buf'])
+            self._steps = int(flat['steps'])
+
+    def count_replayed_step(self):
+        """Host bookkeeping for a step replayed from a CUDA graph (step() itself did not run)."""
+        self._steps += 1
+        self.model.mark_params_dirty()
 
     @torch.no_grad()
     def step(self, closure=None):

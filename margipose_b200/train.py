@@ -1,15 +1,22 @@
 """One MargiPose training step as a user calls it: the fwd / loss / bwd / step sequence of the
 reference's `do_training_pass` (/root/reference/src/margipose/bin/train_3d.py:159-186) with
-`forward_loss` (:126-142, all-3D branch) as the loss, on the B200 engine.
+`forward_loss` (:126-142, 3D / 2D / mixed batches) as the loss, on the B200 engine.
 
     step = TrainStep(model, optimizer, batch=32)
-    loss = step(images, targets, joint_mask)        # host or device tensors
+    loss = step(images, targets, joint_mask, valid_depth)      # host or device tensors
 
-All device buffers are static, so after a few eager iterations the whole step (≈730 kernel
-launches for the 4-stage ResNet-34 model) is captured once into a CUDA graph and replayed; the
-per-step host work is then two async H2D copies, one graph launch and one 4-byte loss read-back.
-With torch.distributed initialised, gradients are averaged across ranks with ONE all-reduce over
-the flat gradient buffer between the backward graph and the optimiser graph.
+All device buffers are static, so after a few eager iterations the whole step (≈700 kernel
+launches for the 4-stage ResNet-34 model) is captured once into CUDA graphs and replayed; the
+per-step host work is then a few async H2D copies, the graph launches and one 4-byte loss
+read-back.  The loss is computed by the fused tail kernels inside the engine's programs: per stage
+ONE forward launch (softmax + soft-argmax + xyz + Gaussian + JS x3 + Euclid, accumulating the
+per-joint loss) and ONE backward launch (loss gradient + combiner gradient + softmax backward).
+
+With torch.distributed initialised, gradients are summed across ranks bucket by bucket: the flat
+gradient buffer is laid out stage by stage, the backward program is cut where a stage's parameter
+gradients are complete, and each bucket's all-reduce (NCCL over NVLink) is issued from a side stream
+while the next stage's backward runs; only the small stem bucket is exposed.  The 1 / world_size
+factor is folded into the SGD kernel (no extra pass over the gradients).
 """
 import torch
 
@@ -17,83 +24,195 @@ from . import dsntnn as K
 from . import parallel
 
 
+def forward_loss(model, out_var, target_var, mask_var, valid_depth):
+    """Mirror of bin/train_3d.py:126-142: the 3D loss for samples with valid depth, the 2D loss for the
+    others, masked-averaged over joints.  `valid_depth`: per-sample flags (list / tensor).  The reference
+    stacks per-sample rows in a Python loop; here the flag goes into the fused tail kernels."""
+    target_var = target_var.narrow(-1, 0, 3)
+    if not torch.is_tensor(valid_depth):
+        valid_depth = torch.as_tensor(list(valid_depth))
+    vd = valid_depth.to(device=target_var.device, dtype=torch.int32)
+    if not 0 in vd.tolist():
+        losses = model.forward_3d_losses(out_var, target_var)
+    elif not 1 in vd.tolist():
+        losses = model.forward_2d_losses(out_var, target_var)
+    else:
+        losses = model.forward_mixed_losses(out_var, target_var, vd)
+    return K.average_loss(losses, mask_var)
+
+
 class TrainStep:
-    def __init__(self, model, optimizer, batch, height=256, width=256, use_graph=True, warmup=3):
+    def __init__(self, model, optimizer, batch, height=256, width=256, use_graph=True, warmup=3,
+                 fused_loss=True, overlap_allreduce=True):
         self.model, self.opt = model, optimizer
         dev = next(model.parameters()).device
         if dev.type != 'cuda':
             raise ValueError('TrainStep needs the model on a CUDA device')
         self.device = dev
         J = model.n_joints
-        self.x = torch.zeros(batch, 3, height, width, device=dev)
-        self.target = torch.zeros(batch, J, 3, device=dev)
-        self.mask = torch.ones(batch, J, device=dev)
-        self.loss = torch.zeros((), device=dev)
-        self.coords = torch.zeros(batch, J, 3, device=dev)
+        model.train()
+        model._ensure(dev)
+        self.eng = model.engine_for(batch, height, width, True)
+        self.fused = bool(fused_loss) and self.eng.group
+        self.x = self.eng.x_in if self.fused else torch.zeros(batch, 3, height, width, device=dev)
+        if self.fused:
+            L = self.eng.enable_fused_loss(pixelwise=model._pixelwise_flag())
+            self.target, self.mask, self.valid_depth = L.target, L.mask, L.valid_depth
+            self.coords = L.coords[-1]
+            self.loss = L.out2[0]
+        else:
+            self.target = torch.zeros(batch, J, 3, device=dev)
+            self.mask = torch.ones(batch, J, device=dev)
+            self.valid_depth = None
+            self.coords = torch.zeros(batch, J, 3, device=dev)
+            self.loss = torch.zeros((), device=dev)
         self.use_graph = use_graph
         self.warmup = warmup
         self._graphs = None
         self._eager_runs = 0
         self.world = parallel.world()[1]
-        model.train()
+        self.overlap = bool(overlap_allreduce) and self.world > 1 and self.fused
+        self.comm = torch.cuda.Stream(device=dev) if self.overlap else None
+        if self.world > 1 and hasattr(optimizer, 'grad_scale'):
+            optimizer.grad_scale = 1.0 / self.world      # the all-reduce sums; the SGD kernel scales
+        self._scale_in_opt = self.world > 1 and hasattr(optimizer, 'grad_scale')
+        # backward program slices [lo, hi) and the flat-gradient ranges that are final after each
+        self._pieces = parallel.bucket_plan(self.eng.bwd_marks, self.eng.L.stage_ranges,
+                                            model._bank.flat_grad.numel())
 
-    # ---- the step, split where the gradient all-reduce goes
-    def _fwd_bwd(self):
+    # ---- pieces of the step
+    def _forward_and_loss(self):
+        model, eng = self.model, self.eng
         self.opt.zero_grad()
-        out = self.model(self.x)
-        loss = K.average_loss(self.model.forward_3d_losses(out, self.target), self.mask)
-        loss.backward()
+        if self.fused:
+            model._refresh_packs()
+            probs = eng.forward(self.x, fused=True)
+            model.xy_heatmaps = [row[0] for row in probs]
+            model.zy_heatmaps = [row[1] for row in probs]
+            model.xz_heatmaps = [row[2] for row in probs]
+            eng.loss_reduce()
+            model._bank.attach_grads()
+            return None
+        out = model(self.x)
+        loss = K.average_loss(model.forward_3d_losses(out, self.target), self.mask)
         self.loss.copy_(loss.detach())
         self.coords.copy_(out.detach())
+        return loss
+
+    def _fwd_bwd(self):
+        loss = self._forward_and_loss()
+        if self.fused:
+            self.eng.backward()
+        else:
+            loss.backward()
 
     def _update(self):
         self.opt.step()
 
-    def _allreduce(self):
+    def _allreduce_all(self):
         if self.world > 1:
-            parallel.allreduce_mean_(self.model.flat_grads)
+            g = self.model.flat_grads
+            if self._scale_in_opt:
+                parallel.allreduce_sum_(g)
+            else:
+                parallel.allreduce_mean_(g)
+
+    def _reduce_ranges(self, ranges, works):
+        """All-reduce finished gradient ranges on the side stream, behind everything issued so far."""
+        g = self.model.flat_grads
+        self.comm.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.comm):
+            for lo, hi in ranges:
+                works.append(parallel.allreduce_sum_(g[lo:hi], async_op=True))
 
     def run(self):
         """One step on whatever is in the static buffers (self.x / self.target / self.mask)."""
         if self.use_graph and self._graphs is None and self._eager_runs >= self.warmup:
             self._capture()
         if self._graphs is not None:
-            self._graphs[0].replay()
-            self._allreduce()
+            if self.overlap:
+                works = []
+                for g, (_lo, _hi, ranges) in zip(self._graphs[:-1], self._pieces):
+                    g.replay()
+                    self._reduce_ranges(ranges, works)
+                for w in works:
+                    if w is not None:
+                        w.wait()
+            else:
+                self._graphs[0].replay()
+                self._allreduce_all()
             if hasattr(self.opt, 'refresh_hyper'):
                 self.opt.refresh_hyper()   # LR / momentum schedules reach the captured optimiser step
-            self._graphs[1].replay()
+            self._graphs[-1].replay()
+            if hasattr(self.opt, 'count_replayed_step'):
+                self.opt.count_replayed_step()
         else:
-            self._fwd_bwd()
-            self._allreduce()
+            if self.overlap:
+                works = []
+                self._forward_and_loss()
+                for lo, hi, ranges in self._pieces:
+                    self.eng.backward(lo=lo, hi=hi)
+                    self._reduce_ranges(ranges, works)
+                for w in works:
+                    if w is not None:
+                        w.wait()
+            else:
+                self._fwd_bwd()
+                self._allreduce_all()
             self._update()
             self._eager_runs += 1
 
     def _capture(self):
         torch.cuda.synchronize(self.device)
-        g0, g1 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g0):
-            self._fwd_bwd()
-        with torch.cuda.graph(g1, pool=g0.pool()):
+        graphs = []
+        if self.overlap:
+            pool = None
+            for i, (lo, hi, _ranges) in enumerate(self._pieces):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    if i == 0:
+                        self._forward_and_loss()
+                    self.eng.backward(lo=lo, hi=hi)
+                pool = pool or g.pool()
+                graphs.append(g)
+        else:
+            g0 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g0):
+                self._fwd_bwd()
+            graphs.append(g0)
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1, pool=graphs[0].pool()):
             self._update()
-        self._graphs = (g0, g1)
+        # the capture ran step() once on the host without executing it: undo its bookkeeping
+        if hasattr(self.opt, '_steps'):
+            self.opt._steps -= 1
+        graphs.append(g1)
+        self._graphs = tuple(graphs)
 
-    def load(self, images, targets, mask=None):
+    def load(self, images, targets, mask=None, valid_depth=None):
         self.x.copy_(images, non_blocking=True)
-        self.target.copy_(targets, non_blocking=True)
+        self.target.copy_(targets[..., :3], non_blocking=True)
         if mask is not None:
             self.mask.copy_(mask, non_blocking=True)
+        if valid_depth is not None:
+            if not self.fused:
+                raise ValueError('per-sample valid_depth flags need the fused loss path')
+            self.valid_depth.copy_(torch.as_tensor(valid_depth).to(torch.int32), non_blocking=True)
 
-    def __call__(self, images, targets, mask=None):
+    def __call__(self, images, targets, mask=None, valid_depth=None):
         """Copies one batch in (pinned host tensors copy asynchronously), runs the step and returns
-        the loss as a Python float (a 4-byte device-to-host read, like train_3d.py:167)."""
-        self.load(images, targets, mask)
+        the loss as a Python float (a 4-byte device-to-host read, like train_3d.py:167).
+        valid_depth: optional per-sample flags, 1 = 3D loss, 0 = 2D loss (bin/train_3d.py:126-142)."""
+        self.load(images, targets, mask, valid_depth)
         self.run()
         return self.loss.item()
 
     def launches_per_step(self):
         """Kernel launches of OUR library in one step (for bench.py's gpu_launches)."""
-        eng = self.model.engine_for(self.x.size(0), self.x.size(2), self.x.size(3), True)
+        eng = self.eng
         n_stages = len(eng.probs)
-        extra = 1 + 2 * n_stages + 1 + 2 + 1   # pack, stage losses fwd+bwd, coords, masked mean fwd+bwd, sgd
+        if self.fused:
+            extra = 1 + 2 + 1               # pack, masked mean fwd + bwd, sgd (stage tails are in the programs)
+        else:
+            extra = 1 + 2 * n_stages + 1 + 2 + 1   # pack, stage losses fwd+bwd, coords, masked mean fwd+bwd, sgd
         return eng.launches() + extra

@@ -28,7 +28,7 @@ def _gather(v, c0, nc, dw, p, dh, out_h, out_w):
 
 
 def igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_c, res=None,
-          stats=None, out_offset=0, bn=None, defer=None):
+          stats=None, out_offset=0, bn=None, defer=None, ep=None):
     views = [_view5(t, parity) for t, parity in srcs]
     wm = wmat.float()
     acc = torch.zeros(n_img, out_h, out_w, wm.shape[0])
@@ -40,9 +40,16 @@ def igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_
     sn, sh, sw = out_strides
     flat = out.view(-1)
     dst = torch.as_strided(flat, (n_img, out_h, out_w, out_c), (sn, sh, sw, 1), out_offset)
+    if ep is not None:     # (scale, shift, relu mode) as fp32 tensors here (device pointers on the GPU)
+        scale, shift, relu = ep
+        acc = acc * scale[:out_c] + shift[:out_c]
+        if relu == 1:
+            acc = acc.clamp_min(0)
     if res is not None:
         acc = acc + torch.as_strided(res.view(-1), (n_img, out_h, out_w, out_c), (sn, sh, sw, 1),
                                      out_offset).float()
+    if ep is not None and ep[2] == 2:
+        acc = acc.clamp_min(0)
     rounded = acc.to(torch.bfloat16)
     dst.copy_(rounded)
     if stats is not None:
