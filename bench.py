@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the MargiPose training hot path on B200 (BASELINE.json metric: images/sec fwd+bwd).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference|torch-gpu]
+                    [--config r34x4_256|r50x5_384]
 
 Workload (config.workload): BASELINE.json configs[1] -- 4-stage ResNet-34 MargiPose, 256x256,
 17 joints, batch 32 per GPU, one training step = forward + forward_3d_losses/average_loss +
@@ -17,6 +18,12 @@ seeded random-init weights (no network for datasets / checkpoints).
   cpu_baseline / --impl reference : the reference algorithm's CPU path (the fp32 oracle port
           of /root/reference/src/margipose, the unmodified reference cannot travel to the GPU box)
           on the host cores, on a bounded sample of the same workload
+  gpu_library_baseline / --impl torch-gpu : the same-box GPU comparator of SURVEY.md section 8(d): the oracle
+          module (stock nn.Conv2d / BatchNorm2d / ATen ops = cuDNN + cuBLAS, cudnn.benchmark as the reference
+          sets it, utils.py:23-24) running the SAME step on the B200 in fp32, TF32 and bf16-autocast
+  inference : eval-mode forward (bin/infer_single.py:58-66, bin/eval_3d.py:60-62) through InferStep (BatchNorm
+          folded into the convs, one captured CUDA graph), batch 1 latency and batch 32 throughput
+--config r50x5_384 measures BASELINE.json configs[4] (ResNet-50, 5 stages, 384x384, 16 images per GPU).
 """
 import argparse
 import json
@@ -30,12 +37,29 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DESC = {'type': 'margipose', 'version': '6.0.1',
-        'settings': {'n_stages': 4, 'axis_permutation': True, 'feature_extractor': 'resnet34',
-                     'pixelwise_loss': 'jsd'}}
-RES, JOINTS = 256, 17
-FLOPS_PER_IMAGE = 161.35e9      # conv fwd+bwd, SURVEY.md section 6 (FlopCounterMode on the reference)
-METRIC = 'images/sec fwd+bwd (4-stage ResNet-34 MargiPose, 256x256, 17 joints)'
+JOINTS = 17
+CONFIGS = {   # conv FLOPs per image fwd+bwd: SURVEY.md section 6 (FlopCounterMode on the reference)
+    'r34x4_256': dict(fe='resnet34', n_stages=4, res=256, batch=32, flops=161.35e9, cpu_batch=8,
+                      workload='configs[1]: 4-stage ResNet-34 MargiPose, 256x256, 17 joints',
+                      metric='images/sec fwd+bwd (4-stage ResNet-34 MargiPose, 256x256, 17 joints)'),
+    'r50x5_384': dict(fe='resnet50', n_stages=5, res=384, batch=16, flops=449.75e9, cpu_batch=2,
+                      workload='configs[4]: ResNet-50 backbone, 5 stages, 384x384, 17 joints',
+                      metric='images/sec fwd+bwd (5-stage ResNet-50 MargiPose, 384x384, 17 joints)'),
+}
+CFG = CONFIGS['r34x4_256']
+DESC = RES = FLOPS_PER_IMAGE = METRIC = None
+
+
+def select_config(name):
+    global CFG, DESC, RES, FLOPS_PER_IMAGE, METRIC
+    CFG = CONFIGS[name]
+    DESC = {'type': 'margipose', 'version': '6.0.1',
+            'settings': {'n_stages': CFG['n_stages'], 'axis_permutation': True,
+                         'feature_extractor': CFG['fe'], 'pixelwise_loss': 'jsd'}}
+    RES, FLOPS_PER_IMAGE, METRIC = CFG['res'], CFG['flops'], CFG['metric']
+
+
+select_config('r34x4_256')
 
 
 def peaks():
@@ -147,16 +171,82 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    base = cpu_reference(batch=4, steps=max(1, args.steps), warmup=1, budget_s=150.0)
+    warm = max(1, min(args.warmup, 3))
+    base = cpu_reference(batch=CFG['cpu_batch'], steps=max(1, args.steps), warmup=warm, budget_s=150.0)
     line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'images/s', 'n_gpus': args.gpus,
-            'steps': base['steps'], 'warmup': 1, 'ms_per_step': base['ms_per_step'], 'higher_is_better': True,
+            'steps': base['steps'], 'warmup': warm, 'ms_per_step': base['ms_per_step'], 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'configs[1]: 4-stage ResNet-34 MargiPose 256x256 17 joints, training step; '
-                                   'CPU sample of batch 4 per step'},
+            'config': {'workload': '%s, training step; CPU sample of batch %d per step'
+                                   % (CFG['workload'], CFG['cpu_batch'])},
             'cpu_baseline': {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
             'e2e': {'value': base['value'], 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------- stock PyTorch on the same GPU
+def gpu_library_baseline(batch, steps=5, warmup=3):
+    """SURVEY.md section 8(d) / BASELINE.md 4.6: the reference module's training step (bin/train_3d.py:159-186)
+    executed by stock PyTorch on the B200 -- cuDNN convolutions / BatchNorm, ATen softmax and elementwise ops,
+    autograd, torch.optim.SGD -- in the three precisions a user could pick.  channels_last + cudnn.benchmark
+    (utils.py:23-24).  None of this repository's kernels are on this path; it is the bar to beat on the box."""
+    import torch
+    from oracle import model_oracle as M
+    from oracle import dsnt_oracle as D
+    dev = torch.device('cuda', torch.cuda.current_device())
+    torch.backends.cudnn.benchmark = True
+    x, t, m = synthetic(batch, 1, seed=7, device=dev)[0]
+    x = x.contiguous(memory_format=torch.channels_last)
+    out = {'module': 'oracle restatement of the reference nn.Module (same op sites), stock PyTorch %s / cuDNN %s'
+                     % (torch.__version__, torch.backends.cudnn.version()),
+           'batch': batch, 'steps': steps, 'warmup': warmup, 'unit': 'images/s'}
+    for name in ('fp32', 'tf32', 'bf16_autocast'):
+        torch.backends.cudnn.allow_tf32 = name != 'fp32'
+        torch.backends.cuda.matmul.allow_tf32 = name != 'fp32'
+        torch.manual_seed(0)
+        om = M.create_oracle(DESC).to(dev).to(memory_format=torch.channels_last).train()
+        opt = torch.optim.SGD(om.parameters(), lr=1e-3, momentum=0.9)
+
+        def one():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast('cuda', dtype=torch.bfloat16, enabled=name == 'bf16_autocast'):
+                y = om(x)
+                hm = [[h.float() for h in hs] for hs in (om.xy_heatmaps, om.zy_heatmaps, om.xz_heatmaps)]
+            om.xy_heatmaps, om.zy_heatmaps, om.xz_heatmaps = hm
+            loss = D.average_loss(om.forward_3d_losses(y.float(), t), m)
+            loss.backward()
+            opt.step()
+            return loss
+        try:
+            for _ in range(warmup):
+                one()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss = one()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {'value': batch / (ms * 1e-3), 'ms_per_step': ms, 'last_loss': loss.item()}
+        except Exception as exc:       # comparator only: never fail the bench line because of it
+            out[name] = {'error': '%s: %s' % (type(exc).__name__, str(exc)[:200])}
+        del om, opt
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = True
+    return out
+
+
+def run_torch_gpu(args):
+    import torch
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    base = gpu_library_baseline(args.batch or CFG['batch'], steps=max(1, min(args.steps, 20)), warmup=3)
+    best = max((v['value'] for v in base.values() if isinstance(v, dict) and 'value' in v), default=None)
+    print(json.dumps({'impl': 'torch-gpu', 'metric': METRIC, 'value': best, 'unit': 'images/s', 'n_gpus': 1,
+                      'higher_is_better': True, 'data': 'synthetic', 'config': {'workload': CFG['workload']},
+                      'gpu_library_baseline': base}))
 
 
 def tail_sweep(peak_bw, sizes=(32, 64, 128), batch=128):
@@ -211,6 +301,41 @@ def tail_sweep(peak_bw, sizes=(32, 64, 128), batch=128):
     return out
 
 
+def inference_bench(model, dev, batch, reps=50):
+    """Eval-mode forward through InferStep (folded BatchNorm, captured graph): batch 1 latency (the reference's
+    `margipose infer` / eval_3d.py batch size) and batch `batch` throughput; fp32 NCHW input copied from pinned
+    host memory and the (B, 17, 3) result read back to the host inside the timed region, plus the device-only
+    time of the captured forward.  The model keeps the running statistics the training steps above produced."""
+    import torch
+    from margipose_b200.infer import InferStep
+    out = {'api': 'margipose_b200.infer.InferStep (model.eval(), BatchNorm folded into the conv epilogues, '
+                  'one CUDA graph)', 'unit': 'images/s'}
+    model.eval()
+    for b in sorted({1, batch}):
+        inf = InferStep(model, b, RES, RES)
+        x = torch.randn(b, 3, RES, RES).pin_memory()
+        for _ in range(5):
+            inf(x).cpu()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            xyz = inf(x).cpu()
+        wall = (time.perf_counter() - t0) / reps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            inf.run()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        gpu_ms = e0.elapsed_time(e1) / reps
+        out['batch_%d' % b] = {'e2e_ms': 1e3 * wall, 'e2e_images_per_s': b / wall, 'gpu_ms': gpu_ms,
+                               'gpu_images_per_s': b / (gpu_ms * 1e-3), 'launches': inf.launches(),
+                               'finite': bool(torch.isfinite(xyz).all())}
+        del inf
+    model.train()
+    return out
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def run_b200(args):
     import torch
@@ -227,7 +352,7 @@ def run_b200(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    B, K, W = args.batch or CFG['batch'], args.steps, max(args.warmup, 3)
 
     torch.manual_seed(0)
     model = create_model(DESC).to(dev).train()
@@ -319,25 +444,36 @@ def run_b200(args):
         tail = {'bound': 'hbm', 'unit': 'GB/s', 'peak': peak_bw, 'peak_source': src + ' copy bandwidth (MEASURED_PEAKS.json)',
                 'workload': 'configs[3]: heatmap 32/64/128, 17 joints, batch 128, three planes',
                 'sweep': tail_sweep(peak_bw)}
+    infer = None
+    if world == 1 and not args.skip_infer:
+        infer = inference_bench(model, dev, B)
     cpu = None
     if world == 1 and not args.skip_cpu:
-        cpu = cpu_reference(batch=4, steps=2, warmup=1, budget_s=60.0)
+        cpu = cpu_reference(batch=CFG['cpu_batch'], steps=3, warmup=1, budget_s=60.0)
         cpu = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+    n_launches = step.launches_per_step() * K * 2
+    gpu_lib = None
+    if world == 1 and not args.skip_gpu_lib:
+        del step, eng
+        model.drop_engines()
+        torch.cuda.empty_cache()
+        gpu_lib = gpu_library_baseline(B)
     value = B * world * K / (ms * 1e-3)
     line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': 'configs[1]: 4-stage ResNet-34 MargiPose, 256x256, 17 joints, batch %d per GPU, '
-                                   'fwd + 3D loss + bwd + SGD-momentum step' % B,
+            'config': {'workload': '%s, batch %d per GPU, fwd + 3D loss + bwd + SGD-momentum step'
+                                   % (CFG['workload'], B),
                        'global_batch': B * world, 'parallelism': 'dp%d' % world,
                        'cuda_graph': not args.no_graph,
                        'l2': 'per-step working set (~10 GB of activations) exceeds the 126 MB L2; 4 input sets rotate'},
             'conv_flops_per_image': FLOPS_PER_IMAGE,
             'conv_tflops_whole_step': value / world * FLOPS_PER_IMAGE / 1e12,
-            'roofline': roof, 'tail_roofline': tail, 'cpu_baseline': cpu,
+            'roofline': roof, 'tail_roofline': tail, 'cpu_baseline': cpu, 'gpu_library_baseline': gpu_lib,
+            'inference': infer,
             'e2e': {'value': B * world * K / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'last_loss': last},
-            'gpu_launches': step.launches_per_step() * K * 2, 'clocks': clocks}
+            'gpu_launches': n_launches, 'clocks': clocks}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -348,14 +484,20 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=10)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=32, help='images per GPU per step')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'torch-gpu'])
+    ap.add_argument('--config', default='r34x4_256', choices=sorted(CONFIGS))
+    ap.add_argument('--batch', type=int, default=0, help='images per GPU per step (default: the config\'s)')
+    ap.add_argument('--skip-gpu-lib', action='store_true', help='skip the stock-PyTorch-on-GPU comparator')
+    ap.add_argument('--skip-infer', action='store_true', help='skip the eval-mode inference measurement')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-tail', action='store_true', help='skip the soft-argmax fusion HBM sweep (configs[3])')
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == 'reference':
         run_reference(args)
+    elif args.impl == 'torch-gpu':
+        run_torch_gpu(args)
     else:
         run_b200(args)
 

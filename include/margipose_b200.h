@@ -310,6 +310,11 @@ MP_API int mp_combiner_bwd(const void* dout, const float* const p[3], const floa
  * into bf16 patch rows (N, H/2, W/2, 192) with k = (r*7 + s)*3 + c (147 real + zero padding), so
  * the conv and its weight gradient run as 1x1 cases of mp_conv_igemm / mp_conv_wgrad. */
 MP_API int mp_stem_im2col(const float* x, void* patches, int N, int H, int W, void* stream);
+/* Same from a uint8 NHWC image (N, H, W, 3) with the reference's input step fused in: ImageSpecs.convert =
+ * to_tensor (/255) + (x - mean) / stddev (data_specs.py:6-13,38-39; mean / stddev: HOST pointers to 3 floats,
+ * ImageNet statistics for the MargiPose model, models/margipose_model.py:206-209). */
+MP_API int mp_stem_im2col_u8(const uint8_t* x, void* patches, const float mean[3], const float stddev[3],
+                             int N, int H, int W, void* stream);
 
 /* out = sum of n (<= 4) bf16 tensors of `count` elements (gradient fan-in). */
 MP_API int mp_add_bf16(const void* const in[4], int n, void* out, int64_t count, void* stream);

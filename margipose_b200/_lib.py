@@ -118,6 +118,8 @@ def _signatures():
         'mp_combiner_fwd': (I, [PT, P, P, P, I, I, I, I, P]),
         'mp_combiner_bwd': (I, [P, PT, P, PT, P, I, I, I, I, I, P]),
         'mp_stem_im2col': (I, [P, P, I, I, I, P]),
+        'mp_stem_im2col_u8': (I, [P, P, ctypes.POINTER(ctypes.c_float * 3), ctypes.POINTER(ctypes.c_float * 3),
+                                  I, I, I, P]),
         'mp_add_bf16': (I, [ctypes.POINTER(c_void_p * 4), I, P, ctypes.c_int64, P]),
         'mp_pack_weights': (I, [P, P, P, I, ctypes.c_int64, P]),
         'mp_sgd_step': (I, [P, P, P, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float,

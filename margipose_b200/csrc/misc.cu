@@ -438,6 +438,41 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* _
   *reinterpret_cast<uint4*>(out + (((long long)n * Ho + ho) * Wo + wo) * 192 + g * 8) = pack8(v);
 }
 
+// Same gather from a uint8 NHWC image (what an image decoder produces) with the input step of the reference fused
+// in: to_tensor (/255) and ImageNet normalisation (x - mean) / std (data_specs.py:6-13,38-39).  Padding taps are
+// zeros of the NORMALISED tensor, as the conv's zero padding sees them.
+__global__ void stem_im2col_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
+                                      int W, float3 scale, float3 shift) {
+  pdl_trigger();
+  pdl_wait();
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Ho * Wo * 24;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int wo = (int)(i % Wo);
+  long long t = i / Wo;
+  const int g = (int)(t % 24); t /= 24;
+  const int ho = (int)(t % Ho);
+  const int n = (int)(t / Ho);
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = g * 8 + j;
+    float val = 0.f;
+    if (k < 147) {
+      const int tap = k / 3, c = k - tap * 3;
+      const int r = tap / 7, s = tap - r * 7;
+      const int h = 2 * ho + r - 3, w = 2 * wo + s - 3;
+      if (h >= 0 && h < H && w >= 0 && w < W) {
+        const float px = (float)__ldg(x + (((long long)n * H + h) * W + w) * 3 + c);
+        val = fmaf(px, c == 0 ? scale.x : (c == 1 ? scale.y : scale.z), c == 0 ? shift.x : (c == 1 ? shift.y : shift.z));
+      }
+    }
+    v[j] = val;
+  }
+  *reinterpret_cast<uint4*>(out + (((long long)n * Ho + ho) * Wo + wo) * 192 + g * 8) = pack8(v);
+}
+
 // -------------------------------------------------------------------------------------- add_n
 __global__ void add_bf16_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, const __nv_bfloat16* c,
                                 const __nv_bfloat16* d, int n, __nv_bfloat16* out, long long groups) {
@@ -641,6 +676,21 @@ int mp_stem_im2col(const float* x, void* patches, int N, int H, int W, void* str
   MP_CUDA(mp_launch(stem_im2col_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
       x, (__nv_bfloat16*)patches, N, H, W));
   MP_CHECK_LAUNCH("mp_stem_im2col");
+  return MP_OK;
+}
+
+int mp_stem_im2col_u8(const uint8_t* x, void* patches, const float mean[3], const float stddev[3], int N, int H, int W,
+                      void* stream) {
+  MP_CHECK_ARG(x && patches && mean && stddev && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0,
+               "mp_stem_im2col_u8: bad arguments");
+  MP_CHECK_ARG(stddev[0] > 0.f && stddev[1] > 0.f && stddev[2] > 0.f, "mp_stem_im2col_u8: stddev must be positive");
+  const long long total = (long long)N * (H / 2) * (W / 2) * 24;
+  // (p / 255 - mean) / std = p * scale + shift
+  const float3 scale = make_float3(1.f / (255.f * stddev[0]), 1.f / (255.f * stddev[1]), 1.f / (255.f * stddev[2]));
+  const float3 shift = make_float3(-mean[0] / stddev[0], -mean[1] / stddev[1], -mean[2] / stddev[2]);
+  MP_CUDA(mp_launch(stem_im2col_u8_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
+      x, (__nv_bfloat16*)patches, N, H, W, scale, shift));
+  MP_CHECK_LAUNCH("mp_stem_im2col_u8");
   return MP_OK;
 }
 

@@ -25,7 +25,7 @@ from torch import nn
 
 from . import convops as C
 from . import dsntnn as K
-from ._lib import (BnArgs, BnBranch, PackEntry, lib, check, stream_ptr, planes, MargiposeB200Error)
+from ._lib import (BnArgs, BnBranch, BnFoldEntry, PackEntry, lib, check, stream_ptr, planes, MargiposeB200Error)
 
 
 def _ptr(t):
@@ -241,6 +241,7 @@ class BNL:
         layers.bn_floats += 2 * self.Cp
         self.index = layers.n_bn              # ticket-counter index
         layers.n_bn += 1
+        layers.bns.append(self)
 
 
 class _NS:
@@ -257,6 +258,7 @@ def build_layers(model, bank):
     L = _NS()
     L.bn_floats = 0
     L.n_bn = 0
+    L.bns = []
     inner = model.inner
     L.n_stages, L.n_joints = inner.n_stages, model.n_joints
     cnn = inner.in_cnn
@@ -354,7 +356,14 @@ class Engine:
         self._fused = False    # this forward / backward runs the fused loss path (forward(x, fused=True))
         self.bwd_marks = []    # index into self.bwd after which stage t's parameter gradients are complete
         self.trace = []        # (name, buffer, real channels) of every block output, in forward order
+        # inference: eval-mode BatchNorm is a per-channel affine, applied in the producing conv's epilogue
+        # (bin/infer_single.py:58-66): no BatchNorm pass, no pre-BatchNorm tensor
+        self.fold = (not training) and os.environ.get('MARGIPOSE_B200_FOLD', '1') != '0'
+        self._u8 = False       # this forward gathers from the uint8 NHWC image buffer (normalisation fused)
+        self.x_u8 = None
         self._record()
+        if self.fold:
+            self._build_fold_table()
 
     def act(self, n, h, w, c, dtype=torch.bfloat16):
         t = torch.zeros(n, h, w, c, dtype=dtype, device=self.device)
@@ -519,6 +528,25 @@ class Engine:
         op._keep = (pp, gp)
         return op
 
+    def _gather_op(self, patches, n, h, w):
+        """ResNet stem conv1 gather from the fp32 NCHW image, or -- forward(uint8 NHWC image) -- from the raw
+        image with /255 and ImageNet normalisation fused in (data_specs.py:6-13,38-39)."""
+        fn, fn8, dev = lib().mp_stem_im2col, lib().mp_stem_im2col_u8, self.device
+        specs = self.model.data_specs.input_specs
+        mean = (ctypes.c_float * 3)(*(specs.mean or (0.0, 0.0, 0.0)))
+        std = (ctypes.c_float * 3)(*(specs.stddev or (1.0, 1.0, 1.0)))
+
+        def op():
+            if self._u8:
+                rc = fn8(self.x_u8.data_ptr(), patches.data_ptr(), ctypes.byref(mean), ctypes.byref(std), n, h, w,
+                         stream_ptr(dev))
+            else:
+                rc = fn(self.x_in.data_ptr(), patches.data_ptr(), n, h, w, stream_ptr(dev))
+            if rc != 0:
+                check(rc, 'mp_stem_im2col')
+        op.name = 'mp_stem_im2col'
+        return op
+
     @staticmethod
     def _on_aux(ops):
         for op in ops:
@@ -608,9 +636,44 @@ class Engine:
         prog.append(self._launch('mp_bn_bwd_reduce', args))
         prog.append(self._launch('mp_bn_bwd_apply', args))
 
+    # ---- inference with folded BatchNorm
+    def _build_fold_table(self):
+        bns = self.L.bns
+        table = (BnFoldEntry * len(bns))()
+        base = self.affine.data_ptr()
+        for e, bn in zip(table, bns):
+            e.gamma, e.beta = bn.gamma.data.data_ptr(), bn.beta.data.data_ptr()
+            e.running_mean, e.running_var = bn.rm.data.data_ptr(), bn.rv.data.data_ptr()
+            e.conv_bias = bn.conv_bias.data.data_ptr() if bn.conv_bias is not None else None
+            e.scale, e.shift = base + 4 * bn.slot, base + 4 * (bn.slot + bn.Cp)
+            e.C, e.Cp, e.eps = bn.C, bn.Cp, bn.mod.eps
+        raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8)
+        self._fold_table = raw.to(self.device)
+        self._n_fold = len(bns)
+
+    def conv_folded(self, prog, conv, x, bn, relu, res=None):
+        """y = relu?(BatchNorm_eval(conv(x))) (+ res): one launch, the affine rides in the conv epilogue."""
+        g = conv.g
+        n, h, w, _ = x.shape
+        ho, wo = g.out_hw(h, w)
+        y = self.act(n, ho, wo, g.cout_p)
+        base = self.affine.data_ptr()
+        ep = (base + 4 * bn.slot, base + 4 * (bn.slot + bn.Cp), relu)
+        prog += self.conv_ops(lambda: C.conv_forward(g, x, conv.fwd.t, y, res=res, ep=ep))
+        return y
+
+    @staticmethod
+    def _foldable(conv):
+        # a 1x1 transposed conv writes one of four output parity classes; BatchNorm's shift belongs on all four
+        return not (conv.g.transposed and conv.g.k == 1)
+
     # ---- blocks: each returns (output buffer, backward builder)
     def residual_block(self, fwd, rb, x, logits_out=None):
         """MargiPose ResidualBlock (margipose_model.py:25-40)."""
+        if self.fold and logits_out is None and self._foldable(rb.convs):
+            ys = self.conv_folded(fwd, rb.convs, x, rb.bns, 0)                 # bn_s(conv_s(x))
+            a1 = self.conv_folded(fwd, rb.conv1, x, rb.bn1, 1)                 # relu(bn_1(conv_1(x)))
+            return self.conv_folded(fwd, rb.conv2, a1, rb.bn2, 1, res=ys), None   # relu(bn_2(conv_2(a1))) + shortcut
         side = []
         ys = self.conv_fwd(side, rb.convs, x, rb.bns)
         fwd += self._on_aux(side)
@@ -646,6 +709,12 @@ class Engine:
     def resnet_block(self, fwd, blk, x):
         """torchvision BasicBlock / Bottleneck: relu(bn_last(conv_last(...)) + identity)."""
         chain, down = blk.chain, blk.down
+        if self.fold:
+            ident = x if down is None else self.conv_folded(fwd, down[0], x, down[1], 0)
+            a = x
+            for conv, bn in chain[:-1]:
+                a = self.conv_folded(fwd, conv, a, bn, 1)
+            return self.conv_folded(fwd, chain[-1][0], a, chain[-1][1], 2, res=ident), None   # relu(bn(conv) + identity)
         acts, ys, fargs = [x], [], []
         for i, (conv, bn) in enumerate(chain):
             y = self.conv_fwd(fwd, conv, acts[-1], bn)
@@ -705,13 +774,17 @@ class Engine:
         # ---- stem (margipose_model.py:119-138)
         self.x_in = torch.zeros(n, 3, h, w, device=dev)
         patches = self.act(n, h // 2, w // 2, 192)
-        fwd.append(self._call('mp_stem_im2col', self.x_in.data_ptr(), patches.data_ptr(), n, h, w))
+        fwd.append(self._gather_op(patches, n, h, w))
         conv0, bn0 = L.stem
-        y0 = self.conv_fwd(fwd, conv0, patches, bn0)
-        a0 = self.act(*y0.shape)
-        f0 = self.bn_args(bn0, y0, relu_a=True, out=a0)
-        fwd.append(self._launch('mp_bn_fwd', f0))
-        hp, wp, c0 = h // 4, w // 4, y0.shape[-1]
+        if self.fold:
+            y0 = f0 = None
+            a0 = self.conv_folded(fwd, conv0, patches, bn0, 1)
+        else:
+            y0 = self.conv_fwd(fwd, conv0, patches, bn0)
+            a0 = self.act(*y0.shape)
+            f0 = self.bn_args(bn0, y0, relu_a=True, out=a0)
+            fwd.append(self._launch('mp_bn_fwd', f0))
+        hp, wp, c0 = h // 4, w // 4, a0.shape[-1]
         p0 = self.act(n, hp, wp, c0)
         idx = torch.zeros(n, hp, wp, c0, dtype=torch.uint8, device=dev)
         self._bufs.append(idx)
@@ -726,10 +799,13 @@ class Engine:
         x_pre = x
         if L.adapter is not None:
             conva, bna = L.adapter
-            ya = self.conv_fwd(fwd, conva, x, bna)
-            x = self.act(*ya.shape)
-            fa = self.bn_args(bna, ya, relu_a=True, out=x)
-            fwd.append(self._launch('mp_bn_fwd', fa))
+            if self.fold:
+                x = self.conv_folded(fwd, conva, x, bna, 1)
+            else:
+                ya = self.conv_fwd(fwd, conva, x, bna)
+                x = self.act(*ya.shape)
+                fa = self.bn_args(bna, ya, relu_a=True, out=x)
+                fwd.append(self._launch('mp_bn_fwd', fa))
             self.trace.append(('adapter', x, bna.C))
         feats = x
         hf, wf, cf = feats.shape[1], feats.shape[2], feats.shape[3]
@@ -784,6 +860,7 @@ class Engine:
             self.logits.append(lz)
             col_bwd.append(lane_bwd)
         self.fwd = segs
+        self.stage_inputs = inps     # feats + sum of the earlier stages' combiner outputs (layer-wise parity tests)
         if not training:
             return
 
@@ -919,8 +996,19 @@ class Engine:
         tensors (and everything a backward reads) are the engine's static buffers: the next forward of this
         engine overwrites them, and a backward is only valid for the most recent forward (checked through
         `generation`)."""
-        if x.data_ptr() != self.x_in.data_ptr():
-            self.x_in.copy_(x)
+        if x.dtype == torch.uint8:      # raw NHWC image: the stem gather normalises on the fly
+            if tuple(x.shape) != (self.n, self.h, self.w, 3):
+                raise MargiposeB200Error('uint8 input must be (N, H, W, 3) = %s, got %s'
+                                         % ((self.n, self.h, self.w, 3), tuple(x.shape)))
+            if self.x_u8 is None:
+                self.x_u8 = torch.zeros(self.n, self.h, self.w, 3, dtype=torch.uint8, device=self.device)
+            if x.data_ptr() != self.x_u8.data_ptr():
+                self.x_u8.copy_(x)
+            self._u8 = True
+        else:
+            if x.data_ptr() != self.x_in.data_ptr():
+                self.x_in.copy_(x)
+            self._u8 = False
         self.generation += 1
         self._fused = bool(fused)
         if fused and self.loss_ctx is None:
@@ -929,6 +1017,9 @@ class Engine:
             self.stats[:self._stat_fwd_n].zero_()       # forward BatchNorm sums
             self.stats[self._counter_base:].zero_()     # ticket counters
             self.bank.flat_cnt.add_(1)
+        if self.fold:   # running statistics -> per-channel affines for every BatchNorm of the network, one launch
+            check(lib().mp_bn_fold_eval(self._fold_table.data_ptr(), self._n_fold, stream_ptr(self.device)),
+                  'mp_bn_fold_eval')
         self._run(self.fwd)
         return self.probs
 

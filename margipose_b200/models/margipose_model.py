@@ -285,6 +285,10 @@ class MargiPoseModel(nn.Module):
             self._engines[key] = eng
         return eng
 
+    def drop_engines(self):
+        """Frees the activation buffers / launch programs of every (batch, resolution, mode) seen so far."""
+        self._engines = {}
+
     def mark_params_dirty(self):
         """Call after writing parameters through raw device pointers (the flat optimiser does)."""
         self._packed_version = None
@@ -312,11 +316,20 @@ class MargiPoseModel(nn.Module):
 
     def _inner_forward(self, x):
         require_cuda(x)
-        if x.dim() != 4 or x.size(1) != 3:
-            raise ValueError('expected a (B, 3, H, W) image batch, got %s' % (tuple(x.shape),))
-        x = x.float().contiguous()
+        if x.dtype == torch.uint8:
+            # raw image batch (B, H, W, 3) as a decoder produces it: /255 and the ImageNet normalisation of
+            # data_specs (ImageSpecs.convert, data_specs.py:38-39) are fused into the stem conv's gather
+            if x.dim() != 4 or x.size(3) != 3:
+                raise ValueError('expected a uint8 (B, H, W, 3) image batch, got %s' % (tuple(x.shape),))
+            x = x.contiguous()
+            n, h, w = x.size(0), x.size(1), x.size(2)
+        else:
+            if x.dim() != 4 or x.size(1) != 3:
+                raise ValueError('expected a (B, 3, H, W) image batch, got %s' % (tuple(x.shape),))
+            x = x.float().contiguous()
+            n, h, w = x.size(0), x.size(2), x.size(3)
         self._ensure(x.device)
-        eng = self.engine_for(x.size(0), x.size(2), x.size(3), self.training)
+        eng = self.engine_for(n, h, w, self.training)
         self._refresh_packs()
         if self.training and torch.is_grad_enabled():
             # A fresh leaf ties the node into the autograd graph.  (Using a long-lived Parameter here

@@ -40,6 +40,9 @@ class _Numerics:
     def __init__(self, emulate_bf16):
         self.emulate = emulate_bf16
         self.trace = None      # set to a list to record every block output (layer-wise parity)
+        # inference path of the CUDA engine: eval-mode BatchNorm rides in the conv epilogue, so the conv
+        # output is NOT rounded to bf16 before the affine (only after it) for the convs marked fold=True
+        self.fold_eval = True
 
     def rec(self, x):
         if self.trace is not None:
@@ -49,7 +52,7 @@ class _Numerics:
     def q(self, x):
         return _bf16(x) if self.emulate else x
 
-    def conv(self, m, x):
+    def conv(self, m, x, fold=False):
         if not self.emulate:
             return m(x)
         w = _bf16(m.weight)
@@ -57,6 +60,8 @@ class _Numerics:
             y = F.conv_transpose2d(x, w, m.bias, m.stride, m.padding, m.output_padding)
         else:
             y = F.conv2d(x, w, m.bias, m.stride, m.padding)
+        if fold and self.fold_eval and not m.training:
+            return y
         return _bf16(y)
 
     def bn(self, m, x):
@@ -102,9 +107,13 @@ class ResidualBlock(nn.Module):
         self.shortcut = nn.Sequential(shortcut_conv_in, nn.BatchNorm2d(chans))
 
     def run(self, nm, x, keep_fp32=False):
-        a = nm.q(F.relu(nm.bn(self.module[1], nm.conv(self.module[0], x))))
-        main = F.relu(nm.bn(self.module[4], nm.conv(self.module[3], a)))
-        short = nm.bn(self.shortcut[1], nm.conv(self.shortcut[0], x))
+        # folded inference (engine.py residual_block): not for the logits block, nor for a 1x1 transposed shortcut
+        fold = not keep_fp32 and not (isinstance(self.shortcut[0], nn.ConvTranspose2d))
+        a = nm.q(F.relu(nm.bn(self.module[1], nm.conv(self.module[0], x, fold))))
+        short = nm.bn(self.shortcut[1], nm.conv(self.shortcut[0], x, fold))
+        if fold and nm.emulate and nm.fold_eval and not self.training:
+            short = nm.q(short)        # the shortcut branch is stored before the main conv adds it
+        main = F.relu(nm.bn(self.module[4], nm.conv(self.module[3], a, fold)))
         out = main + short
         return nm.rec(out if keep_fp32 else nm.q(out))
 
@@ -185,10 +194,12 @@ class BasicBlock(nn.Module):
             self.downsample = None
 
     def run(self, nm, x):
-        a = nm.q(F.relu(nm.bn(self.bn1, nm.conv(self.conv1, x))))
-        main = nm.bn(self.bn2, nm.conv(self.conv2, a))
+        a = nm.q(F.relu(nm.bn(self.bn1, nm.conv(self.conv1, x, True))))
+        main = nm.bn(self.bn2, nm.conv(self.conv2, a, True))
         if self.downsample is not None:
-            ident = nm.bn(self.downsample[1], nm.conv(self.downsample[0], x))
+            ident = nm.bn(self.downsample[1], nm.conv(self.downsample[0], x, True))
+            if nm.emulate and nm.fold_eval and not self.training:
+                ident = nm.q(ident)
         else:
             ident = x
         return nm.rec(nm.q(F.relu(main + ident)))
@@ -214,11 +225,13 @@ class Bottleneck(nn.Module):
             self.downsample = None
 
     def run(self, nm, x):
-        a = nm.q(F.relu(nm.bn(self.bn1, nm.conv(self.conv1, x))))
-        b = nm.q(F.relu(nm.bn(self.bn2, nm.conv(self.conv2, a))))
-        main = nm.bn(self.bn3, nm.conv(self.conv3, b))
+        a = nm.q(F.relu(nm.bn(self.bn1, nm.conv(self.conv1, x, True))))
+        b = nm.q(F.relu(nm.bn(self.bn2, nm.conv(self.conv2, a, True))))
+        main = nm.bn(self.bn3, nm.conv(self.conv3, b, True))
         if self.downsample is not None:
-            ident = nm.bn(self.downsample[1], nm.conv(self.downsample[0], x))
+            ident = nm.bn(self.downsample[1], nm.conv(self.downsample[0], x, True))
+            if nm.emulate and nm.fold_eval and not self.training:
+                ident = nm.q(ident)
         else:
             ident = x
         return nm.rec(nm.q(F.relu(main + ident)))
@@ -267,14 +280,14 @@ def make_image_feature_extractor(model_name):
 
 def run_feature_extractor(nm, net, x):
     x = nm.q(x)
-    x = nm.rec(nm.q(F.relu(nm.bn(net[1], nm.conv(net[0], x)))))
+    x = nm.rec(nm.q(F.relu(nm.bn(net[1], nm.conv(net[0], x, True)))))
     x = nm.rec(net[3](x))
     for blk in net[4]:
         x = blk.run(nm, x)
     for blk in net[5]:
         x = blk.run(nm, x)
     if len(net) > 6:
-        x = nm.rec(nm.q(F.relu(nm.bn(net[7], nm.conv(net[6], x)))))
+        x = nm.rec(nm.q(F.relu(nm.bn(net[7], nm.conv(net[6], x, True)))))
     return x
 
 

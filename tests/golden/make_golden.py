@@ -1,6 +1,7 @@
 """Generates tests/golden/*.pt from the UNMODIFIED reference (run in the build container):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # margipose_golden.pt (tail + small models)
+    python tests/golden/make_golden.py large      # margipose_golden_large.pt (the benchmarked architectures)
 
 The vectors are produced by /root/reference code (through oracle/ref_shim.py); inputs and
 weights are reproducible from seeds with torch's CPU generator, so the GPU box -- which has
@@ -48,6 +49,14 @@ MODEL_CASES = [  # (name, weight seed, input seed, batch, desc settings)
     ('r18x1', 21, 22, 1, dict(n_stages=1, feature_extractor='resnet18')),
     ('r18x2', 23, 24, 2, dict(n_stages=2, feature_extractor='resnet18')),
     ('r34x1', 25, 26, 1, dict(n_stages=1, feature_extractor='resnet34')),
+]
+
+
+# The architectures bench.py measures (BASELINE.json configs[1] and configs[4]) at a batch the CPU reference
+# finishes in seconds: (name, weight seed, input seed, batch, resolution, desc settings)
+LARGE_CASES = [
+    ('r34x4', 51, 52, 4, 256, dict(n_stages=4, feature_extractor='resnet34')),
+    ('r50x5@384', 53, 54, 2, 384, dict(n_stages=5, feature_extractor='resnet50')),
 ]
 
 
@@ -105,14 +114,25 @@ def main():
         ))
     gold['tail'] = tails
 
+    gold['model'] = model_cases(ref, [c[:4] + (256,) + c[4:] for c in MODEL_CASES])
+    gold['joint_names'] = list(ref.CanonicalSkeletonDesc.joint_names)
+    gold['joint_tree'] = list(ref.CanonicalSkeletonDesc.joint_tree)
+    gold['hflip_indices'] = list(ref.CanonicalSkeletonDesc.hflip_indices)
+    out_path = os.path.join(HERE, 'margipose_golden.pt')
+    torch.save(gold, out_path)
+    print('wrote', out_path, os.path.getsize(out_path), 'bytes')
+
+
+def model_cases(ref, cases):
+    R = ref.dsntnn
     models = []
-    for name, wseed, iseed, batch, settings in MODEL_CASES:
+    for name, wseed, iseed, batch, res, settings in cases:
         desc = desc_of(settings)
         torch.manual_seed(wseed)
         om = M.create_oracle(desc)          # weights reproducible from the seed
         rm = ref.models.create_model(desc)  # the reference executes them
         rm.load_state_dict(om.state_dict())
-        x, target, mask = model_inputs(iseed, batch)
+        x, target, mask = model_inputs(iseed, batch, res)
         rm.train()
         out = rm(x)
         l3 = R.average_loss(rm.forward_3d_losses(out, target), mask)
@@ -130,7 +150,7 @@ def main():
         with torch.no_grad():
             out_eval = rm(x)
         models.append(dict(
-            name=name, desc=desc, weight_seed=wseed, input_seed=iseed, batch=batch,
+            name=name, desc=desc, weight_seed=wseed, input_seed=iseed, batch=batch, res=res,
             train_coords=out.detach(), loss3=l3.detach(), loss2=l2.detach(),
             **train_hm,
             grad_norms={k: g.norm() for k, g in grads.items()},
@@ -141,14 +161,20 @@ def main():
             n_params=sum(p.numel() for p in rm.parameters()),
             state_keys=list(sd.keys()),
         ))
-    gold['model'] = models
-    gold['joint_names'] = list(ref.CanonicalSkeletonDesc.joint_names)
-    gold['joint_tree'] = list(ref.CanonicalSkeletonDesc.joint_tree)
-    gold['hflip_indices'] = list(ref.CanonicalSkeletonDesc.hflip_indices)
-    out_path = os.path.join(HERE, 'margipose_golden.pt')
+        print('case', name, 'loss3', l3.item())
+    return models
+
+
+def main_large():
+    ref = load_reference()
+    gold = {'model': model_cases(ref, LARGE_CASES)}
+    out_path = os.path.join(HERE, 'margipose_golden_large.pt')
     torch.save(gold, out_path)
     print('wrote', out_path, os.path.getsize(out_path), 'bytes')
 
 
 if __name__ == '__main__':
-    main()
+    if 'large' in sys.argv[1:]:
+        main_large()
+    else:
+        main()

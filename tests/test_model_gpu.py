@@ -25,11 +25,15 @@ import torch
 
 from oracle import dsnt_oracle as D
 from oracle import model_oracle as M
+from tests.conftest import parity_log
 from tests.golden.make_golden import model_inputs
 
 pytestmark = pytest.mark.gpu
 GOLD = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'margipose_golden.pt'),
                   weights_only=False)
+# the architectures bench.py measures (4-stage ResNet-34 @256, 5-stage ResNet-50 @384), reference-generated
+LARGE = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'margipose_golden_large.pt'),
+                   weights_only=False)
 
 
 def rel(a, b):
@@ -53,21 +57,33 @@ def run_cuda(model, x, target, mask, loss='3d'):
     return out, l
 
 
-@pytest.mark.parametrize('case', GOLD['model'], ids=lambda c: c['name'])
+@pytest.mark.parametrize('case', GOLD['model'] + LARGE['model'], ids=lambda c: c['name'])
 def test_against_reference_golden(case):
     om, model = make_pair(case['desc'], case['weight_seed'], emulate=False)
     assert list(model.state_dict().keys()) == case['state_keys']
     assert sum(p.numel() for p in model.parameters()) == case['n_params']
-    x, target, mask = model_inputs(case['input_seed'], case['batch'])
+    x, target, mask = model_inputs(case['input_seed'], case['batch'], case.get('res', 256))
     out, l3 = run_cuda(model, x, target, mask)
+    log = 'golden/' + case['name']
+    parity_log(log, coords_max_abs_err=(out.detach().cpu() - case['train_coords']).abs().max(),
+               coords_mean_abs_err=(out.detach().cpu() - case['train_coords']).abs().mean(),
+               loss_rel_err=abs(l3.item() - case['loss3'].item()) / case['loss3'].item(),
+               loss=l3.item(), loss_reference=case['loss3'].item(),
+               tolerance='coords atol 0.1, loss rtol 5e-3 (bf16 storage vs the fp32 reference)')
     print(case['name'], 'coords max err', (out.cpu() - case['train_coords']).abs().max().item(),
           'loss', l3.item(), case['loss3'].item())
     torch.testing.assert_close(out.detach().cpu(), case['train_coords'], rtol=0, atol=0.1)
     torch.testing.assert_close(l3.detach().cpu(), case['loss3'], rtol=5e-3, atol=1e-3)
+    # row / column marginals of every stage's heatmaps; the 5-stage 384x384 case is one stage deeper and its rows
+    # hold more mass each (48 instead of 32 bins of a peaked distribution): atol 0.3 there
+    m_tol, m_err = (0.3 if case.get('res', 256) > 256 else 0.2), 0.0
     for t in range(len(model.xy_heatmaps)):
-        torch.testing.assert_close(model.xy_heatmaps[t].detach().sum(-1).cpu(), case['xy_rowsum'][t], rtol=0, atol=0.2)
-        torch.testing.assert_close(model.zy_heatmaps[t].detach().sum(-1).cpu(), case['zy_rowsum'][t], rtol=0, atol=0.2)
-        torch.testing.assert_close(model.xz_heatmaps[t].detach().sum(-2).cpu(), case['xz_colsum'][t], rtol=0, atol=0.2)
+        for got, want in ((model.xy_heatmaps[t].detach().sum(-1).cpu(), case['xy_rowsum'][t]),
+                          (model.zy_heatmaps[t].detach().sum(-1).cpu(), case['zy_rowsum'][t]),
+                          (model.xz_heatmaps[t].detach().sum(-2).cpu(), case['xz_colsum'][t])):
+            m_err = max(m_err, (got - want).abs().max().item())
+            torch.testing.assert_close(got, want, rtol=0, atol=m_tol)
+    parity_log(log, marginals_max_abs_err=m_err)
     l3.backward()
     # gradient norms against the fp32 reference: the total and every conv weight tensor (tiny tensors
     # such as BatchNorm biases deep in a chaotic net are dominated by the noise the docstring describes)
@@ -80,6 +96,8 @@ def test_against_reference_golden(case):
         if p.dim() == 4 and want > 1e-3:
             worst = max(worst, abs(got - want) / want)
     print(case['name'], 'worst conv-weight grad-norm rel err', worst, 'total', tot_got ** 0.5, tot_want ** 0.5)
+    parity_log(log, grad_total_norm_rel_err=abs(tot_got ** 0.5 - tot_want ** 0.5) / tot_want ** 0.5,
+               grad_worst_conv_weight_norm_rel_err=worst)
     assert abs(tot_got ** 0.5 - tot_want ** 0.5) / tot_want ** 0.5 < 0.25
     assert worst < 0.6
     sd = model.state_dict()
@@ -89,6 +107,7 @@ def test_against_reference_golden(case):
     _, l2 = run_cuda(model, x, target, mask, loss='2d')
     # second forward changed nothing but the BN buffers; the 2D loss of the same batch
     torch.testing.assert_close(l2.detach().cpu(), case['loss2'], rtol=5e-3, atol=1e-3)
+    parity_log(log, loss2d_rel_err=abs(l2.item() - case['loss2'].item()) / case['loss2'].item())
 
 
 SETTINGS = [
@@ -139,6 +158,10 @@ def test_against_bf16_oracle(name, settings, batch):
     cfloor = (out_p - out_o).abs().max().item()
     cerr = (out.detach().cpu() - out_o).abs().max().item()
     print(name, 'coords max err', cerr, 'floor', cfloor, 'loss', l.item(), lo.item(), lp.item())
+    parity_log('bf16_oracle/' + name, coords_max_abs_err=cerr, coords_floor_1e6_perturbation=cfloor,
+               loss_rel_err=abs(l.item() - lo.item()) / abs(lo.item()),
+               logits_rel_l2_last_stage=rel(eng.logits[-1][0].cpu(), logits_o[-1][0]),
+               logits_floor_last_stage=rel(logits_p[-1][0], logits_o[-1][0]))
     assert cerr < 2 * cfloor + 2e-3
     assert abs(l.item() - lo.item()) < 2 * abs(lp.item() - lo.item()) + 2e-3 * abs(lo.item())
     keys = list(grads_o.keys())
@@ -150,6 +173,7 @@ def test_against_bf16_oracle(name, settings, batch):
     cos_floor = torch.nn.functional.cosine_similarity(gp, go, 0).item()
     cos = torch.nn.functional.cosine_similarity(gc, go, 0).item()
     print(name, 'grad rel L2', gerr, 'floor', gfloor, 'cosine', cos, 'floor', cos_floor)
+    parity_log('bf16_oracle/' + name, grad_rel_l2=gerr, grad_floor=gfloor, grad_cosine=cos, grad_cosine_floor=cos_floor)
     assert gerr < 2 * gfloor + 1e-2
     assert 1 - cos < 2 * (1 - cos_floor) + 1e-3
     worst = 0.0
@@ -340,3 +364,136 @@ def test_full_size_properties_of_the_bench_workload():
             assert int(b) == counters0[k] + 1, k
     eng = model.engine_for(32, 256, 256, True)
     assert eng.group and eng.launches() < 900, 'the three columns of a stage should share grouped launches'
+
+
+def _warm_pair(desc, seed, batch, emulate=True):
+    """Oracle + CUDA model with running statistics := the statistics of one batch (momentum 1), in eval mode."""
+    om, model = make_pair(desc, seed, emulate=emulate)
+    for m in list(om.modules()) + list(model.modules()):
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.momentum = 1.0
+    x, target, mask = model_inputs(seed + 1, batch)
+    with torch.no_grad():
+        om(x)
+        model(x.cuda())
+    return om.eval(), model.eval(), x
+
+
+def test_inference_folded_batchnorm_graph_and_uint8_input(monkeypatch):
+    """Inference path (bin/infer_single.py:58-66): BatchNorm folded into the conv epilogues vs the unfolded
+    eval path and the oracle; InferStep's captured graph vs eager; uint8 NHWC input with the ImageNet
+    normalisation fused into the stem gather (data_specs.py:38-39) vs the normalised fp32 tensor."""
+    from margipose_b200.infer import InferStep
+    desc = {'type': 'margipose', 'version': '6.0.1',
+            'settings': dict(n_stages=2, feature_extractor='resnet18', axis_permutation=True, pixelwise_loss='jsd')}
+    om, model, x = _warm_pair(desc, 81, 3)
+    with torch.no_grad():
+        want = om(x)
+        folded = model(x.cuda()).clone()
+    eng = model.engine_for(3, 256, 256, False)
+    assert eng.fold
+    n_folded = eng.launches(eng.fwd)
+    monkeypatch.setenv('MARGIPOSE_B200_FOLD', '0')
+    model.drop_engines()
+    with torch.no_grad():
+        unfolded = model(x.cuda()).clone()
+    n_unfolded = model.engine_for(3, 256, 256, False).launches()
+    monkeypatch.setenv('MARGIPOSE_B200_FOLD', '1')
+    model.drop_engines()
+    print('eval coords: folded vs oracle %.3e, unfolded vs oracle %.3e, folded vs unfolded %.3e; launches %d vs %d'
+          % ((folded.cpu() - want).abs().max(), (unfolded.cpu() - want).abs().max(),
+             (folded - unfolded).abs().max(), n_folded, n_unfolded))
+    parity_log('inference/r18x2_folded_bn', coords_max_abs_err_vs_bf16_oracle=(folded.cpu() - want).abs().max(),
+               unfolded_coords_max_abs_err=(unfolded.cpu() - want).abs().max(),
+               folded_vs_unfolded=(folded - unfolded).abs().max(), launches_folded=n_folded,
+               launches_unfolded=n_unfolded, tolerance='atol 3e-2 vs the bf16-emulating oracle in eval mode')
+    assert n_folded < n_unfolded
+    torch.testing.assert_close(folded.cpu(), want, rtol=0, atol=3e-2)
+    torch.testing.assert_close(unfolded.cpu(), want, rtol=0, atol=3e-2)
+
+    # captured graph == eager, call after call
+    infer = InferStep(model, 3, warmup=1)
+    outs = [infer(x).clone() for _ in range(4)]
+    assert infer._graph is not None
+    for o in outs:
+        torch.testing.assert_close(o, folded, rtol=0, atol=0)
+    assert len(model.xy_heatmaps) == 2 and model.xy_heatmaps[-1].shape == (3, 17, 32, 32)
+
+    # uint8 NHWC pixels: (p / 255 - mean) / std inside the stem gather
+    g = torch.Generator().manual_seed(5)
+    img = torch.randint(0, 256, (3, 256, 256, 3), generator=g, dtype=torch.uint8)
+    specs = model.data_specs.input_specs
+    mean, std = torch.tensor(specs.mean).view(1, 3, 1, 1), torch.tensor(specs.stddev).view(1, 3, 1, 1)
+    norm = (img.permute(0, 3, 1, 2).float() / 255 - mean) / std
+    with torch.no_grad():
+        a = model(norm.cuda()).clone()
+        b = model(img.cuda()).clone()
+    infer8 = InferStep(model, 3, warmup=1, uint8=True)
+    c = [infer8(img).clone() for _ in range(3)][-1]
+    print('uint8 fused normalisation vs fp32 normalised input: %.3e' % (a - b).abs().max())
+    parity_log('inference/uint8_fused_normalisation', coords_max_abs_diff=(a - b).abs().max(),
+               tolerance='atol 2e-2 (one extra fp32 rounding before the bf16 store)')
+    torch.testing.assert_close(b, a, rtol=0, atol=2e-2)
+    torch.testing.assert_close(c, b, rtol=0, atol=0)
+
+
+def test_eval_weight_packs_follow_parameter_writes():
+    """eval forward, load_state_dict of different weights, eval forward -- the second forward
+    must use the new weights (the bf16 pack cache keys on the parameters' version counters)."""
+    from margipose_b200.models import create_model
+    desc = {'type': 'margipose', 'version': '6.0.1',
+            'settings': dict(n_stages=1, feature_extractor='resnet18')}
+    torch.manual_seed(91)
+    a, b = create_model(desc), create_model(desc)
+    sd_b = {k: v.clone() for k, v in b.state_dict().items()}
+    x, _t, _m = model_inputs(92, 2)
+    a.cuda().eval()
+    b.cuda().eval()
+    with torch.no_grad():
+        out_a = a(x.cuda()).clone()
+        a.load_state_dict(sd_b)
+        out_ab = a(x.cuda()).clone()
+        out_b = b(x.cuda()).clone()
+        assert not torch.equal(out_a, out_b)
+        torch.testing.assert_close(out_ab, out_b, rtol=0, atol=0)
+        # a stock torch optimiser writing through the nn.Parameters is seen as well
+        with torch.no_grad():
+            for p in a.parameters():
+                p.mul_(1.01)
+        out_scaled = a(x.cuda()).clone()
+    assert not torch.equal(out_scaled, out_b)
+
+
+def test_checkpoint_wire_format_roundtrip(tmp_path):
+    """bin/train_3d.py:374-382 saves {'state_dict', 'model_desc', 'train_datasets', 'optimizer', 'epoch'};
+    models/__init__.py:30-34 loads it.  Written by this package, read back by load_model (weights_only) and by
+    the oracle (whose module tree has the reference's key names)."""
+    from margipose_b200.models import create_model, load_model
+    from margipose_b200.optim import FlatSGD
+    desc = {'type': 'margipose', 'version': '6.0.1',
+            'settings': dict(n_stages=2, feature_extractor='resnet18', axis_permutation=True, pixelwise_loss='jsd')}
+    torch.manual_seed(95)
+    model = create_model(desc).cuda().train()
+    opt = FlatSGD(model, lr=1e-2, momentum=0.9)
+    x, target, mask = model_inputs(96, 2)
+    from margipose_b200 import dsntnn as K
+    for _ in range(2):
+        opt.zero_grad()
+        out = model(x.cuda())
+        K.average_loss(model.forward_3d_losses(out, target.cuda()), mask.cuda()).backward()
+        opt.step()
+    path = str(tmp_path / 'model-latest.pth')
+    torch.save({'state_dict': model.state_dict(), 'model_desc': desc, 'train_datasets': ['synthetic'],
+                'optimizer': opt.state_dict(), 'epoch': 1}, path)
+    loaded = load_model(path).cuda().eval()
+    model.eval()
+    with torch.no_grad():
+        torch.testing.assert_close(loaded(x.cuda()), model(x.cuda()), rtol=0, atol=0)
+    details = torch.load(path, map_location='cpu', weights_only=True)
+    om = M.create_oracle(details['model_desc'])
+    om.load_state_dict(details['state_dict'])
+    # the optimiser state survives too (momentum buffer + step count)
+    opt2 = FlatSGD(loaded.train(), lr=1e-2, momentum=0.9)
+    opt2.load_state_dict(details['optimizer'])
+    torch.testing.assert_close(opt2.momentum_buf, opt.momentum_buf, rtol=0, atol=0)
+    assert opt2._steps == opt._steps == 2
