@@ -175,6 +175,14 @@ typedef struct mp_igemm_args {
   const float* ep_scale;
   const float* ep_shift;
   int32_t ep_relu;
+  /* Split ("bf16x3") precision mode, lo_delta > 0: every activation VALUE is a pair of bf16 tensors, hi = bf16(v) and
+   * lo = bf16(v - hi) stored lo_delta ELEMENTS after hi (~16 significant bits; see DESIGN.md "Precision modes").
+   * out, res and acc_in are such pairs.  A convolution is then three launches over the same accumulator,
+   *   x_hi * W_hi,   x_lo * W_hi (acc_in = out),   x_hi * W_lo (acc_in = out; + res, statistics, affine)
+   * i.e. the epilogue computes  out = relu2?( relu1?((acc + acc_in) * scale + shift) + res )  on fp32 values and
+   * stores the pair.  The BatchNorm statistics are those of the stored pair sums.  lo_delta == 0: plain bf16. */
+  const void* acc_in;
+  int64_t lo_delta;
 } mp_igemm_args;
 
 MP_API int mp_conv_igemm(const mp_igemm_args* args, void* stream);
@@ -255,6 +263,8 @@ typedef struct mp_bn_args {
   int32_t C, Cp, HW;
   int32_t training;
   float momentum, eps;
+  int64_t lo_delta;         /* split (bf16x3) mode: every bf16 (M, Cp) tensor above is a hi / lo pair, lo stored lo_delta
+                               elements after hi (see mp_igemm_args.lo_delta); 0 = plain bf16 */
 } mp_bn_args;
 
 MP_API int mp_bn_fwd(const mp_bn_args* args, void* stream);
@@ -285,9 +295,14 @@ typedef struct mp_bn_fold_entry {
 } mp_bn_fold_entry;
 MP_API int mp_bn_fold_eval(const mp_bn_fold_entry* table, int n, void* stream);
 
-/* nn.MaxPool2d(3, 2, 1) of the ResNet stem on bf16 NHWC; idx (N, H/2, W/2, C) uint8 records the
+/* `lo_delta` of the entry points below: 0 = plain bf16 activations; > 0 = split (bf16x3) mode, every bf16 activation
+ * tensor argument is a hi / lo pair with lo stored lo_delta elements after hi (see mp_igemm_args.lo_delta).  The pure
+ * data movements (mp_maxpool_bwd, mp_axis_permute) are linear: call them once per half.
+ *
+ * nn.MaxPool2d(3, 2, 1) of the ResNet stem on bf16 NHWC; idx (N, H/2, W/2, C) uint8 records the
  * arg-max tap (first maximum in row-major window order, as ATen does) for the backward. */
-MP_API int mp_maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, void* stream);
+MP_API int mp_maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, int64_t lo_delta,
+                          void* stream);
 MP_API int mp_maxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int N, int H, int W, int C,
                           void* stream);
 
@@ -299,32 +314,33 @@ MP_API int mp_axis_permute(const void* in, void* out, int mode, int N, int S, in
 /* HeatmapCombiner (models/margipose_model.py:142-150) fused with the stage-input update (:195):
  * out[pix, c] = inp[pix, c] + sum_k sum_j w[c, k*J + j] * p_k[n, j, pix]; p_k fp32 (N, J, HW). */
 MP_API int mp_combiner_fwd(const float* const p[3], const float* w, const void* inp, void* out,
-                           int N, int J, int HW, int C, void* stream);
+                           int N, int J, int HW, int C, int64_t lo_delta, void* stream);
 /* d p_k (fp32 (N, J, HW); overwritten, or += when accumulate != 0) and d w (+=) from
  * d out (bf16 (N*HW, C)). */
 MP_API int mp_combiner_bwd(const void* dout, const float* const p[3], const float* w,
                            float* const dp[3], float* dw, int accumulate, int N, int J, int HW,
-                           int C, void* stream);
+                           int C, int64_t lo_delta, void* stream);
 
 /* ResNet stem conv1 (7x7, stride 2, padding 3, 3 input channels): gathers the fp32 NCHW image
  * into bf16 patch rows (N, H/2, W/2, 192) with k = (r*7 + s)*3 + c (147 real + zero padding), so
  * the conv and its weight gradient run as 1x1 cases of mp_conv_igemm / mp_conv_wgrad. */
-MP_API int mp_stem_im2col(const float* x, void* patches, int N, int H, int W, void* stream);
+MP_API int mp_stem_im2col(const float* x, void* patches, int N, int H, int W, int64_t lo_delta, void* stream);
 /* Same from a uint8 NHWC image (N, H, W, 3) with the reference's input step fused in: ImageSpecs.convert =
  * to_tensor (/255) + (x - mean) / stddev (data_specs.py:6-13,38-39; mean / stddev: HOST pointers to 3 floats,
  * ImageNet statistics for the MargiPose model, models/margipose_model.py:206-209). */
 MP_API int mp_stem_im2col_u8(const uint8_t* x, void* patches, const float mean[3], const float stddev[3],
-                             int N, int H, int W, void* stream);
+                             int N, int H, int W, int64_t lo_delta, void* stream);
 
 /* out = sum of n (<= 4) bf16 tensors of `count` elements (gradient fan-in). */
-MP_API int mp_add_bf16(const void* const in[4], int n, void* out, int64_t count, void* stream);
+MP_API int mp_add_bf16(const void* const in[4], int n, void* out, int64_t count, int64_t lo_delta, void* stream);
 
 /* fp32 master weights -> bf16 GEMM operands, one launch for the whole network.  `table` is a
  * DEVICE array of n_entries records sorted by work_off; dst elements beyond the source extent are
  * zero-filled.  Entry e fills the [rows_p][taps][cols_p] block
  *   packed[dst_off + r*dst_row_stride + t*cols_p + c] = transpose ? src[c][t][r] : src[r][t][c]
  * (src = master + src_off, fp32 [A][taps][B]); a row stride larger than taps*cols_p lets two layers
- * share one matrix along K (fused data gradient of a residual block). */
+ * share one matrix along K (fused data gradient of a residual block).  lo_delta > 0 (split mode): the rounding
+ * residual bf16(w - bf16(w)) of every element is written lo_delta elements after it (the W_lo operand). */
 typedef struct mp_pack_entry {
   int64_t src_off;         /* elements into `master` */
   int64_t dst_off;         /* elements into `packed` */
@@ -336,7 +352,7 @@ typedef struct mp_pack_entry {
   int32_t rows_p, cols_p;  /* padded destination extents (cols_p % 8 == 0) */
 } mp_pack_entry;
 MP_API int mp_pack_weights(const float* master, void* packed, const mp_pack_entry* table,
-                           int n_entries, int64_t total_work, void* stream);
+                           int n_entries, int64_t total_work, int64_t lo_delta, void* stream);
 
 /* torch.optim.SGD step over flat fp32 buffers (momentum buffer initialised on first_step):
  *   g = grad*grad_scale + wd*p;  buf = first ? g : mom*buf + (1-dampening)*g;

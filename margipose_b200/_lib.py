@@ -40,7 +40,8 @@ class IgemmArgs(ctypes.Structure):
                 ('bn', c_void_p), ('bn_counter', c_void_p), ('bn_launches', ctypes.c_int32),
                 ('bn_channels', ctypes.c_int32), ('bn_count', ctypes.c_int64),
                 ('bn_momentum', ctypes.c_float), ('bn_eps', ctypes.c_float),
-                ('ep_scale', c_void_p), ('ep_shift', c_void_p), ('ep_relu', ctypes.c_int32)]
+                ('ep_scale', c_void_p), ('ep_shift', c_void_p), ('ep_relu', ctypes.c_int32),
+                ('acc_in', c_void_p), ('lo_delta', ctypes.c_int64)]
 
 
 class WgradArgs(ctypes.Structure):
@@ -63,7 +64,7 @@ class BnArgs(ctypes.Structure):
                 ('stat_replicas', ctypes.c_int32), ('stat_stride', ctypes.c_int64),
                 ('M', ctypes.c_int64), ('C', ctypes.c_int32), ('Cp', ctypes.c_int32),
                 ('HW', ctypes.c_int32), ('training', ctypes.c_int32), ('momentum', ctypes.c_float),
-                ('eps', ctypes.c_float)]
+                ('eps', ctypes.c_float), ('lo_delta', ctypes.c_int64)]
 
 
 class BnFoldEntry(ctypes.Structure):
@@ -112,16 +113,16 @@ def _signatures():
         'mp_bn_fwd_grouped': (I, [ctypes.POINTER(BnArgs), I, P]),
         'mp_bn_bwd_reduce_grouped': (I, [ctypes.POINTER(BnArgs), I, P]),
         'mp_bn_bwd_apply_grouped': (I, [ctypes.POINTER(BnArgs), I, P]),
-        'mp_maxpool_fwd': (I, [P, P, P, I, I, I, I, P]),
+        'mp_maxpool_fwd': (I, [P, P, P, I, I, I, I, ctypes.c_int64, P]),
         'mp_maxpool_bwd': (I, [P, P, P, I, I, I, I, P]),
         'mp_axis_permute': (I, [P, P, I, I, I, I, I, P]),
-        'mp_combiner_fwd': (I, [PT, P, P, P, I, I, I, I, P]),
-        'mp_combiner_bwd': (I, [P, PT, P, PT, P, I, I, I, I, I, P]),
-        'mp_stem_im2col': (I, [P, P, I, I, I, P]),
+        'mp_combiner_fwd': (I, [PT, P, P, P, I, I, I, I, ctypes.c_int64, P]),
+        'mp_combiner_bwd': (I, [P, PT, P, PT, P, I, I, I, I, I, ctypes.c_int64, P]),
+        'mp_stem_im2col': (I, [P, P, I, I, I, ctypes.c_int64, P]),
         'mp_stem_im2col_u8': (I, [P, P, ctypes.POINTER(ctypes.c_float * 3), ctypes.POINTER(ctypes.c_float * 3),
-                                  I, I, I, P]),
-        'mp_add_bf16': (I, [ctypes.POINTER(c_void_p * 4), I, P, ctypes.c_int64, P]),
-        'mp_pack_weights': (I, [P, P, P, I, ctypes.c_int64, P]),
+                                  I, I, I, ctypes.c_int64, P]),
+        'mp_add_bf16': (I, [ctypes.POINTER(c_void_p * 4), I, P, ctypes.c_int64, ctypes.c_int64, P]),
+        'mp_pack_weights': (I, [P, P, P, I, ctypes.c_int64, ctypes.c_int64, P]),
         'mp_sgd_step': (I, [P, P, P, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                             ctypes.c_float, I, I, ctypes.c_float, P]),
         'mp_sgd_step_hp': (I, [P, P, P, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float,

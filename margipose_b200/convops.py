@@ -15,6 +15,11 @@ Conventions
                 [rows padded to 64][taps][K padded to 64]
 Supported: kernel 1 or 3 (padding k // 2), stride 1 or 2; transposed only with stride 2 and
 output_padding 1 -- everything the reference's columns and ResNet blocks use.
+
+Split ("bf16x3") precision mode: while a `SplitPairs` object is installed in `SPLIT`, every activation and
+every weight pack is a PAIR of bf16 tensors (hi = bf16(v), lo = bf16(v - hi), ~16 significant bits) and each
+convolution / weight gradient becomes three tensor-core passes -- hi*hi, lo*hi, hi*lo -- over one accumulator
+(DESIGN.md "Precision modes").  The geometry code below is unchanged by it.
 """
 import ctypes
 
@@ -25,6 +30,40 @@ from ._lib import (IgemmArgs, WgradArgs, View5, MP_MAX_TAPS, lib, check, stream_
 
 def pad64(c):
     return (c + 63) // 64 * 64
+
+
+class SplitPairs:
+    """hi tensor -> lo tensor registry of the split precision mode (keyed by device pointer)."""
+
+    def __init__(self):
+        self._lo = {}
+
+    def register(self, hi, lo):
+        assert hi.shape == lo.shape and hi.dtype == lo.dtype == torch.bfloat16
+        self._lo[hi.data_ptr()] = lo
+        return hi
+
+    def lo(self, hi):
+        return self._lo[hi.data_ptr()]
+
+    def delta(self, hi):
+        """Element offset from hi to lo (the C ABI's lo_delta)."""
+        lo = self._lo[hi.data_ptr()]
+        d = lo.data_ptr() - hi.data_ptr()
+        assert d > 0 and d % 16 == 0
+        return d // 2
+
+    def value(self, hi):
+        return hi.float() + self._lo[hi.data_ptr()].float()
+
+
+def split_bf16(v):
+    """fp32 tensor -> (hi, lo) bf16 pair."""
+    hi = v.to(torch.bfloat16)
+    return hi, (v - hi.float()).to(torch.bfloat16)
+
+
+SPLIT = None    # a SplitPairs while launches are to be issued in split precision mode
 
 
 def _view(t, parity=False):
@@ -113,11 +152,39 @@ def _fill_taps(args, taps):
 
 def _igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_c, res=None,
            stats=None, out_offset=0, bn=None, defer=None, ep=None):
+    """One convolution accumulation: a single launch, or -- split precision mode -- three passes
+    x_hi * W_hi, x_lo * W_hi, x_hi * W_lo chained through `acc_in`; residual, statistics, BatchNorm
+    finalize and epilogue affine belong to the last one."""
+    S = SPLIT
+    if S is None:
+        return _igemm_one(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_c, res=res,
+                          stats=stats, out_offset=out_offset, bn=bn, defer=defer, ep=ep)
+    common = (taps, cblocks, n_img, out_h, out_w, out, out_strides, out_c)
+    out_lo = S.lo(out)
+    res_lo = S.lo(res) if res is not None else None
+    # a residual that aliases the output (in-place accumulation) must be read before the first pass overwrites it
+    first = dict(res=res, res_lo=res_lo) if (res is not None and res.data_ptr() == out.data_ptr()) else {}
+    assert not (first and ep is not None), 'an in-place residual cannot be combined with an epilogue affine'
+    last = {} if first else dict(res=res, res_lo=res_lo)
+    flop_channels = _FLOP_CHANNELS[0]
+    _FLOP_CHANNELS[0] = 0          # algorithmic FLOPs are counted once, on the last pass
+    _igemm_one(srcs, wmat, *common, out_offset=out_offset, defer=defer, out_lo=out_lo, **first)
+    _igemm_one([(S.lo(t), par) for t, par in srcs], wmat, *common, out_offset=out_offset, defer=defer,
+               out_lo=out_lo, acc_in=out)
+    _FLOP_CHANNELS[0] = flop_channels
+    _igemm_one(srcs, S.lo(wmat), *common, stats=stats, out_offset=out_offset, bn=bn, defer=defer, ep=ep,
+               out_lo=out_lo, acc_in=out, **last)
+
+
+def _igemm_one(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_c, res=None,
+               stats=None, out_offset=0, bn=None, defer=None, ep=None, out_lo=None, acc_in=None, res_lo=None):
     """srcs: list of (tensor, parity) pairs; see mp_conv_igemm in include/margipose_b200.h.
     bn = dict(branch=BnBranch, counter=ptr, channels=C, count=M, momentum=, eps=): fuse the BatchNorm
     finalize into the launch(es); defer = list collecting the argument structs of a multi-launch
     conv so the caller can set the shared arrival total before launching.
-    ep = (scale ptr, shift ptr, relu mode): per-channel affine + ReLU in the epilogue (eval-mode BatchNorm)."""
+    ep = (scale ptr, shift ptr, relu mode): per-channel affine + ReLU in the epilogue (eval-mode BatchNorm).
+    out_lo (split mode): low half of the output pair; acc_in: output pair (hi tensor) of the earlier passes;
+    res_lo: low half of the residual pair."""
     a = IgemmArgs()
     for i, (t, parity) in enumerate(srcs):
         a.src[i] = _view(t, parity)
@@ -142,6 +209,12 @@ def _igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out
         a.bn_launches = 1
     if ep is not None:
         a.ep_scale, a.ep_shift, a.ep_relu = ep
+    if out_lo is not None:
+        a.lo_delta = (out_lo.data_ptr() - out.data_ptr()) // 2
+        assert a.lo_delta > 0 and (res is None or res_lo.data_ptr() - res.data_ptr() == 2 * a.lo_delta), \
+            'the halves of every activation pair must be the same distance apart'
+        if acc_in is not None:
+            a.acc_in = acc_in.data_ptr() + 2 * out_offset
     if defer is not None:
         defer.append((a, out.device))
     else:
@@ -163,6 +236,19 @@ def _wgrad_launch(a, device):
 
 
 def _wgrad(a_t, b_t, b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, grid_h, grid_w, dw):
+    """One weight gradient: a single accumulation, or -- split precision mode -- a_hi*b_hi + a_lo*b_hi +
+    a_hi*b_lo accumulated into the same fp32 gradient."""
+    S = SPLIT
+    rest = (b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, grid_h, grid_w, dw)
+    if S is None:
+        return _wgrad_one(a_t, b_t, *rest)
+    _wgrad_one(a_t, b_t, *rest)
+    _wgrad_one(S.lo(a_t), b_t, *rest, count_flops=False)
+    _wgrad_one(a_t, S.lo(b_t), *rest, count_flops=False)
+
+
+def _wgrad_one(a_t, b_t, b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, grid_h, grid_w, dw,
+               count_flops=True):
     """See mp_conv_wgrad in include/margipose_b200.h; wide b operands go in 256-channel slices."""
     for n_off in range(0, n_cols, 256):
         a = WgradArgs()
@@ -173,7 +259,8 @@ def _wgrad(a_t, b_t, b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, gri
         a.n_cols, a.n_off = min(256, n_cols - n_off), n_off
         a.n_img, a.grid_h, a.grid_w = n_img, grid_h, grid_w
         a.dw = dw.data_ptr()
-        a._flops = 2.0 * n_img * grid_h * grid_w * len(taps) * m_real * min(a.n_cols, n_real - n_off)
+        a._flops = 2.0 * n_img * grid_h * grid_w * len(taps) * m_real * min(a.n_cols, n_real - n_off) \
+            if count_flops else 0.0
         if n_off < n_real:
             _wgrad_launch(a, dw.device)
 
@@ -241,8 +328,10 @@ def _scatter_up(k, src, wpack, k_stride, cb, n, h, w, out, c_out_p, stats, res, 
             _igemm(srcs, wpack, taps, cb, n, h, w, out, strides, c_out_p, res=res, stats=stats,
                    out_offset=(ph * wo + pw) * c_out_p, bn=bn, defer=pending, ep=ep)
     if pending:   # the BatchNorm statistics are complete when the CTAs of ALL parity classes have arrived
+        n_bn = sum(1 for a, _dev in pending if a.bn)
         for a, dev in pending:
-            a.bn_launches = len(pending)
+            if a.bn:
+                a.bn_launches = n_bn
             _igemm_launch(a, dev)
 
 

@@ -36,6 +36,46 @@ __device__ __forceinline__ uint4 ldg16(const void* base, long long elem_off) {
   return __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off));
 }
 
+// An 8-channel group of an activation tensor: one 128-bit load (plain bf16) or two (split mode: value = hi + lo,
+// lo stored lo_delta elements after hi).
+template <bool SPLIT>
+struct Act8 {
+  uint4 hi;
+};
+template <>
+struct Act8<true> {
+  uint4 hi, lo;
+};
+template <bool SPLIT>
+__device__ __forceinline__ Act8<SPLIT> ld_act(const void* base, long long off, long long lo_delta) {
+  Act8<SPLIT> a;
+  a.hi = ldg16(base, off);
+  if constexpr (SPLIT) a.lo = ldg16(base, off + lo_delta);
+  return a;
+}
+template <bool SPLIT>
+__device__ __forceinline__ void act_unpack(const Act8<SPLIT>& a, float (&v)[8]) {
+  unpack8(a.hi, v);
+  if constexpr (SPLIT) {
+    float t[8];
+    unpack8(a.lo, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += t[j];
+  }
+}
+template <bool SPLIT>
+__device__ __forceinline__ void st_act(void* base, long long off, long long lo_delta, const float (&v)[8]) {
+  const uint4 hi = pack8(v);
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off) = hi;
+  if constexpr (SPLIT) {
+    float h[8], r[8];
+    unpack8(hi, h);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = v[j] - h[j];
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + off + lo_delta) = pack8(r);
+  }
+}
+
 constexpr int MAXR = 8;   // replicas summed with all loads in flight (more fall back to a loop)
 
 // Sum over replicas of 8 consecutive channels of a per-channel statistic: 2 x 128-bit loads per
@@ -123,6 +163,7 @@ __device__ __forceinline__ void affine(const mp_bn_args& A, const mp_bn_branch& 
 }
 
 // ------------------------------------------------------------------------------------- forward
+template <bool SPLIT>
 __global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const __grid_constant__ BnGroup GRP) {
   pdl_trigger();
   pdl_wait();
@@ -158,19 +199,19 @@ __global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const __grid_constant__
 
   const long long ppb = (long long)blockDim.y * U;
   const long long stride = (long long)gridDim.x * ppb;
-  auto load = [&](long long p0, uint4 (&la)[U], uint4 (&lb)[U]) {
+  auto load = [&](long long p0, Act8<SPLIT> (&la)[U], Act8<SPLIT> (&lb)[U]) {
 #pragma unroll
     for (int i = 0; i < U; ++i) {
       const long long pix = p0 + (long long)i * blockDim.y;
       if (pix < A.M) {
         const long long off = pix * A.Cp + c0;
-        la[i] = ldg16(A.a.y, off);
-        if (has_b) lb[i] = ldg16(A.b.y, off);
-        else if (A.res) lb[i] = ldg16(A.res, off);
+        la[i] = ld_act<SPLIT>(A.a.y, off, A.lo_delta);
+        if (has_b) lb[i] = ld_act<SPLIT>(A.b.y, off, A.lo_delta);
+        else if (A.res) lb[i] = ld_act<SPLIT>(A.res, off, A.lo_delta);
       }
     }
   };
-  uint4 la[U], lb[U], na[U], nb[U];
+  Act8<SPLIT> la[U], lb[U], na[U], nb[U];
   long long base = (long long)blockIdx.x * ppb;
   if (base < A.M) load(base + threadIdx.y, la, lb);
   for (; base < A.M; base += stride) {
@@ -182,18 +223,18 @@ __global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const __grid_constant__
       if (pix >= A.M) break;
       const long long off = pix * A.Cp + c0;
       float z[8], t[8];
-      unpack8(la[i], z);
+      act_unpack<SPLIT>(la[i], z);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         z[j] = fmaf(z[j], sa[j], ha[j]);
         if (A.relu_a) z[j] = fmaxf(z[j], 0.f);
       }
       if (has_b) {
-        unpack8(lb[i], t);
+        act_unpack<SPLIT>(lb[i], t);
 #pragma unroll
         for (int j = 0; j < 8; ++j) z[j] += fmaf(t[j], sb[j], hb[j]);
       } else if (A.res) {
-        unpack8(lb[i], t);
+        act_unpack<SPLIT>(lb[i], t);
 #pragma unroll
         for (int j = 0; j < 8; ++j) z[j] += t[j];
       }
@@ -202,7 +243,7 @@ __global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const __grid_constant__
         if (A.relu_out) z[j] = fmaxf(z[j], 0.f);
         if (c0 + j >= A.C) z[j] = 0.f;
       }
-      if (A.out) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.out) + off) = pack8(z);
+      if (A.out) st_act<SPLIT>(A.out, off, A.lo_delta, z);
       if (A.out_nchw) {
         const long long n = pix / A.HW, hw = pix - n * A.HW;
 #pragma unroll
@@ -220,44 +261,47 @@ __global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const __grid_constant__
 // branch a, by the pre-ReLU (bn_a(y_a) > 0, recomputed with the forward's exact coefficients).
 // NCHW = the incoming gradient is the fp32 (N, C, HW) logits gradient (last block of a column);
 // its 8 channel values then travel in the two 128-bit slots g / g2 instead of one bf16x8 load.
+template <bool SPLIT>
 struct Loads {
-  uint4 g, o, ya, yb;
+  Act8<SPLIT> g, ya, yb;   // NCHW: g.hi carries the first four fp32 gradient values, g2 the other four
+  uint4 o;                 // forward output, read for the sign of the post-ReLU only (hi decides it)
 };
-template <bool NCHW>
-struct LoadsX : Loads {};
-template <>
-struct LoadsX<true> : Loads {
+template <bool NCHW, bool SPLIT>
+struct LoadsX : Loads<SPLIT> {};
+template <bool SPLIT>
+struct LoadsX<true, SPLIT> : Loads<SPLIT> {
   uint4 g2;
 };
 
-template <bool NCHW>
-__device__ __forceinline__ void load_pixel(const mp_bn_args& A, bool has_b, long long pix, int c0, LoadsX<NCHW>& L) {
+template <bool NCHW, bool SPLIT>
+__device__ __forceinline__ void load_pixel(const mp_bn_args& A, bool has_b, long long pix, int c0,
+                                           LoadsX<NCHW, SPLIT>& L) {
   const long long off = pix * A.Cp + c0;
   if constexpr (!NCHW) {
-    L.g = ldg16(A.dout, off);
+    L.g = ld_act<SPLIT>(A.dout, off, A.lo_delta);
   } else {
     const long long n = pix / A.HW, hw = pix - n * A.HW;
     float gn[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) gn[j] = (c0 + j < A.C) ? __ldg(A.dout_nchw + (n * A.C + c0 + j) * A.HW + hw) : 0.f;
-    L.g = make_uint4(__float_as_uint(gn[0]), __float_as_uint(gn[1]), __float_as_uint(gn[2]), __float_as_uint(gn[3]));
+    L.g.hi = make_uint4(__float_as_uint(gn[0]), __float_as_uint(gn[1]), __float_as_uint(gn[2]), __float_as_uint(gn[3]));
     L.g2 = make_uint4(__float_as_uint(gn[4]), __float_as_uint(gn[5]), __float_as_uint(gn[6]), __float_as_uint(gn[7]));
   }
   if (A.relu_out) L.o = ldg16(A.out, off);
-  L.ya = ldg16(A.a.y, off);
-  if (has_b) L.yb = ldg16(A.b.y, off);
+  L.ya = ld_act<SPLIT>(A.a.y, off, A.lo_delta);
+  if (has_b) L.yb = ld_act<SPLIT>(A.b.y, off, A.lo_delta);
 }
 
-template <bool NCHW>
-__device__ __forceinline__ void grads_at(const mp_bn_args& A, const LoadsX<NCHW>& L, const float (&sa)[8],
+template <bool NCHW, bool SPLIT>
+__device__ __forceinline__ void grads_at(const mp_bn_args& A, const LoadsX<NCHW, SPLIT>& L, const float (&sa)[8],
                                          const float (&ha)[8], int c0, float (&dza)[8], float (&dzb)[8],
                                          float (&ya)[8]) {
   float g[8];
   if constexpr (!NCHW) {
-    unpack8(L.g, g);
+    act_unpack<SPLIT>(L.g, g);
   } else {
-    g[0] = __uint_as_float(L.g.x); g[1] = __uint_as_float(L.g.y); g[2] = __uint_as_float(L.g.z);
-    g[3] = __uint_as_float(L.g.w); g[4] = __uint_as_float(L.g2.x); g[5] = __uint_as_float(L.g2.y);
+    g[0] = __uint_as_float(L.g.hi.x); g[1] = __uint_as_float(L.g.hi.y); g[2] = __uint_as_float(L.g.hi.z);
+    g[3] = __uint_as_float(L.g.hi.w); g[4] = __uint_as_float(L.g2.x); g[5] = __uint_as_float(L.g2.y);
     g[6] = __uint_as_float(L.g2.z); g[7] = __uint_as_float(L.g2.w);
   }
   if (A.relu_out) {
@@ -267,7 +311,7 @@ __device__ __forceinline__ void grads_at(const mp_bn_args& A, const LoadsX<NCHW>
     for (int j = 0; j < 8; ++j)
       if (!(o[j] > 0.f)) g[j] = 0.f;
   }
-  unpack8(L.ya, ya);
+  act_unpack<SPLIT>(L.ya, ya);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (c0 + j >= A.C) g[j] = 0.f;
@@ -277,7 +321,7 @@ __device__ __forceinline__ void grads_at(const mp_bn_args& A, const LoadsX<NCHW>
 }
 
 // sums layout per replica: [0] sum dz_a, [1] sum dz_a * y_a, [2] sum dz_b, [3] sum dz_b * y_b
-template <bool NCHW>
+template <bool NCHW, bool SPLIT>
 __global__ void __launch_bounds__(MAXT, 2) bn_bwd_reduce_kernel(const __grid_constant__ BnGroup GRP) {
   pdl_trigger();
   pdl_wait();
@@ -293,14 +337,14 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_reduce_kernel(const __grid_con
 
   const long long ppb = (long long)blockDim.y * U;
   const long long stride = (long long)gridDim.x * ppb;
-  auto load = [&](long long p0, LoadsX<NCHW> (&L)[U]) {
+  auto load = [&](long long p0, LoadsX<NCHW, SPLIT> (&L)[U]) {
 #pragma unroll
     for (int i = 0; i < U; ++i) {
       const long long pix = p0 + (long long)i * blockDim.y;
-      if (pix < A.M) load_pixel<NCHW>(A, has_b, pix, c0, L[i]);
+      if (pix < A.M) load_pixel<NCHW, SPLIT>(A, has_b, pix, c0, L[i]);
     }
   };
-  LoadsX<NCHW> L[U], Ln[U];
+  LoadsX<NCHW, SPLIT> L[U], Ln[U];
   long long base = (long long)blockIdx.x * ppb;
   if (base < A.M) load(base + threadIdx.y, L);
   for (; base < A.M; base += stride) {
@@ -311,14 +355,14 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_reduce_kernel(const __grid_con
       const long long pix = p0 + (long long)i * blockDim.y;
       if (pix >= A.M) break;
       float dza[8], dzb[8], ya[8], yb[8];
-      grads_at<NCHW>(A, L[i], sa, ha, c0, dza, dzb, ya);
+      grads_at<NCHW, SPLIT>(A, L[i], sa, ha, c0, dza, dzb, ya);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         acc[j] += dza[j];
         acc[8 + j] = fmaf(dza[j], ya[j], acc[8 + j]);
       }
       if (has_b) {
-        unpack8(L[i].yb, yb);
+        act_unpack<SPLIT>(L[i].yb, yb);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           acc[16 + j] += dzb[j];
@@ -403,7 +447,7 @@ __device__ __forceinline__ void bwd_coefs(const mp_bn_args& A, const mp_bn_branc
   }
 }
 
-template <bool NCHW>
+template <bool NCHW, bool SPLIT>
 __global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_kernel(const __grid_constant__ BnGroup GRP) {
   pdl_trigger();
   pdl_wait();
@@ -428,14 +472,14 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_kernel(const __grid_cons
 
   const long long ppb = (long long)blockDim.y * UA;
   const long long stride = (long long)gridDim.x * ppb;
-  auto load = [&](long long p0, LoadsX<NCHW> (&L)[UA]) {
+  auto load = [&](long long p0, LoadsX<NCHW, SPLIT> (&L)[UA]) {
 #pragma unroll
     for (int i = 0; i < UA; ++i) {
       const long long pix = p0 + (long long)i * blockDim.y;
-      if (pix < A.M) load_pixel<NCHW>(A, has_b, pix, c0, L[i]);
+      if (pix < A.M) load_pixel<NCHW, SPLIT>(A, has_b, pix, c0, L[i]);
     }
   };
-  LoadsX<NCHW> L[UA], Ln[UA];
+  LoadsX<NCHW, SPLIT> L[UA], Ln[UA];
   long long base = (long long)blockIdx.x * ppb;
   if (base < A.M) load(base + threadIdx.y, L);
   for (; base < A.M; base += stride) {
@@ -447,18 +491,18 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_kernel(const __grid_cons
       if (pix >= A.M) break;
       const long long off = pix * A.Cp + c0;
       float dza[8], dzb[8], ya[8], o[8];
-      grads_at<NCHW>(A, L[i], sa, ha, c0, dza, dzb, ya);
+      grads_at<NCHW, SPLIT>(A, L[i], sa, ha, c0, dza, dzb, ya);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (c0 + j < A.C) ? fmaf(sa[j], dza[j], fmaf(ka[j], ya[j], ca[j])) : 0.f;
-      if (A.a.dy) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.a.dy) + off) = pack8(o);
+      if (A.a.dy) st_act<SPLIT>(A.a.dy, off, A.lo_delta, o);
       if (has_b) {
         float yb[8];
-        unpack8(L[i].yb, yb);
+        act_unpack<SPLIT>(L[i].yb, yb);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = (c0 + j < A.C) ? fmaf(sb[j], dzb[j], fmaf(kb[j], yb[j], cb[j])) : 0.f;
-        if (A.b.dy) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.b.dy) + off) = pack8(o);
+        if (A.b.dy) st_act<SPLIT>(A.b.dy, off, A.lo_delta, o);
       } else if (A.dres) {
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(A.dres) + off) = pack8(dzb);
+        st_act<SPLIT>(A.dres, off, A.lo_delta, dzb);
       }
     }
 #pragma unroll
@@ -512,6 +556,7 @@ int check_args(const mp_bn_args* a, const char* what, bool bwd) {
                  "%s: the fused coefficient finalize needs coef buffers and un-replicated sums", what);
   }
   MP_CHECK_ARG(!(a->out_nchw || a->dout_nchw) || a->HW > 0, "%s: HW missing", what);
+  MP_CHECK_ARG(a->lo_delta >= 0 && a->lo_delta % 8 == 0, "%s: lo_delta must be a non-negative multiple of 8", what);
   return MP_OK;
 }
 
@@ -533,6 +578,7 @@ void launch_dims(const mp_bn_args* a, dim3* grid, dim3* block, int u, int cap) {
 static bool same_shape(const mp_bn_args* x, const mp_bn_args* y) {
   return x->M == y->M && x->C == y->C && x->Cp == y->Cp && x->HW == y->HW && x->training == y->training &&
          x->relu_a == y->relu_a && x->relu_out == y->relu_out && x->stat_replicas == y->stat_replicas &&
+         x->lo_delta == y->lo_delta &&
          (x->b.y == nullptr) == (y->b.y == nullptr) && (x->res == nullptr) == (y->res == nullptr) &&
          (x->dout == nullptr) == (y->dout == nullptr) && (x->out_nchw == nullptr) == (y->out_nchw == nullptr);
 }
@@ -569,7 +615,8 @@ int mp_bn_fwd_grouped(const mp_bn_args* args, int n, void* stream) {
   dim3 grid, block;
   launch_dims(args, &grid, &block, U, 2 * 148 / n);
   grid.y = n;
-  MP_CUDA(mp_launch(bn_fwd_kernel, grid, block, 0, (cudaStream_t)stream, g));
+  if (args->lo_delta) MP_CUDA(mp_launch(bn_fwd_kernel<true>, grid, block, 0, (cudaStream_t)stream, g));
+  else MP_CUDA(mp_launch(bn_fwd_kernel<false>, grid, block, 0, (cudaStream_t)stream, g));
   MP_CHECK_LAUNCH("mp_bn_fwd");
   return MP_OK;
 }
@@ -581,8 +628,11 @@ int mp_bn_bwd_reduce_grouped(const mp_bn_args* args, int n, void* stream) {
   dim3 grid, block;
   launch_dims(args, &grid, &block, U, n > 1 ? 2 * 148 / n : 148);
   grid.y = n;
-  if (args->dout) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<false>, grid, block, 0, (cudaStream_t)stream, g));
-  else MP_CUDA(mp_launch(bn_bwd_reduce_kernel<true>, grid, block, 0, (cudaStream_t)stream, g));
+  const bool split = args->lo_delta != 0;
+  if (args->dout && split) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<false, true>, grid, block, 0, (cudaStream_t)stream, g));
+  else if (args->dout) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<false, false>, grid, block, 0, (cudaStream_t)stream, g));
+  else if (split) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<true, true>, grid, block, 0, (cudaStream_t)stream, g));
+  else MP_CUDA(mp_launch(bn_bwd_reduce_kernel<true, false>, grid, block, 0, (cudaStream_t)stream, g));
   MP_CHECK_LAUNCH("mp_bn_bwd_reduce");
   return MP_OK;
 }
@@ -594,8 +644,11 @@ int mp_bn_bwd_apply_grouped(const mp_bn_args* args, int n, void* stream) {
   dim3 grid, block;
   launch_dims(args, &grid, &block, UA, 2 * 148 / n);
   grid.y = n;
-  if (args->dout) MP_CUDA(mp_launch(bn_bwd_apply_kernel<false>, grid, block, 0, (cudaStream_t)stream, g));
-  else MP_CUDA(mp_launch(bn_bwd_apply_kernel<true>, grid, block, 0, (cudaStream_t)stream, g));
+  const bool split = args->lo_delta != 0;
+  if (args->dout && split) MP_CUDA(mp_launch(bn_bwd_apply_kernel<false, true>, grid, block, 0, (cudaStream_t)stream, g));
+  else if (args->dout) MP_CUDA(mp_launch(bn_bwd_apply_kernel<false, false>, grid, block, 0, (cudaStream_t)stream, g));
+  else if (split) MP_CUDA(mp_launch(bn_bwd_apply_kernel<true, true>, grid, block, 0, (cudaStream_t)stream, g));
+  else MP_CUDA(mp_launch(bn_bwd_apply_kernel<true, false>, grid, block, 0, (cudaStream_t)stream, g));
   MP_CHECK_LAUNCH("mp_bn_bwd_apply");
   return MP_OK;
 }

@@ -86,3 +86,32 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+
+// 8 consecutive channels of an activation tensor as fp32.  lo_delta == 0: plain bf16.  lo_delta > 0 (split / "bf16x3"
+// mode): the value is the sum of two bf16 tensors, hi at p and lo at p + lo_delta (hi = bf16(v), lo = bf16(v - hi)).
+__device__ __forceinline__ void mp_ld8(const __nv_bfloat16* p, long long lo_delta, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+  if (lo_delta) {
+    const uint4 l = __ldg(reinterpret_cast<const uint4*>(p + lo_delta));
+    f = unpack_bf16x2(l.x); v[0] += f.x; v[1] += f.y;
+    f = unpack_bf16x2(l.y); v[2] += f.x; v[3] += f.y;
+    f = unpack_bf16x2(l.z); v[4] += f.x; v[5] += f.y;
+    f = unpack_bf16x2(l.w); v[6] += f.x; v[7] += f.y;
+  }
+}
+__device__ __forceinline__ void mp_st8(__nv_bfloat16* p, long long lo_delta, const float (&v)[8]) {
+  const uint4 hi = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                              pack_bf16x2(v[6], v[7]));
+  *reinterpret_cast<uint4*>(p) = hi;
+  if (lo_delta) {
+    const float2 a = unpack_bf16x2(hi.x), b = unpack_bf16x2(hi.y), c = unpack_bf16x2(hi.z), d = unpack_bf16x2(hi.w);
+    *reinterpret_cast<uint4*>(p + lo_delta) =
+        make_uint4(pack_bf16x2(v[0] - a.x, v[1] - a.y), pack_bf16x2(v[2] - b.x, v[3] - b.y),
+                   pack_bf16x2(v[4] - c.x, v[5] - c.y), pack_bf16x2(v[6] - d.x, v[7] - d.y));
+  }
+}

@@ -13,7 +13,7 @@ void mp_set_error(const char* fmt, ...) {
 }
 
 extern "C" {
-int mp_abi_version(void) { return 3; }   // 3: epilogue affine (ep_*), mp_bn_fold_eval, deterministic mode, hyper[5]
+int mp_abi_version(void) { return 4; }   // 4: split (bf16x3) mode (lo_delta, acc_in), epilogue affine, mp_bn_fold_eval, mp_stem_im2col_u8, hyper[5]
 const char* mp_last_error(void) { return g_err; }
 }
 

@@ -76,6 +76,7 @@ struct IgemmParams {
   struct Problem {
     __nv_bfloat16* out;
     const __nv_bfloat16* res;
+    const __nv_bfloat16* acc_in;   // split mode: partial sum of the earlier launches (added before affine / ReLU)
     float* stat_sum;
     float* stat_sq;
     // BatchNorm finalize by the last CTA (see mp_igemm_args.bn)
@@ -86,6 +87,7 @@ struct IgemmParams {
     const float* ep_scale; const float* ep_shift;
   } q[MP_MAX_GROUP];
   int ep_relu;   // 0 = none, 1 = ReLU before the residual add, 2 = ReLU after it
+  long long lo_delta;   // split (bf16x3) mode: out / res / acc_in are value pairs hi + lo, lo at +lo_delta elements
   int fin_total, fin_C, fin_Cp;
   long long fin_count;
   float fin_momentum, fin_eps;
@@ -115,7 +117,24 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& P, int t) {
   return c;
 }
 
-template <bool PAIR, bool AFFINE>
+// v[0..31] += 32 consecutive bf16 channels at p (only the 8-channel groups below out_c)
+__device__ __forceinline__ void add_tile32(float (&v)[32], const __nv_bfloat16* p, int ch, int out_c) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (ch + i * 8 < out_c) {
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p + i * 8));
+      const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(rr[j]);
+        v[i * 8 + j * 2] += f.x;
+        v[i * 8 + j * 2 + 1] += f.y;
+      }
+    }
+  }
+}
+
+template <bool PAIR, bool AFFINE, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS)
 igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ IgemmParams P) {
   const CUtensorMap& tmA0 = TM.a0[blockIdx.z];
@@ -326,6 +345,10 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
           float v[32];
           tc::tmem_ld32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * P.n_tile + c * 32), v);
           if (!valid) continue;
+          if (SPLIT && Q.acc_in) {   // the products of the other operand halves, accumulated by the earlier launches
+            add_tile32(v, Q.acc_in + pix + ch, ch, P.out_c);
+            add_tile32(v, Q.acc_in + pix + ch + P.lo_delta, ch, P.out_c);
+          }
           if (AFFINE) {   // y = relu?(acc * scale[c] + shift[c]): warp-uniform addresses, 128-bit broadcast loads
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -342,19 +365,8 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
             }
           }
           if (Q.res) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (ch + i * 8 < P.out_c) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(Q.res + pix + ch + i * 8));
-                const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f = unpack_bf16x2(rr[j]);
-                  v[i * 8 + j * 2] += f.x;
-                  v[i * 8 + j * 2 + 1] += f.y;
-                }
-              }
-            }
+            add_tile32(v, Q.res + pix + ch, ch, P.out_c);
+            if (SPLIT) add_tile32(v, Q.res + pix + ch + P.lo_delta, ch, P.out_c);
           }
           if (AFFINE && P.ep_relu == 2) {
 #pragma unroll
@@ -369,10 +381,28 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
               *reinterpret_cast<uint4*>(Q.out + pix + ch + i * 8) =
                   make_uint4(packed[i * 4], packed[i * 4 + 1], packed[i * 4 + 2], packed[i * 4 + 3]);
           }
-          if (Q.stat_sum) {   // statistics of the values as stored (bf16-rounded)
+          if (SPLIT) {   // second bf16 of the pair: what the first rounding lost (value = hi + lo, ~16 significant bits)
+            uint32_t plo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float2 f = unpack_bf16x2(packed[j]);
+              plo[j] = pack_bf16x2(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+              const float2 g = unpack_bf16x2(plo[j]);
+              v[2 * j] = f.x + g.x;           // the value as stored, for the statistics below
+              v[2 * j + 1] = f.y + g.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (ch + i * 8 < P.out_c)
+                *reinterpret_cast<uint4*>(Q.out + pix + ch + i * 8 + P.lo_delta) =
+                    make_uint4(plo[i * 4], plo[i * 4 + 1], plo[i * 4 + 2], plo[i * 4 + 3]);
+            }
+          }
+          if (Q.stat_sum) {   // statistics of the values as stored (bf16-rounded; split mode: hi + lo)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float2 f = unpack_bf16x2(packed[j]);
+              if (SPLIT) f = make_float2(v[2 * j], v[2 * j + 1]);
               s1[2 * j] += f.x; s1[2 * j + 1] += f.y;
               s2[2 * j] = fmaf(f.x, f.x, s2[2 * j]); s2[2 * j + 1] = fmaf(f.y, f.y, s2[2 * j + 1]);
             }
@@ -627,6 +657,7 @@ static bool same_geometry(const mp_igemm_args* x, const mp_igemm_args* y) {
       (x->res == nullptr) != (y->res == nullptr) || (x->stat_sum == nullptr) != (y->stat_sum == nullptr) ||
       (x->bn == nullptr) != (y->bn == nullptr) || x->stat_replicas != y->stat_replicas ||
       (x->ep_scale == nullptr) != (y->ep_scale == nullptr) || x->ep_relu != y->ep_relu ||
+      (x->acc_in == nullptr) != (y->acc_in == nullptr) || x->lo_delta != y->lo_delta ||
       x->stat_stride != y->stat_stride || !same_view(x->src[0], y->src[0]) ||
       (x->src[1].ptr == nullptr) != (y->src[1].ptr == nullptr) || (x->src[1].ptr && !same_view(x->src[1], y->src[1])))
     return false;
@@ -733,6 +764,9 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
   P.stat_replicas = a->stat_replicas > 1 ? a->stat_replicas : 1;
   P.stat_stride = a->stat_stride;
   P.ep_relu = a->ep_relu;
+  P.lo_delta = a->lo_delta;
+  MP_CHECK_ARG(a->lo_delta >= 0 && a->lo_delta % 8 == 0, "mp_conv_igemm: lo_delta must be a non-negative multiple of 8");
+  MP_CHECK_ARG(a->lo_delta > 0 || a->acc_in == nullptr, "mp_conv_igemm: acc_in needs split mode (lo_delta > 0)");
   MP_CHECK_ARG(a->ep_relu >= 0 && a->ep_relu <= 2, "mp_conv_igemm: ep_relu %d out of range", a->ep_relu);
   P.fin_total = 0; P.fin_C = 0; P.fin_Cp = 0; P.fin_count = 0; P.fin_momentum = 0.f; P.fin_eps = 0.f;
   if (a->bn) {
@@ -758,6 +792,7 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
     IgemmParams::Problem& Q = P.q[i];
     Q.out = reinterpret_cast<__nv_bfloat16*>(x->out);
     Q.res = reinterpret_cast<const __nv_bfloat16*>(x->res);
+    Q.acc_in = reinterpret_cast<const __nv_bfloat16*>(x->acc_in);
     Q.stat_sum = x->stat_sum;
     Q.stat_sq = x->stat_sq;
     Q.fin_gamma = Q.fin_beta = Q.fin_bias = nullptr;
@@ -802,10 +837,13 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
   const size_t smem = (size_t)a_stages * P.a_slot_bytes + (size_t)b_stages * P.b_slot_bytes + overhead;
   MP_CHECK_ARG(smem <= 227 * 1024, "mp_conv_igemm: %zu bytes of shared memory needed", smem);
   if (!g_attr_set) {
-    MP_CUDA(cudaFuncSetAttribute(igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    MP_CUDA(cudaFuncSetAttribute(igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    MP_CUDA(cudaFuncSetAttribute(igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    MP_CUDA(cudaFuncSetAttribute(igemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define MP_IGEMM_ATTR(P_, A_, S_) \
+    MP_CUDA(cudaFuncSetAttribute(igemm_kernel<P_, A_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024))
+    MP_IGEMM_ATTR(false, false, false); MP_IGEMM_ATTR(true, false, false);
+    MP_IGEMM_ATTR(false, true, false); MP_IGEMM_ATTR(true, true, false);
+    MP_IGEMM_ATTR(false, false, true); MP_IGEMM_ATTR(true, false, true);
+    MP_IGEMM_ATTR(false, true, true); MP_IGEMM_ATTR(true, true, true);
+#undef MP_IGEMM_ATTR
     g_attr_set = true;
   }
   dim3 grid((unsigned)(workers * (pair ? 2 : 1)), 1, (unsigned)n_problems);
@@ -825,10 +863,20 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
   cfg.numAttrs = mp_pdl_enabled() ? 2 : 1;
   const bool affine = a->ep_scale != nullptr;
   MP_CHECK_ARG(affine || a->ep_relu == 0, "mp_conv_igemm: ep_relu needs ep_scale / ep_shift");
-  if (pair && affine) MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<true, true>, TM, P));
-  else if (pair) MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<true, false>, TM, P));
-  else if (affine) MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<false, true>, TM, P));
-  else MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<false, false>, TM, P));
+  const bool split = a->lo_delta > 0;
+#define MP_IGEMM_GO(P_, A_, S_) MP_CUDA(cudaLaunchKernelEx(&cfg, igemm_kernel<P_, A_, S_>, TM, P))
+  if (split) {
+    if (pair && affine) MP_IGEMM_GO(true, true, true);
+    else if (pair) MP_IGEMM_GO(true, false, true);
+    else if (affine) MP_IGEMM_GO(false, true, true);
+    else MP_IGEMM_GO(false, false, true);
+  } else {
+    if (pair && affine) MP_IGEMM_GO(true, true, false);
+    else if (pair) MP_IGEMM_GO(true, false, false);
+    else if (affine) MP_IGEMM_GO(false, true, false);
+    else MP_IGEMM_GO(false, false, false);
+  }
+#undef MP_IGEMM_GO
   MP_CHECK_LAUNCH("mp_conv_igemm");
   return MP_OK;
 }

@@ -24,7 +24,7 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
 
 // ------------------------------------------------------------------ maxpool 3x3 / stride 2 / pad 1
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                   uint8_t* __restrict__ idx, int N, int H, int W, int C) {
+                                   uint8_t* __restrict__ idx, int N, int H, int W, int C, long long lo_delta) {
   pdl_trigger();
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2, G = C / 8;
@@ -47,14 +47,14 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
       const int w = 2 * wo + s - 1;
       if (w < 0 || w >= W) continue;
       float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + g * 8)), v);
+      mp_ld8(x + (((long long)n * H + h) * W + w) * C + g * 8, lo_delta, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         if (v[j] > best[j] || v[j] != v[j]) { best[j] = v[j]; arg[j] = r * 3 + s; }
     }
   }
   const long long o = (((long long)n * Ho + ho) * Wo + wo) * C + g * 8;
-  *reinterpret_cast<uint4*>(y + o) = pack8(best);
+  mp_st8(y + o, lo_delta, best);
   uint2 a;
   a.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
   a.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
@@ -136,7 +136,8 @@ constexpr int CT_PIX = 64;
 __global__ void __launch_bounds__(256) combiner_fwd_tiled_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
                                                                const float* __restrict__ p2, const float* __restrict__ w,
                                                                const __nv_bfloat16* __restrict__ inp,
-                                                               __nv_bfloat16* __restrict__ out, int J, int HW, int C) {
+                                                               __nv_bfloat16* __restrict__ out, int J, int HW, int C,
+                                                               long long lo_delta) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) float smt[];
@@ -178,11 +179,11 @@ __global__ void __launch_bounds__(256) combiner_fwd_tiled_kernel(const float* __
     if (px >= HW) break;
     const long long o = ((long long)n * HW + px) * C + g * 8;
     float base[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(inp + o)), base);
+    mp_ld8(inp + o, lo_delta, base);
     // fp32 weights, fp32 probabilities, fp32 accumulate; the new stage input is rounded to bf16 once
 #pragma unroll
     for (int j = 0; j < 8; ++j) base[j] += acc[i][j];
-    *reinterpret_cast<uint4*>(out + o) = pack8(base);
+    mp_st8(out + o, lo_delta, base);
   }
 }
 
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(256) combiner_bwd_tiled_kernel(const __nv_bflo
                                                                const float* __restrict__ p2, const float* __restrict__ w,
                                                                float* __restrict__ dp0, float* __restrict__ dp1,
                                                                float* __restrict__ dp2, float* __restrict__ dw,
-                                                               int accumulate, int J, int HW, int C) {
+                                                               int accumulate, int J, int HW, int C, long long lo_delta) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) float smt[];
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(256) combiner_bwd_tiled_kernel(const __nv_bflo
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = 0.f;
-      if (pix0 + px < HW) unpack8(__ldg(reinterpret_cast<const uint4*>(dout + ((long long)n * HW + pix0 + px) * C + g * 8)), v);
+      if (pix0 + px < HW) mp_ld8(dout + ((long long)n * HW + pix0 + px) * C + g * 8, lo_delta, v);
       *reinterpret_cast<float4*>(sdT + px * CS + g * 8) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(sdT + px * CS + g * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
@@ -300,7 +301,8 @@ constexpr int CMB_PIX = 32;
 __global__ void __launch_bounds__(256) combiner_fwd_kernel(const float* __restrict__ p0, const float* __restrict__ p1,
                                                          const float* __restrict__ p2, const float* __restrict__ w,
                                                          const __nv_bfloat16* __restrict__ inp,
-                                                         __nv_bfloat16* __restrict__ out, int J, int HW, int C) {
+                                                         __nv_bfloat16* __restrict__ out, int J, int HW, int C,
+                                                         long long lo_delta) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
@@ -331,11 +333,11 @@ __global__ void __launch_bounds__(256) combiner_fwd_kernel(const float* __restri
     }
     const long long o = ((long long)n * HW + pix0 + px) * C + g * 8;
     float base[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(inp + o)), base);
+    mp_ld8(inp + o, lo_delta, base);
     // fp32 weights, fp32 probabilities, fp32 accumulate; the new stage input is rounded to bf16 once
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = base[j] + acc[j];
-    *reinterpret_cast<uint4*>(out + o) = pack8(acc);
+    mp_st8(out + o, lo_delta, acc);
   }
 }
 
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(256) combiner_bwd_kernel(const __nv_bfloat16* 
                                                          const float* __restrict__ p2, const float* __restrict__ w,
                                                          float* __restrict__ dp0, float* __restrict__ dp1,
                                                          float* __restrict__ dp2, float* __restrict__ dw,
-                                                         int accumulate, int J, int HW, int C) {
+                                                         int accumulate, int J, int HW, int C, long long lo_delta) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
@@ -368,8 +370,13 @@ __global__ void __launch_bounds__(256) combiner_bwd_kernel(const __nv_bfloat16* 
     __syncthreads();
     for (int i = threadIdx.x; i < CMB_PIX * C; i += blockDim.x) {
       const int px = i / C, c = i - px * C;
-      sd[px * (C + 1) + c] =
-          (pix0 + px < HW) ? __bfloat162float(dout[((long long)n * HW + pix0 + px) * C + c]) : 0.f;
+      float dv = 0.f;
+      if (pix0 + px < HW) {
+        const long long o = ((long long)n * HW + pix0 + px) * C + c;
+        dv = __bfloat162float(dout[o]);
+        if (lo_delta) dv += __bfloat162float(dout[o + lo_delta]);
+      }
+      sd[px * (C + 1) + c] = dv;
     }
     for (int i = threadIdx.x; i < K * CMB_PIX; i += blockDim.x) {
       const int k = i / CMB_PIX, px = i - k * CMB_PIX;
@@ -408,7 +415,7 @@ __global__ void __launch_bounds__(256) combiner_bwd_kernel(const __nv_bfloat16* 
 // -------------------------------------------------------------------------------- stem im2col
 // patches[n, ho, wo, (r*7+s)*3 + c] = x[n, c, 2*ho + r - 3, 2*wo + s - 3]; 192 columns per row.
 __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
-                                   int W) {
+                                   int W, long long lo_delta) {
   pdl_trigger();
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
@@ -435,14 +442,14 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* _
     }
     v[j] = val;
   }
-  *reinterpret_cast<uint4*>(out + (((long long)n * Ho + ho) * Wo + wo) * 192 + g * 8) = pack8(v);
+  mp_st8(out + (((long long)n * Ho + ho) * Wo + wo) * 192 + g * 8, lo_delta, v);
 }
 
 // Same gather from a uint8 NHWC image (what an image decoder produces) with the input step of the reference fused
 // in: to_tensor (/255) and ImageNet normalisation (x - mean) / std (data_specs.py:6-13,38-39).  Padding taps are
 // zeros of the NORMALISED tensor, as the conv's zero padding sees them.
 __global__ void stem_im2col_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
-                                      int W, float3 scale, float3 shift) {
+                                      int W, float3 scale, float3 shift, long long lo_delta) {
   pdl_trigger();
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
@@ -470,33 +477,35 @@ __global__ void stem_im2col_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat
     }
     v[j] = val;
   }
-  *reinterpret_cast<uint4*>(out + (((long long)n * Ho + ho) * Wo + wo) * 192 + g * 8) = pack8(v);
+  mp_st8(out + (((long long)n * Ho + ho) * Wo + wo) * 192 + g * 8, lo_delta, v);
 }
 
 // -------------------------------------------------------------------------------------- add_n
 __global__ void add_bf16_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, const __nv_bfloat16* c,
-                                const __nv_bfloat16* d, int n, __nv_bfloat16* out, long long groups) {
+                                const __nv_bfloat16* d, int n, __nv_bfloat16* out, long long groups,
+                                long long lo_delta) {
   pdl_trigger();
   pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= groups) return;
   float acc[8], v[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(a) + i), acc);
+  mp_ld8(a + i * 8, lo_delta, acc);
   const __nv_bfloat16* rest[3] = {b, c, d};
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     if (k + 1 < n) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(rest[k]) + i), v);
+      mp_ld8(rest[k] + i * 8, lo_delta, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += v[j];
     }
   }
-  reinterpret_cast<uint4*>(out)[i] = pack8(acc);
+  mp_st8(out + i * 8, lo_delta, acc);
 }
 
 // ------------------------------------------------------------------------------- weight packing
 __global__ void pack_weights_kernel(const float* __restrict__ master, __nv_bfloat16* __restrict__ packed,
-                                    const mp_pack_entry* __restrict__ table, int n_entries, long long groups) {
+                                    const mp_pack_entry* __restrict__ table, int n_entries, long long groups,
+                                    long long lo_delta) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= groups) return;
   const long long e0 = i * 8;   // first work element of this thread's 8
@@ -532,8 +541,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ master, __nv_bfloa
     }
     v[j] = val;
   }
-  *reinterpret_cast<uint4*>(packed + E.dst_off + (long long)r * E.dst_row_stride + (long long)t * E.cols_p + c0) =
-      pack8(v);
+  mp_st8(packed + E.dst_off + (long long)r * E.dst_row_stride + (long long)t * E.cols_p + c0, lo_delta, v);
 }
 
 // ------------------------------------------------------------------------------------------ SGD
@@ -582,12 +590,16 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
 
 extern "C" {
 
-int mp_maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, void* stream) {
+#define MP_CHECK_DELTA(what) \
+  MP_CHECK_ARG(lo_delta >= 0 && lo_delta % 8 == 0, what ": lo_delta must be a non-negative multiple of 8")
+
+int mp_maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, int64_t lo_delta, void* stream) {
+  MP_CHECK_DELTA("mp_maxpool_fwd");
   MP_CHECK_ARG(x && y && idx && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0,
                "mp_maxpool_fwd: bad arguments");
   const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
   MP_CUDA(mp_launch(maxpool_fwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, idx, N, H, W, C));
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, idx, N, H, W, C, (long long)lo_delta));
   MP_CHECK_LAUNCH("mp_maxpool_fwd");
   return MP_OK;
 }
@@ -612,7 +624,8 @@ int mp_axis_permute(const void* in, void* out, int mode, int N, int S, int C, in
 }
 
 int mp_combiner_fwd(const float* const p[3], const float* w, const void* inp, void* out, int N, int J, int HW,
-                    int C, void* stream) {
+                    int C, int64_t lo_delta, void* stream) {
+  MP_CHECK_DELTA("mp_combiner_fwd");
   MP_CHECK_ARG(p && p[0] && p[1] && p[2] && w && inp && out && N > 0 && J > 0 && HW > 0 && C % 8 == 0,
                "mp_combiner_fwd: bad arguments");
   if (C <= 128 && 3 * J <= 64 && 256 % (C / 8) == 0) {   // register-tiled kernel (the MargiPose shape: C = 128, J = 17)
@@ -624,7 +637,7 @@ int mp_combiner_fwd(const float* const p[3], const float* w, const void* inp, vo
     }
     dim3 grid_t((HW + CT_PIX - 1) / CT_PIX, N);
     MP_CUDA(mp_launch(combiner_fwd_tiled_kernel, grid_t, dim3(256), smem_t, (cudaStream_t)stream, p[0], p[1], p[2], w,
-                      (const __nv_bfloat16*)inp, (__nv_bfloat16*)out, J, HW, C));
+                      (const __nv_bfloat16*)inp, (__nv_bfloat16*)out, J, HW, C, (long long)lo_delta));
     MP_CHECK_LAUNCH("mp_combiner_fwd");
     return MP_OK;
   }
@@ -632,13 +645,14 @@ int mp_combiner_fwd(const float* const p[3], const float* w, const void* inp, vo
   MP_CHECK_ARG(smem <= 48 * 1024, "mp_combiner_fwd: J*C too large");
   dim3 grid((HW + CMB_PIX - 1) / CMB_PIX, N);
   MP_CUDA(mp_launch(combiner_fwd_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, p[0], p[1], p[2], w, (const __nv_bfloat16*)inp,
-                                                                 (__nv_bfloat16*)out, J, HW, C));
+                                                                 (__nv_bfloat16*)out, J, HW, C, (long long)lo_delta));
   MP_CHECK_LAUNCH("mp_combiner_fwd");
   return MP_OK;
 }
 
 int mp_combiner_bwd(const void* dout, const float* const p[3], const float* w, float* const dp[3], float* dw,
-                    int accumulate, int N, int J, int HW, int C, void* stream) {
+                    int accumulate, int N, int J, int HW, int C, int64_t lo_delta, void* stream) {
+  MP_CHECK_DELTA("mp_combiner_bwd");
   MP_CHECK_ARG(dout && p && p[0] && p[1] && p[2] && w && dp && dp[0] && dp[1] && dp[2] && dw && N > 0 && J > 0 &&
                    HW > 0 && C > 0,
                "mp_combiner_bwd: bad arguments");
@@ -652,7 +666,8 @@ int mp_combiner_bwd(const void* dout, const float* const p[3], const float* w, f
     }
     dim3 grid_t((HW + CT_PIX * CT_TILES - 1) / (CT_PIX * CT_TILES), N);
     MP_CUDA(mp_launch(combiner_bwd_tiled_kernel, grid_t, dim3(256), smem_t, (cudaStream_t)stream,
-                      (const __nv_bfloat16*)dout, p[0], p[1], p[2], w, dp[0], dp[1], dp[2], dw, accumulate, J, HW, C));
+                      (const __nv_bfloat16*)dout, p[0], p[1], p[2], w, dp[0], dp[1], dp[2], dw, accumulate, J, HW, C,
+                      (long long)lo_delta));
     MP_CHECK_LAUNCH("mp_combiner_bwd");
     return MP_OK;
   }
@@ -665,22 +680,25 @@ int mp_combiner_bwd(const void* dout, const float* const p[3], const float* w, f
   }
   dim3 grid((HW + CMB_PIX * CMB_TILES - 1) / (CMB_PIX * CMB_TILES), N);
   MP_CUDA(mp_launch(combiner_bwd_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const __nv_bfloat16*)dout, p[0], p[1], p[2], w,
-                                                                 dp[0], dp[1], dp[2], dw, accumulate, J, HW, C));
+                                                                 dp[0], dp[1], dp[2], dw, accumulate, J, HW, C,
+                                                                 (long long)lo_delta));
   MP_CHECK_LAUNCH("mp_combiner_bwd");
   return MP_OK;
 }
 
-int mp_stem_im2col(const float* x, void* patches, int N, int H, int W, void* stream) {
+int mp_stem_im2col(const float* x, void* patches, int N, int H, int W, int64_t lo_delta, void* stream) {
+  MP_CHECK_DELTA("mp_stem_im2col");
   MP_CHECK_ARG(x && patches && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "mp_stem_im2col: bad arguments");
   const long long total = (long long)N * (H / 2) * (W / 2) * 24;
   MP_CUDA(mp_launch(stem_im2col_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
-      x, (__nv_bfloat16*)patches, N, H, W));
+      x, (__nv_bfloat16*)patches, N, H, W, (long long)lo_delta));
   MP_CHECK_LAUNCH("mp_stem_im2col");
   return MP_OK;
 }
 
 int mp_stem_im2col_u8(const uint8_t* x, void* patches, const float mean[3], const float stddev[3], int N, int H, int W,
-                      void* stream) {
+                      int64_t lo_delta, void* stream) {
+  MP_CHECK_DELTA("mp_stem_im2col_u8");
   MP_CHECK_ARG(x && patches && mean && stddev && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0,
                "mp_stem_im2col_u8: bad arguments");
   MP_CHECK_ARG(stddev[0] > 0.f && stddev[1] > 0.f && stddev[2] > 0.f, "mp_stem_im2col_u8: stddev must be positive");
@@ -689,30 +707,32 @@ int mp_stem_im2col_u8(const uint8_t* x, void* patches, const float mean[3], cons
   const float3 scale = make_float3(1.f / (255.f * stddev[0]), 1.f / (255.f * stddev[1]), 1.f / (255.f * stddev[2]));
   const float3 shift = make_float3(-mean[0] / stddev[0], -mean[1] / stddev[1], -mean[2] / stddev[2]);
   MP_CUDA(mp_launch(stem_im2col_u8_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
-      x, (__nv_bfloat16*)patches, N, H, W, scale, shift));
+      x, (__nv_bfloat16*)patches, N, H, W, scale, shift, (long long)lo_delta));
   MP_CHECK_LAUNCH("mp_stem_im2col_u8");
   return MP_OK;
 }
 
-int mp_add_bf16(const void* const in[4], int n, void* out, int64_t count, void* stream) {
+int mp_add_bf16(const void* const in[4], int n, void* out, int64_t count, int64_t lo_delta, void* stream) {
+  MP_CHECK_DELTA("mp_add_bf16");
   MP_CHECK_ARG(in && out && n >= 1 && n <= 4 && count > 0 && count % 8 == 0, "mp_add_bf16: bad arguments");
   for (int i = 0; i < n; ++i) MP_CHECK_ARG(in[i] && mp_aligned16(in[i]), "mp_add_bf16: bad input %d", i);
   const long long groups = count / 8;
   MP_CUDA(mp_launch(add_bf16_kernel, dim3((unsigned)((groups + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)in[0], (const __nv_bfloat16*)(n > 1 ? in[1] : nullptr),
       (const __nv_bfloat16*)(n > 2 ? in[2] : nullptr), (const __nv_bfloat16*)(n > 3 ? in[3] : nullptr), n,
-      (__nv_bfloat16*)out, groups));
+      (__nv_bfloat16*)out, groups, (long long)lo_delta));
   MP_CHECK_LAUNCH("mp_add_bf16");
   return MP_OK;
 }
 
 int mp_pack_weights(const float* master, void* packed, const mp_pack_entry* table, int n_entries,
-                    int64_t total_work, void* stream) {
+                    int64_t total_work, int64_t lo_delta, void* stream) {
+  MP_CHECK_DELTA("mp_pack_weights");
   MP_CHECK_ARG(master && packed && table && n_entries > 0 && total_work > 0 && total_work % 8 == 0,
                "mp_pack_weights: bad arguments");
   const long long groups = total_work / 8;
   pack_weights_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      master, (__nv_bfloat16*)packed, table, n_entries, groups);
+      master, (__nv_bfloat16*)packed, table, n_entries, groups, (long long)lo_delta);
   MP_CHECK_LAUNCH("mp_pack_weights");
   return MP_OK;
 }

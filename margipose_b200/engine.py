@@ -47,7 +47,9 @@ class _Slot:
 class ParamBank:
     """Flat storage for parameters, gradients, BatchNorm buffers and bf16 weight packs."""
 
-    def __init__(self):
+    def __init__(self, split=False):
+        self.split = bool(split)       # bf16x3 precision mode: every weight pack has a low half (W_lo)
+        self.pairs = C.SplitPairs() if split else None
         self.params, self.buffers, self.counters = [], [], []
         self.n_param = self.n_buffer = 0
         self.pack_entries = []          # dicts; turned into a device table by finalize()
@@ -110,7 +112,9 @@ class ParamBank:
         self.flat_grad = torch.zeros_like(self.flat)
         self.flat_buf = torch.zeros(max(self.n_buffer, 8), device=device)
         self.flat_cnt = torch.zeros(max(len(self.counters), 1), dtype=torch.int64, device=device)
-        self.packs = torch.zeros(max(self.n_pack, 8), dtype=torch.bfloat16, device=device)
+        n_pack = (max(self.n_pack, 8) + 7) // 8 * 8
+        self.packs = torch.zeros((2 if self.split else 1) * n_pack, dtype=torch.bfloat16, device=device)
+        self.pack_lo_delta = n_pack if self.split else 0
         for s in self.params:
             p = getattr(s.mod, s.name)
             s.data = self.flat[s.off:s.off + s.numel]
@@ -149,6 +153,9 @@ class ParamBank:
         self.pack_table = raw.to(device)
         for m in self._mats:
             m.t = self.packs[m.off:m.off + m.rows * m.k].view(m.rows, m.k)
+            if self.split:
+                lo = self.pack_lo_delta + m.off
+                self.pairs.register(m.t, self.packs[lo:lo + m.rows * m.k].view(m.rows, m.k))
         self.device = device
 
     def linked(self):
@@ -170,8 +177,8 @@ class ParamBank:
         if not self.pack_entries:
             return
         check(lib().mp_pack_weights(self.flat.data_ptr(), self.packs.data_ptr(), self.pack_table.data_ptr(),
-                                    len(self.pack_entries), self.n_work, stream_ptr(self.device)),
-              'mp_pack_weights')
+                                    len(self.pack_entries), self.n_work, self.pack_lo_delta,
+                                    stream_ptr(self.device)), 'mp_pack_weights')
 
     def attach_grads(self):
         """Makes p.grad a view of the flat gradient buffer; zeroes the buffer when the caller has
@@ -328,6 +335,15 @@ class Engine:
         self.bank, self.L = model._bank, model._layers
         self._bufs = []
         self._keep = []
+        # split (bf16x3) precision mode: every activation is a hi / lo pair of bf16 tensors a FIXED distance
+        # apart (lo_delta elements), carved from chunks [hi half | lo half]
+        self.split = self.bank.split
+        self.pairs = self.bank.pairs
+        self.lo_delta = 0
+        self._chunk = None
+        self._chunk_used = 0
+        if self.split:
+            self.lo_delta = int(os.environ.get('MARGIPOSE_B200_SPLIT_CHUNK', str(1 << 29)))   # elements (1 GiB)
         # one grouped launch per layer for the three columns of a stage (default) or three stream lanes
         self.group = os.environ.get('MARGIPOSE_B200_GROUP', '1') != '0'
         self.streams = [torch.cuda.Stream(device=device) for _ in range(3)]
@@ -366,9 +382,28 @@ class Engine:
             self._build_fold_table()
 
     def act(self, n, h, w, c, dtype=torch.bfloat16):
-        t = torch.zeros(n, h, w, c, dtype=dtype, device=self.device)
-        self._bufs.append(t)
-        return t
+        if not self.split:
+            t = torch.zeros(n, h, w, c, dtype=dtype, device=self.device)
+            self._bufs.append(t)
+            return t
+        numel = (n * h * w * c + 7) // 8 * 8
+        half = self.lo_delta
+        if numel > half:
+            raise MargiposeB200Error('an activation of %d elements does not fit a split-mode chunk of %d; raise '
+                                     'MARGIPOSE_B200_SPLIT_CHUNK or lower the batch size' % (numel, half))
+        if self._chunk is None or self._chunk_used + numel > half:
+            self._chunk = torch.zeros(2 * half, dtype=dtype, device=self.device)
+            self._chunk_used = 0
+            self._bufs.append(self._chunk)
+        off = self._chunk_used
+        self._chunk_used += numel
+        hi = self._chunk[off:off + n * h * w * c].view(n, h, w, c)
+        lo = self._chunk[half + off:half + off + n * h * w * c].view(n, h, w, c)
+        return self.pairs.register(hi, lo)
+
+    def value(self, t):
+        """fp32 value of an activation buffer (hi + lo in split mode)."""
+        return self.pairs.value(t) if self.split and t.dtype == torch.bfloat16 else t.float()
 
     def activation_bytes(self):
         return sum(t.numel() * t.element_size() for t in self._bufs)
@@ -394,10 +429,12 @@ class Engine:
         old_i, old_w = C._igemm_launch, C._wgrad_launch
         C._igemm_launch = lambda a, dev: captured.append(self._launch('mp_conv_igemm', a))
         C._wgrad_launch = lambda a, dev: captured.append(self._launch('mp_conv_wgrad', a))
+        old_split, C.SPLIT = C.SPLIT, self.pairs
         try:
             record()
         finally:
             C._igemm_launch, C._wgrad_launch = old_i, old_w
+            C.SPLIT = old_split
         return captured
 
     # C-ABI entry points with a grouped variant (<name>_grouped(args[], n, stream))
@@ -521,7 +558,7 @@ class Engine:
 
         def op():
             rc = fn(d_next.data_ptr(), pp, wc.data.data_ptr(), gp, wc.grad.data_ptr(),
-                    0 if self._fused else 1, n, J, hw, cf, stream_ptr(dev))
+                    0 if self._fused else 1, n, J, hw, cf, self.lo_delta, stream_ptr(dev))
             if rc != 0:
                 check(rc, 'mp_combiner_bwd')
         op.name = 'mp_combiner_bwd'
@@ -539,9 +576,9 @@ class Engine:
         def op():
             if self._u8:
                 rc = fn8(self.x_u8.data_ptr(), patches.data_ptr(), ctypes.byref(mean), ctypes.byref(std), n, h, w,
-                         stream_ptr(dev))
+                         self.lo_delta, stream_ptr(dev))
             else:
-                rc = fn(self.x_in.data_ptr(), patches.data_ptr(), n, h, w, stream_ptr(dev))
+                rc = fn(self.x_in.data_ptr(), patches.data_ptr(), n, h, w, self.lo_delta, stream_ptr(dev))
             if rc != 0:
                 check(rc, 'mp_stem_im2col')
         op.name = 'mp_stem_im2col'
@@ -551,6 +588,13 @@ class Engine:
     def _on_aux(ops):
         for op in ops:
             op.aux = True
+        return ops
+
+    def _moves(self, fn_name, src, dst, *argv):
+        """A pure data movement (src, dst, ...): linear, so the split mode runs it once per half of the pair."""
+        ops = [self._call(fn_name, src.data_ptr(), dst.data_ptr(), *argv)]
+        if self.split:
+            ops.append(self._call(fn_name, self.pairs.lo(src).data_ptr(), self.pairs.lo(dst).data_ptr(), *argv))
         return ops
 
     def _call(self, fn_name, *argv):
@@ -600,6 +644,7 @@ class Engine:
                                      'path; the reference uses the default momentum 0.1')
         args.momentum = a.mod.momentum
         args.eps = a.mod.eps
+        args.lo_delta = self.lo_delta
         return args
 
     def stats_of(self, bn):
@@ -788,7 +833,8 @@ class Engine:
         p0 = self.act(n, hp, wp, c0)
         idx = torch.zeros(n, hp, wp, c0, dtype=torch.uint8, device=dev)
         self._bufs.append(idx)
-        fwd.append(self._call('mp_maxpool_fwd', a0.data_ptr(), p0.data_ptr(), idx.data_ptr(), n, h // 2, w // 2, c0))
+        fwd.append(self._call('mp_maxpool_fwd', a0.data_ptr(), p0.data_ptr(), idx.data_ptr(), n, h // 2, w // 2, c0,
+                              self.lo_delta))
         self.trace += [('stem.relu', a0, bn0.C), ('stem.maxpool', p0, bn0.C)]
         x = p0
         res_bwd = []
@@ -820,7 +866,8 @@ class Engine:
                 prev, wc = self.probs[t - 1], L.combiners[t - 1]
                 new_inp = self.act(*inp.shape)
                 segs.append(('serial', [self._call('mp_combiner_fwd', planes(prev), wc.data.data_ptr(),
-                                                   inp.data_ptr(), new_inp.data_ptr(), n, J, hf * wf, cf)]))
+                                                   inp.data_ptr(), new_inp.data_ptr(), n, J, hf * wf, cf,
+                                                   self.lo_delta)]))
                 comb.append((prev, wc))
                 inp = new_inp
             inps.append(inp)
@@ -839,8 +886,7 @@ class Engine:
                             'axis permutation needs a square mid feature map whose side (%d) divides '
                             'the channel count (%d)' % (s, cmid))
                     xp = self.act(*xcol.shape)
-                    ops.append(self._call('mp_axis_permute', xcol.data_ptr(), xp.data_ptr(), col.mode, n, s,
-                                          cmid, xcol.shape[-1]))
+                    ops += self._moves('mp_axis_permute', xcol, xp, col.mode, n, s, cmid, xcol.shape[-1])
                     perm = (col.mode, s, cmid, tuple(xcol.shape))
                     xcol = xp
                 logits = torch.zeros(n, J, hf, wf, device=dev)
@@ -888,8 +934,7 @@ class Engine:
                     if perm is not None and i == n_down:
                         mode, s, cmid, shp = perm
                         dp = self.act(*shp)
-                        ops.append(self._call('mp_axis_permute', d.data_ptr(), dp.data_ptr(), mode, n, s, cmid,
-                                              shp[-1]))
+                        ops += self._moves('mp_axis_permute', d, dp, mode, n, s, cmid, shp[-1])
                         d = dp
                 lanes.append(ops)
                 dxs.append(d)
@@ -898,7 +943,7 @@ class Engine:
             terms = dxs + ([d_next] if d_next is not None else [])
             arr = (ctypes.c_void_p * 4)(*([x.data_ptr() for x in terms] + [None] * (4 - len(terms))))
             bsegs.append(('serial', [self._call('mp_add_bf16', ctypes.byref(arr), len(terms), d_inp.data_ptr(),
-                                                d_inp.numel())]))
+                                                d_inp.numel(), self.lo_delta)]))
             self._keep.append(arr)
             d_next = d_inp
             self.bwd_marks.append(len(bsegs))    # stage t's (and combiner t's) parameter gradients are complete
@@ -916,6 +961,9 @@ class Engine:
             d = res_bwd[i](ops, d, need_dx=True)
         da0 = self.act(*a0.shape)
         ops.append(self._call('mp_maxpool_bwd', d.data_ptr(), idx.data_ptr(), da0.data_ptr(), n, h // 2, w // 2, c0))
+        if self.split:
+            ops.append(self._call('mp_maxpool_bwd', self.pairs.lo(d).data_ptr(), idx.data_ptr(),
+                                  self.pairs.lo(da0).data_ptr(), n, h // 2, w // 2, c0))
         dy0 = self.act(*y0.shape)
         self.bn_bwd(ops, f0, dout=da0, dya=dy0)
         ops += self.conv_ops(lambda: C.conv_wgrad(conv0.g, patches, dy0, conv0.w.grad))

@@ -247,8 +247,17 @@ class _Body(torch.autograd.Function):
 
 
 class MargiPoseModel(nn.Module):
-    def __init__(self, skel_desc, n_stages, axis_permutation, feature_extractor, pixelwise_loss):
+    PRECISIONS = ('bf16', 'bf16x3')
+
+    def __init__(self, skel_desc, n_stages, axis_permutation, feature_extractor, pixelwise_loss, precision='bf16'):
         super().__init__()
+        if precision not in self.PRECISIONS:
+            raise ValueError('precision must be one of %s' % (self.PRECISIONS,))
+        # 'bf16'  : bf16 tensor-core operands and bf16 activation storage, fp32 accumulation (the fast path)
+        # 'bf16x3': every activation / weight is a pair of bf16 values (hi + lo, ~16 significant bits) and every
+        #           convolution is three tensor-core passes over one fp32 accumulator -- results agree with the
+        #           reference's fp32 arithmetic to ~1e-4 (PARITY.md) at roughly a third of the speed
+        self.precision = precision
         self.data_specs = DataSpecs(
             ImageSpecs(256, mean=ImageSpecs.IMAGENET_MEAN, stddev=ImageSpecs.IMAGENET_STDDEV),
             JointsSpecs(skel_desc, n_dims=3),
@@ -264,15 +273,23 @@ class MargiPoseModel(nn.Module):
         self._packed_version = None
 
     # ---- engine plumbing
+    def set_precision(self, precision):
+        """Switches the arithmetic of the CUDA engine ('bf16' | 'bf16x3'); parameters and buffers are kept."""
+        if precision not in self.PRECISIONS:
+            raise ValueError('precision must be one of %s' % (self.PRECISIONS,))
+        self.precision = precision
+        return self
+
     def _materialize(self, device):
-        self._bank = ParamBank()
+        self._bank = ParamBank(split=self.precision == 'bf16x3')
         self._layers = build_layers(self, self._bank)
         self._bank.finalize(device)
         self._engines = {}
         self._packed_version = None
 
     def _ensure(self, device):
-        if self._bank is None or self._bank.device != device or not self._bank.linked():
+        if self._bank is None or self._bank.device != device or not self._bank.linked() or \
+                self._bank.split != (self.precision == 'bf16x3'):
             self._materialize(device)
 
     def engine_for(self, n, h, w, training):
@@ -412,5 +429,6 @@ class MargiPoseModelFactory(ModelFactory):
             axis_permutation=s.get('axis_permutation', True),
             feature_extractor=s.get('feature_extractor', 'inceptionv4'),
             pixelwise_loss=s.get('pixelwise_loss', 'jsd'),
+            precision=s.get('precision', 'bf16'),      # extension of the settings dict: engine arithmetic
         )
         return MargiPoseModel(**kwargs)

@@ -60,7 +60,7 @@ def maxpool_fwd(x):
     n, h, w, c = x.shape
     y = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=x.device)
     idx = torch.empty(n, h // 2, w // 2, c, dtype=torch.uint8, device=x.device)
-    check(lib().mp_maxpool_fwd(x.data_ptr(), y.data_ptr(), idx.data_ptr(), n, h, w, c, stream_ptr(x.device)),
+    check(lib().mp_maxpool_fwd(x.data_ptr(), y.data_ptr(), idx.data_ptr(), n, h, w, c, 0, stream_ptr(x.device)),
           'mp_maxpool_fwd')
     return y, idx
 
@@ -86,14 +86,14 @@ def combiner_fwd(probs, w, inp):
     n, j, h, wd = probs[0].shape
     out = torch.empty_like(inp)
     check(lib().mp_combiner_fwd(planes(probs), w.data_ptr(), inp.data_ptr(), out.data_ptr(), n, j, h * wd,
-                                inp.shape[-1], stream_ptr(inp.device)), 'mp_combiner_fwd')
+                                inp.shape[-1], 0, stream_ptr(inp.device)), 'mp_combiner_fwd')
     return out
 
 
 def combiner_bwd(dout, probs, w, dprobs, dw, accumulate):
     n, j, h, wd = probs[0].shape
     check(lib().mp_combiner_bwd(dout.data_ptr(), planes(probs), w.data_ptr(), planes(dprobs), dw.data_ptr(),
-                                int(accumulate), n, j, h * wd, dout.shape[-1], stream_ptr(dout.device)),
+                                int(accumulate), n, j, h * wd, dout.shape[-1], 0, stream_ptr(dout.device)),
           'mp_combiner_bwd')
 
 
@@ -102,14 +102,14 @@ def stem_im2col(x):
     n, c, h, w = x.shape
     assert c == 3 and x.dtype == torch.float32 and x.is_contiguous()
     out = torch.empty(n, h // 2, w // 2, 192, dtype=torch.bfloat16, device=x.device)
-    check(lib().mp_stem_im2col(x.data_ptr(), out.data_ptr(), n, h, w, stream_ptr(x.device)), 'mp_stem_im2col')
+    check(lib().mp_stem_im2col(x.data_ptr(), out.data_ptr(), n, h, w, 0, stream_ptr(x.device)), 'mp_stem_im2col')
     return out
 
 
 def add_bf16(tensors):
     out = torch.empty_like(tensors[0])
     arr = (ctypes.c_void_p * 4)(*([t.data_ptr() for t in tensors] + [None] * (4 - len(tensors))))
-    check(lib().mp_add_bf16(ctypes.byref(arr), len(tensors), out.data_ptr(), out.numel(),
+    check(lib().mp_add_bf16(ctypes.byref(arr), len(tensors), out.data_ptr(), out.numel(), 0,
                             stream_ptr(out.device)), 'mp_add_bf16')
     return out
 

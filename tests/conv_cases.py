@@ -146,3 +146,96 @@ def check_fused_block_dgrad(stride, tr):
                  second=(g2, to_nhwc(dy2, g2.cout_p), p1.shape[1]))
     _sync()
     torch.testing.assert_close(from_nhwc(dx, cin), x.grad, rtol=1e-2, atol=3e-2)
+
+
+# ---------------------------------------------------------------------------- split ("bf16x3") precision mode
+def _pair(x, cp):
+    """fp32 NCHW (cpu) -> registered (hi, lo) bf16 NHWC padded pair, halves a fixed distance apart."""
+    from margipose_b200 import convops as C
+    n, c, h, w = x.shape
+    buf = torch.zeros(2, n, h, w, cp, dtype=torch.bfloat16, device=DEV)
+    v = x.permute(0, 2, 3, 1).contiguous()
+    hi, lo = C.split_bf16(v)
+    buf[0, ..., :c] = hi.to(DEV)
+    buf[1, ..., :c] = lo.to(DEV)
+    return buf
+
+
+def _pack_pair(packed_fp32):
+    from margipose_b200 import convops as C
+    hi, lo = C.split_bf16(packed_fp32)
+    buf = torch.stack([hi, lo]).contiguous()
+    return buf
+
+
+def _pack_fp32(g, master, bwd):
+    """Same layout as convops.pack_fwd / pack_bwd, kept in fp32 (the split mode packs W_hi and W_lo from it)."""
+    if not bwd:
+        m = master.permute(2, 1, 0) if g.transposed else master
+        out = torch.zeros(g.cout_p, g.taps, g.cin_p, device=master.device)
+        out[:g.cout, :, :g.cin] = m
+        return out.reshape(g.cout_p, g.taps * g.cin_p)
+    m = master if g.transposed else master.permute(2, 1, 0)
+    out = torch.zeros(g.cin_p, g.taps, g.cout_p, device=master.device)
+    out[:g.cin, :, :g.cout] = m
+    return out.reshape(g.cin_p, g.taps * g.cout_p)
+
+
+def check_split_conv(case):
+    """Forward (+ BatchNorm sums), data gradient (+ residual) and weight gradient with every operand a bf16 pair
+    and three tensor-core passes per accumulation, against the fp64 convolution of the SAME fp32 inputs:
+    agreement ~1e-5 relative (pair rounding 2^-17 per operand), i.e. fp32-grade results from bf16 MMAs."""
+    from margipose_b200 import convops as C
+    cin, cout, k, stride, tr, n, h, w = case
+    g = C.ConvGeom(cin, cout, k, stride, tr)
+    gen = torch.Generator().manual_seed(7)
+    x = torch.randn(n, cin, h, w, generator=gen)
+    wt = torch.randn(*g.torch_weight_shape, generator=gen) / (cin * k * k) ** 0.5
+    ho, wo = g.out_hw(h, w)
+    dy = torch.randn(n, cout, ho, wo, generator=gen)
+    res = torch.randn(n, cin, h, w, generator=gen)
+    xr, wr = x.double().requires_grad_(), wt.double().requires_grad_()
+    y_ref = ref_conv(g, xr, wr)
+    y_ref.backward(dy.double())
+    master = C.master_from_torch(g, wt).to(DEV)
+    pairs = C.SplitPairs()
+
+    def reg(buf):
+        return pairs.register(buf[0], buf[1])
+    xg, dyg, resg = reg(_pair(x, g.cin_p)), reg(_pair(dy, g.cout_p)), reg(_pair(res, g.cin_p))
+    wf, wb = reg(_pack_pair(_pack_fp32(g, master, False))), reg(_pack_pair(_pack_fp32(g, master, True)))
+    out = reg(torch.zeros(2, n, ho, wo, g.cout_p, dtype=torch.bfloat16, device=DEV))
+    dx = reg(torch.zeros(2, n, h, w, g.cin_p, dtype=torch.bfloat16, device=DEV))
+    dx2 = reg(torch.zeros(2, n, h, w, g.cin_p, dtype=torch.bfloat16, device=DEV))
+    stats = torch.zeros(2, g.cout_p, device=DEV)
+    dw = torch.zeros(g.master_shape, device=DEV)
+    old, C.SPLIT = C.SPLIT, pairs
+    try:
+        C.conv_forward(g, xg, wf, out, stats=(stats[0], stats[1]))
+        C.conv_dgrad(g, dyg, wb, dx)
+        if not (g.k == 1 and g.stride == 2):
+            C.conv_dgrad(g, dyg, wb, dx2, res=resg)
+        C.conv_wgrad(g, xg, dyg, dw)
+    finally:
+        C.SPLIT = old
+    _sync()
+
+    def val(t, c):
+        return from_nhwc(pairs.value(t), c)
+    got = val(out, g.cout)
+    err_y = ((got - y_ref.detach().float()).abs().max() / y_ref.abs().max()).item()
+    torch.testing.assert_close(got, y_ref.detach().float(), rtol=2e-5, atol=2e-5 * y_ref.abs().max().item())
+    of = pairs.value(out).reshape(-1, g.cout_p)
+    torch.testing.assert_close(stats[0], of.sum(0), rtol=1e-4, atol=1e-2)
+    torch.testing.assert_close(stats[1], (of * of).sum(0), rtol=1e-4, atol=1e-2)
+    gx = xr.grad.float()
+    scale = gx.abs().max().item()
+    if not (g.k == 1 and g.stride == 2 and not g.transposed):
+        torch.testing.assert_close(val(dx, g.cin), gx, rtol=2e-5, atol=2e-5 * scale)
+    else:
+        torch.testing.assert_close(val(dx, g.cin)[..., ::2, ::2], gx[..., ::2, ::2], rtol=2e-5, atol=2e-5 * scale)
+    if not (g.k == 1 and g.stride == 2):
+        torch.testing.assert_close(val(dx2, g.cin), gx + res, rtol=2e-5, atol=2e-5 * (scale + 4))
+    want = C.master_from_torch(g, wr.grad.float())
+    torch.testing.assert_close(dw.cpu(), want, rtol=5e-5, atol=5e-5 * want.abs().max().item())
+    return err_y

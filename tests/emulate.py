@@ -27,8 +27,13 @@ def _gather(v, c0, nc, dw, p, dh, out_h, out_w):
     return out
 
 
+def _strided(t, n_img, out_h, out_w, out_c, strides, off):
+    # (as_strided takes an ABSOLUTE storage offset: tensors here may be views into a larger hi / lo buffer)
+    return torch.as_strided(t, (n_img, out_h, out_w, out_c), tuple(strides) + (1,), t.storage_offset() + off)
+
+
 def igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_c, res=None,
-          stats=None, out_offset=0, bn=None, defer=None, ep=None):
+          stats=None, out_offset=0, bn=None, defer=None, ep=None, out_lo=None, acc_in=None, res_lo=None):
     views = [_view5(t, parity) for t, parity in srcs]
     wm = wmat.float()
     acc = torch.zeros(n_img, out_h, out_w, wm.shape[0])
@@ -38,27 +43,37 @@ def igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_
         acc += a @ wm[:, koff:koff + nc].t()
     acc = acc[..., :out_c]
     sn, sh, sw = out_strides
-    flat = out.view(-1)
-    dst = torch.as_strided(flat, (n_img, out_h, out_w, out_c), (sn, sh, sw, 1), out_offset)
+    shape = (n_img, out_h, out_w, out_c, out_strides, out_offset)
+    dst = _strided(out, *shape)
+    shape = (n_img, out_h, out_w, out_c, out_strides, out_offset)
+    if acc_in is not None:     # split mode: the pair written by the earlier passes (acc_in is `out` itself)
+        assert acc_in.data_ptr() == out.data_ptr() and out_lo is not None
+        acc = acc + _strided(out, *shape).float() + _strided(out_lo, *shape).float()
     if ep is not None:     # (scale, shift, relu mode) as fp32 tensors here (device pointers on the GPU)
         scale, shift, relu = ep
         acc = acc * scale[:out_c] + shift[:out_c]
         if relu == 1:
             acc = acc.clamp_min(0)
     if res is not None:
-        acc = acc + torch.as_strided(res.view(-1), (n_img, out_h, out_w, out_c), (sn, sh, sw, 1),
-                                     out_offset).float()
+        acc = acc + _strided(res, *shape).float()
+        if res_lo is not None:
+            acc = acc + _strided(res_lo, *shape).float()
     if ep is not None and ep[2] == 2:
         acc = acc.clamp_min(0)
     rounded = acc.to(torch.bfloat16)
     dst.copy_(rounded)
+    stored = rounded.float()
+    if out_lo is not None:
+        lo = (acc - stored).to(torch.bfloat16)
+        _strided(out_lo, *shape).copy_(lo)
+        stored = stored + lo.float()
     if stats is not None:
-        r = rounded.float().reshape(-1, out_c)
+        r = stored.reshape(-1, out_c)
         stats[0][:out_c] += r.sum(0)
         stats[1][:out_c] += (r * r).sum(0)
 
 
-def wgrad(a_t, b_t, b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, grid_h, grid_w, dw):
+def wgrad(a_t, b_t, b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, grid_h, grid_w, dw, count_flops=True):
     va = _view5(a_t, False)
     vb = _view5(b_t, b_parity)
     a = _gather(va, 0, va.shape[-1], 0, 0, 0, grid_h, grid_w)[..., :m_real].reshape(-1, m_real)
@@ -69,5 +84,5 @@ def wgrad(a_t, b_t, b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, grid
 
 def install(monkeypatch):
     from margipose_b200 import convops
-    monkeypatch.setattr(convops, '_igemm', igemm)
-    monkeypatch.setattr(convops, '_wgrad', wgrad)
+    monkeypatch.setattr(convops, '_igemm_one', igemm)
+    monkeypatch.setattr(convops, '_wgrad_one', wgrad)

@@ -52,3 +52,13 @@ def test_conv_kernel_variants(tunables):
     finally:
         for k in tunables:
             lib().mp_set_tunable(k.encode(), DEFAULTS[k])
+
+
+@pytest.mark.parametrize('case', K.CASES[:3] + K.CASES[7:9] + K.CASES[10:12] + K.CASES[16:17], ids=IDS)
+def test_split_precision_conv(case):
+    """bf16x3 mode on the tensor cores: every operand a bf16 pair, three passes per accumulation chained through
+    the epilogue's acc_in -- fp32-grade results (~1e-5) from bf16 MMAs."""
+    from tests.conftest import parity_log
+    K.DEV = 'cuda'
+    err = K.check_split_conv(case)
+    parity_log('conv_bf16x3/' + IDS(case), forward_max_err_over_max=err, tolerance='rtol 2e-5 vs the fp64 convolution')

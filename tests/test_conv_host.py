@@ -31,3 +31,9 @@ def test_conv_dgrad_and_wgrad(case):
 @pytest.mark.parametrize('stride,tr', [(1, False), (2, False), (2, True)])
 def test_fused_block_dgrad(stride, tr):
     K.check_fused_block_dgrad(stride, tr)
+
+
+@pytest.mark.parametrize('case', [c for c in SMALL if c[0] >= 64][:8], ids=IDS)
+def test_split_precision_conv(case):
+    """bf16x3 mode: the three-pass expansion (hi*hi, lo*hi, hi*lo chained through acc_in) in convops."""
+    K.check_split_conv(case)

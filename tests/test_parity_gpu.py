@@ -22,11 +22,13 @@ def desc_of(n_stages, fe):
             'settings': dict(n_stages=n_stages, feature_extractor=fe, axis_permutation=True, pixelwise_loss='jsd')}
 
 
-def trace_tensor(buf, c):
-    """An Engine.trace entry as fp32 NCHW on the CPU (bf16 NHWC padded buffers; the logits are fp32 NCHW)."""
+def trace_tensor(buf, c, eng=None):
+    """An Engine.trace entry as fp32 NCHW on the CPU (bf16 NHWC padded buffers -- hi + lo pairs in the bf16x3
+    mode, resolved through `eng` --; the logits are fp32 NCHW)."""
     if buf.dtype == torch.float32:
         return buf.detach().cpu()
-    return buf[..., :c].float().permute(0, 3, 1, 2).contiguous().cpu()
+    v = eng.value(buf) if eng is not None else buf.float()
+    return v[..., :c].permute(0, 3, 1, 2).contiguous().cpu()
 
 
 def test_layerwise_trace_of_the_bench_config():
@@ -108,42 +110,175 @@ def test_layerwise_trace_of_the_bench_config():
     assert max(growth) < 1.6
 
 
-def test_fixed_batch_training_follows_the_fp32_reference_curve():
-    """50 SGD-momentum steps on one fixed batch (1-stage ResNet-18, batch 4): the CUDA path (bf16 operands and
-    activations, fused loss, captured graphs) against the fp32 oracle restating the reference's training step
-    (bin/train_3d.py:164-186).  Evidence that bf16 storage is benign for this loss: the curves stay within a
-    few per cent of each other while the loss falls by a third."""
+_CURVE = {}
+
+
+def _oracle_curve(desc, steps, lr, x, target, mask):
+    """Loss curve of the fp32 oracle (the reference's training step, bin/train_3d.py:164-186) on one fixed batch,
+    and the same with the images perturbed by 1e-6 (relative): how far two fp32 runs drift apart by themselves."""
+    if 'want' not in _CURVE:
+        g = torch.Generator().manual_seed(99)
+        xp = x * (1 + 1e-6 * torch.randn(x.shape, generator=g))
+        for key, xin in (('want', x), ('floor', xp)):
+            torch.manual_seed(61)
+            om = M.create_oracle(desc).train()
+            _CURVE['state'] = {k: v.clone() for k, v in om.state_dict().items()}
+            opt_o = torch.optim.SGD(om.parameters(), lr=lr, momentum=0.9)
+            curve = []
+            for _ in range(steps):
+                opt_o.zero_grad()
+                loss = D.average_loss(om.forward_3d_losses(om(xin), target), mask)
+                loss.backward()
+                opt_o.step()
+                curve.append(loss.item())
+            _CURVE[key] = curve
+    return _CURVE['state'], _CURVE['want'], _CURVE['floor']
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'bf16x3'])
+def test_fixed_batch_training_follows_the_fp32_reference_curve(precision):
+    """50 SGD-momentum steps on one fixed batch (1-stage ResNet-18, batch 4): the CUDA path (fused loss, captured
+    graphs) against the fp32 oracle restating the reference's training step (bin/train_3d.py:164-186).
+    bf16  : evidence that bf16 storage is benign for this loss -- the curves stay within a few per cent of each
+            other while the loss falls by a third;
+    bf16x3: the first step agrees to 1e-5; after that the trajectories separate as two fp32 runs do -- the test
+            measures that too (the fp32 oracle against itself with the images perturbed by 1e-6, "floor") and
+            bounds both precisions by twice that floor plus 2 %."""
     from margipose_b200.models import create_model
     from margipose_b200.optim import FlatSGD
     from margipose_b200.train import TrainStep
     desc = desc_of(1, 'resnet18')
     steps, lr = 50, 0.05
-    torch.manual_seed(61)
-    om = M.create_oracle(desc).train()
-    model = create_model(desc)
-    model.load_state_dict(om.state_dict())
-    model = model.cuda().train()
     x, target, mask = model_inputs(62, 4)
-    opt_o = torch.optim.SGD(om.parameters(), lr=lr, momentum=0.9)
-    want = []
-    for _ in range(steps):
-        opt_o.zero_grad()
-        loss = D.average_loss(om.forward_3d_losses(om(x), target), mask)
-        loss.backward()
-        opt_o.step()
-        want.append(loss.item())
+    state, want, floor = _oracle_curve(desc, steps, lr, x, target, mask)
+    fdev = [abs(f - w) / w for f, w in zip(floor, want)]
+    model = create_model(desc).set_precision(precision)
+    model.load_state_dict(state)
+    model = model.cuda().train()
     opt = FlatSGD(model, lr=lr, momentum=0.9)
     step = TrainStep(model, opt, batch=4, warmup=2)
     got = [step(x, target, mask) for _ in range(steps)]
     assert step._graphs is not None
     dev = [abs(g - w) / w for g, w in zip(got, want)]
     print('loss curve fp32 oracle :', ' '.join('%.3f' % v for v in want[::5]))
-    print('loss curve CUDA (bf16) :', ' '.join('%.3f' % v for v in got[::5]))
-    print('max relative deviation %.4f, first step %.2e' % (max(dev), dev[0]))
-    parity_log('convergence/r18x1_b4_50steps', loss_first_rel_err=dev[0], loss_curve_max_rel_dev=max(dev),
-               loss_curve_mean_rel_dev=sum(dev) / len(dev), loss_final=got[-1], loss_final_reference=want[-1],
-               curve=got, curve_reference=want,
-               tolerance='first step 2e-3, whole curve within 6 % of the fp32 oracle, final loss < 0.7 x initial')
-    assert dev[0] < 2e-3
-    assert max(dev) < 0.06
+    print('loss curve CUDA (%s) :' % precision, ' '.join('%.3f' % v for v in got[::5]))
+    print('max relative deviation %.4f (fp32 oracle vs itself + 1e-6 perturbation: %.4f), first step %.2e'
+          % (max(dev), max(fdev), dev[0]))
+    first = {'bf16': 2e-3, 'bf16x3': 1e-5}[precision]
+    band = 2 * max(fdev) + 0.02
+    parity_log('convergence/r18x1_b4_50steps_' + precision, loss_first_rel_err=dev[0],
+               loss_curve_max_rel_dev=max(dev), loss_curve_mean_rel_dev=sum(dev) / len(dev),
+               fp32_self_drift_max_rel_dev=max(fdev), loss_final=got[-1], loss_final_reference=want[-1],
+               curve=got, curve_reference=want, curve_reference_perturbed=floor,
+               tolerance='first step %g; whole curve within 2 x the fp32 oracle\'s own drift + 2 %% = %.3f; final loss '
+                         '< 0.7 x initial' % (first, band))
+    assert dev[0] < first and max(dev) < band
     assert got[-1] < 0.7 * got[0] and want[-1] < 0.7 * want[0]
+
+
+# ------------------------------------------------------------------------------- bf16x3 ("split") precision mode
+import os  # noqa: E402
+
+_G = os.path.join(os.path.dirname(__file__), 'golden')
+GOLD = torch.load(os.path.join(_G, 'margipose_golden.pt'), weights_only=False)['model'] + \
+    torch.load(os.path.join(_G, 'margipose_golden_large.pt'), weights_only=False)['model']
+
+
+@pytest.mark.parametrize('case', GOLD, ids=lambda c: c['name'])
+def test_bf16x3_mode_matches_the_fp32_reference(case):
+    """The north star's "within a stated fp32 tolerance": with precision='bf16x3' (bf16 pairs, three tensor-core
+    passes per convolution, fp32 accumulation) the CUDA path reproduces what the UNMODIFIED fp32 reference
+    computed (tests/golden) -- coordinates to 2e-3, loss to 5e-4, heatmap marginals to 5e-3, gradients to a few
+    per cent -- on the same randomly initialised, training-mode network on which the bf16 path, cuDNN's TF32 and
+    any other reduced-precision arithmetic drift by several 1e-2 (see PARITY.md for the comparison)."""
+    from margipose_b200.models import create_model
+    from margipose_b200 import dsntnn as K
+    desc = {'type': 'margipose', 'version': '6.0.1', 'settings': dict(case['desc']['settings'], precision='bf16x3')}
+    torch.manual_seed(case['weight_seed'])
+    om = M.create_oracle(case['desc'])
+    model = create_model(desc)
+    model.load_state_dict(om.state_dict())
+    model = model.cuda().train()
+    assert model.precision == 'bf16x3'
+    x, target, mask = model_inputs(case['input_seed'], case['batch'], case.get('res', 256))
+    out = model(x.cuda())
+    l3 = K.average_loss(model.forward_3d_losses(out, target.cuda()), mask.cuda())
+    cerr = (out.detach().cpu() - case['train_coords']).abs().max().item()
+    lerr = abs(l3.item() - case['loss3'].item()) / case['loss3'].item()
+    merr = 0.0
+    for t in range(len(model.xy_heatmaps)):
+        for got, want in ((model.xy_heatmaps[t].detach().sum(-1).cpu(), case['xy_rowsum'][t]),
+                          (model.zy_heatmaps[t].detach().sum(-1).cpu(), case['zy_rowsum'][t]),
+                          (model.xz_heatmaps[t].detach().sum(-2).cpu(), case['xz_colsum'][t])):
+            merr = max(merr, (got - want).abs().max().item())
+    l3.backward()
+    worst, tot_want, tot_got = 0.0, 0.0, 0.0
+    for k, p in model.named_parameters():
+        want, got = case['grad_norms'][k].item(), p.grad.norm().item()
+        tot_want += want ** 2
+        tot_got += got ** 2
+        if p.dim() == 4 and want > 1e-3:
+            worst = max(worst, abs(got - want) / want)
+    perr = 0.0
+    params = dict(model.named_parameters())
+    for k, want in case['grad_probe'].items():
+        got = params[k].grad.flatten()[:64].cpu()
+        perr = max(perr, ((got - want).norm() / want.norm().clamp_min(1e-12)).item())
+    gerr = abs(tot_got ** 0.5 - tot_want ** 0.5) / tot_want ** 0.5
+    sd = model.state_dict()
+    rerr = (sd['inner.in_cnn.1.running_var'].cpu() - case['running_var_bn1']).abs().max().item()
+    print('%s bf16x3: coords %.2e loss %.2e marginals %.2e | grad total norm %.2e worst conv-weight norm %.2e '
+          'probe rel L2 %.2e' % (case['name'], cerr, lerr, merr, gerr, worst, perr))
+    parity_log('bf16x3_golden/' + case['name'], coords_max_abs_err=cerr, loss_rel_err=lerr, marginals_max_abs_err=merr,
+               grad_total_norm_rel_err=gerr, grad_worst_conv_weight_norm_rel_err=worst, grad_probe_rel_l2=perr,
+               running_var_bn1_max_abs_err=rerr,
+               tolerance='coords 2e-3, loss 5e-4, marginals 5e-3, total grad norm 1e-2, conv-weight grad norms 5e-2 '
+                         '(vs the fp32 reference golden)')
+    assert cerr < 2e-3 and lerr < 5e-4 and merr < 5e-3
+    assert gerr < 1e-2 and worst < 5e-2     # (element-wise gradient probes are logged only: the fp32 oracle's own
+    assert rerr < 1e-4                      #  gradients move by tens of per cent under a 1e-6 input perturbation)
+
+
+def test_bf16x3_inference_and_layerwise():
+    """bf16x3 in eval mode (folded BatchNorm, InferStep graph) against the fp32 oracle, and block by block in
+    training mode against the free-running fp32 oracle trace."""
+    from margipose_b200.models import create_model
+    from margipose_b200.infer import InferStep
+    desc = desc_of(2, 'resnet18')
+    torch.manual_seed(83)
+    om = M.create_oracle(desc).train()
+    model = create_model(desc).set_precision('bf16x3')
+    model.load_state_dict(om.state_dict())
+    model = model.cuda().train()
+    x, _t, _m = model_inputs(84, 3)
+    om.nm.trace = []
+    with torch.no_grad():
+        om(x)
+        model(x.cuda())
+    eng = model.engine_for(3, 256, 256, True)
+    assert eng.split
+    errs = [(name, rel(trace_tensor(buf, c, eng), want)) for (name, buf, c), want in zip(eng.trace, om.nm.trace)]
+    om.nm.trace = None
+    worst = max(errs, key=lambda e: e[1])
+    print('bf16x3 free-running rel L2 vs the fp32 oracle: first %.2e, max %.2e at %s' % (errs[0][1], worst[1], worst[0]))
+    # eval with running statistics := this batch's (momentum 1)
+    for m in list(om.modules()) + list(model.modules()):
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.momentum = 1.0
+    model.drop_engines()        # launch programs bake the BatchNorm hyper-parameters in when they are recorded
+    with torch.no_grad():
+        om(x)
+        model(x.cuda())
+    om.eval()
+    model.eval()
+    infer = InferStep(model, 3, warmup=1)
+    with torch.no_grad():
+        want = om(x)
+        got = [infer(x).clone() for _ in range(3)][-1]
+    eerr = (got.cpu() - want).abs().max().item()
+    print('bf16x3 eval coords vs fp32 oracle: %.2e' % eerr)
+    parity_log('bf16x3_layerwise/r18x2_b3', free_rel_l2_first=errs[0][1], free_rel_l2_max=worst[1],
+               free_rel_l2_max_at=worst[0], eval_coords_max_abs_err=eerr,
+               tolerance='every block <= 2e-3 free-running vs the fp32 oracle; eval coords 2e-3')
+    assert worst[1] < 2e-3
+    assert eerr < 2e-3
