@@ -374,9 +374,9 @@ MP_API int mp_sgd_step_hp(float* param, const float* grad, float* momentum_buf, 
  *   "igemm_halo"  : 1 (default) = filter taps that differ only by their row shift share one activation box of
  *                   tile_rows + 2 rows (fetched once, read through row-shifted descriptors); 0 = one box per tap
  *   "igemm_pair"  : 1 = two CTAs of a cluster pair up on M=256 tcgen05.mma.cta_group::2 tiles, each loading half of
- *                   every weight tile (when the M tiles pair up); 0 (default) = one CTA per tile
+ *                   every weight tile (when the M tiles pair up); 0 = one CTA per tile (default 1)
  *   "igemm_mt"    : 2 = two 128-pixel row blocks (TMEM accumulators) per tile share every weight tile when the launch
- *                   keeps at least "igemm_mt_ctas" tiles (0 = the CTA count); 1 (default) = one
+ *                   keeps at least "igemm_mt_ctas" tiles (0 = the CTA count) (default 2); 1 = one
  *   "igemm_split_n": mp_conv_igemm halves its N tile when a launch has fewer tiles than this (default 0 = the CTA count)
  *   "igemm_resident": 1 (default) = a CTA keeps its whole weight operand in shared memory across its tiles when it fits
  *   "igemm_astages": activation (halo box) slots in flight when the weights stream (default 3)
@@ -388,7 +388,9 @@ MP_API int mp_sgd_step_hp(float* param, const float* grad, float* momentum_buf, 
  *   "wgrad_slice" : widest column slice of B per CTA when taps are grouped (default 256; 64 or 128 narrow it)
  *   "wgrad_kp"    : pixels per pipeline stage of mp_conv_wgrad (default 128)
  *   "wgrad_smem"  : shared-memory budget of mp_conv_wgrad's pipeline stages in bytes (default 204800)
- *   "wgrad_dbg"   : experiment switches (1 = skip the gradient atomics, 4 = no MMA) */
+ *   "wgrad_dbg"   : experiment switches (1 = skip the gradient atomics, 4 = no MMA)
+ *   "tail_fast"   : 1 (default) = mp_tail_fwd / mp_tail_bwd use the log2-domain kernels when the heatmap width divides 128;
+ *                   0 = the general warp-sliced kernels */
 MP_API int mp_set_tunable(const char* name, int64_t value);
 
 #ifdef __cplusplus

@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include "../../include/margipose_b200.h"
 
+long long g_tail_fast = 1;   // tunable "tail_fast": 1 = the log2-domain kernels for row lengths dividing 128
+
 namespace {
 
 constexpr int NT = 256;        // threads per CTA
@@ -801,6 +803,439 @@ __global__ void __launch_bounds__(512, 2) tail_bwd_warp_kernel(const BwdArgs A, 
   }
 }
 
+
+// =====================================================================================
+// Fast variants of the warp-sliced kernels for row lengths that divide 128 (W = 32 / 64 / 128, the MargiPose
+// heatmaps): a lane's four columns are the same in every one of its float4 slots, so the column centres and the
+// Gaussian's column factors are per-lane CONSTANTS, rows advance by 128 / W per slot (no integer division), the
+// softmax / JS arithmetic runs in the log2 domain (one FFMA + one MUFU.EX2 per exponential, one MUFU.LG2 per
+// logarithm), and exp() is evaluated once per element unless the JS term needs log p.  ~7 (softmax + dsnt),
+// ~18 (full forward) and ~16 (full backward) instructions per heatmap element instead of 48 / 83 / 83
+// (profiles/r02_tail_ncu.md), which is what moves these kernels from issue-bound to HBM-bound.
+constexpr float L2E = 1.4426950408889634f;    // log2(e)
+constexpr float LN2 = 0.6931471805599453f;
+// single MUFU instructions (no denormal fix-up code around them: exp2 of a very negative number is 0 either way,
+// and every logarithm below is taken of a value >= 1e-24)
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Gaussian factor tables of one plane, computed ONCE by the plane's warps together (entry i by warp i / 32):
+// tab[0..W) = column factors, tab[W..W+H) = row factors, ltab = their exponents (natural log), and per-warp partial
+// sums for the normaliser in gs[warp * 3 + {0, 1}] (slot 2: the forward kernel's entropy partial).
+__device__ __forceinline__ void gauss_tables(const Geom& g, float mc, float mr, int s, int wpp, int lane, float* tab,
+                                             float* ltab, float* gs) {
+  float sc = 0.f, sr = 0.f;
+  for (int i = s * 32 + lane; i < g.W + g.H; i += wpp * 32) {
+    const bool col = i < g.W;
+    const float c = col ? centre(i, g.cw_step, g.cw_first) - mc : centre(i - g.W, g.ch_step, g.ch_first) - mr;
+    const float lg = __fmul_rn(__fmul_rn(c, c), col ? g.kw : g.kh);
+    const float ev = expf(lg);
+    tab[i] = ev;
+    if (ltab) ltab[i] = lg;
+    if (col) sc += ev; else sr += ev;
+  }
+  sc = warp_sum(sc);
+  sr = warp_sum(sr);
+  if (lane == 0) { gs[s * 3] = sc; gs[s * 3 + 1] = sr; }
+}
+
+template <int NV, bool FROM_LOGITS>
+__global__ void __launch_bounds__(512, 2) tail_fwd_fast_kernel(const FwdArgs A, const WarpPlan P, const int wshift) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float sm[];
+  const int W = A.g.W, H = A.g.H, HW = A.g.HW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nslots = P.groups * P.np;
+  const int nseq = P.seq ? P.np : 1;
+  const int w0 = (lane * 4) & (W - 1);                 // this lane's four columns, in every slot
+  const int rpi = 128 >> wshift;                       // rows a warp advances per float4 slot
+  for (int it = 0; it < nseq; ++it) {
+  const int slot = P.seq ? it : warp / P.wpp;
+  const int s = P.seq ? warp : warp - slot * P.wpp;
+  const int g = slot / P.np, ks = slot - g * P.np;
+  const int k = P.pid[ks];
+  const int bj = blockIdx.x * P.groups + g;
+  const bool active = bj < P.BJ;
+  float* tab = sm + slot * 2 * (W + H);                   // ecol[W], erow[H], then their exponents
+  float* ltab = tab + (W + H);
+  float* red = sm + nslots * 2 * (W + H) + slot * (P.wpp * 4);   // per warp: sum, sum*cw, sum*ch, max
+  float* jsr = sm + nslots * 2 * (W + H) + nslots * P.wpp * 4 + slot * P.wpp;   // per warp JS partial
+  float* res = sm + nslots * 2 * (W + H) + nslots * P.wpp * 5 + slot * 2;       // per plane (a, b)
+  float* gs = sm + nslots * 2 * (W + H) + nslots * P.wpp * 5 + nslots * 2 + slot * (P.wpp * 3);   // normaliser partials
+
+  const int b = active ? bj / A.J : 0;
+  const bool is3d = (active && A.valid_depth) ? (A.valid_depth[b] != 0) : true;
+  float tx = 0.f, ty = 0.f, tz = 0.f;
+  if (active && A.target) {
+    tx = A.target[bj * 3 + 0]; ty = A.target[bj * 3 + 1]; tz = A.target[bj * 3 + 2];
+  }
+  float mc = 0.f, mr = 0.f;
+  bool want_js = false;
+  if (active) {
+    if (A.mu[k]) {
+      mc = A.mu[k][bj * 2 + 0]; mr = A.mu[k][bj * 2 + 1];
+      want_js = A.js[k] != nullptr;
+    } else {
+      mc = (k == 1) ? tz : tx;
+      mr = (k == 2) ? tz : ty;
+      want_js = A.target && A.pixelwise && (A.loss || A.js[k]) && (k == 0 || is3d);
+    }
+  }
+  const size_t off = (size_t)bj * HW;
+  const int e0 = (s * NV * 32 + lane) * 4;               // slot i covers elements e0 + i * 128 .. + 3
+  const int h0 = e0 >> wshift;
+  // (a large finite fill instead of -inf keeps exp2(t) * t = 0 * finite in the entropy sum of padded lanes)
+  const float fill = FROM_LOGITS ? -1e30f : 0.f;
+  float4 x[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = e0 + i * 128;
+    x[i] = (active && e < HW) ? __ldg(reinterpret_cast<const float4*>(A.in[k] + off + e))
+                              : make_float4(fill, fill, fill, fill);
+  }
+  if (want_js) gauss_tables(A.g, mc, mr, s, P.wpp, lane, tab, ltab, gs);
+  float m = -INFINITY;
+  if (FROM_LOGITS) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) m = fmaxf(m, fmaxf(fmaxf(x[i].x, x[i].y), fmaxf(x[i].z, x[i].w)));
+    m = warp_max(m);
+    if (lane == 0) red[s * 4 + 3] = m;
+  }
+  __syncthreads();   // #1: Gaussian factors + per-warp maxima visible
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accx = 0.f;
+  if (FROM_LOGITS) {
+    for (int q = 0; q < P.wpp; ++q) m = fmaxf(m, red[q * 4 + 3]);
+  }
+  const float m2 = m * L2E;
+  {
+    float cw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cw[j] = centre(w0 + j, A.g.cw_step, A.g.cw_first);
+    // pass 1: exponentials (log2 domain), partition sum, the two coordinate moments and -- for the JS term --
+    // sum exp(t) * t (the entropy of p in closed form: log2 p = t2 - log2(sum)).  The registers then keep
+    // t2 = (x - max) * log2(e) when a JS term follows (pass 2 re-exponentiates with the normaliser folded in),
+    // otherwise exp(t).  (Two separate loops: a per-element select between the two would keep both alive.)
+    if (FROM_LOGITS && want_js) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float v[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+        float rowsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j] = fmaxf(fmaf(v[j], L2E, -m2), -1e30f);   // -inf logits stay finite: 0 * t2 = 0 below
+          const float ev = fast_ex2(v[j]);
+          accx = fmaf(ev, v[j], accx);
+          rowsum += ev;
+          acc1 = fmaf(ev, cw[j], acc1);
+        }
+        acc0 += rowsum;
+        acc2 = fmaf(rowsum, centre(h0 + i * rpi, A.g.ch_step, A.g.ch_first), acc2);
+        x[i] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float v[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+        float rowsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (FROM_LOGITS) v[j] = fast_ex2(fmaf(v[j], L2E, -m2));
+          rowsum += v[j];
+          acc1 = fmaf(v[j], cw[j], acc1);
+        }
+        acc0 += rowsum;
+        acc2 = fmaf(rowsum, centre(h0 + i * rpi, A.g.ch_step, A.g.ch_first), acc2);
+        x[i] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  }
+  acc0 = warp_sum(acc0); acc1 = warp_sum(acc1); acc2 = warp_sum(acc2);
+  if (FROM_LOGITS && want_js) accx = warp_sum(accx);
+  if (lane == 0) {
+    red[s * 4 + 0] = acc0; red[s * 4 + 1] = acc1; red[s * 4 + 2] = acc2;
+    if (FROM_LOGITS) gs[s * 3 + 2] = accx;
+  }
+  __syncthreads();   // #2
+  acc0 = acc1 = acc2 = accx = 0.f;
+  for (int q = 0; q < P.wpp; ++q) { acc0 += red[q * 4 + 0]; acc1 += red[q * 4 + 1]; acc2 += red[q * 4 + 2]; }
+  float ea, eb;
+  float inv = 1.f, l2inv = 0.f;
+  if (FROM_LOGITS) {
+    inv = 1.0f / acc0;
+    l2inv = -log2f(acc0);
+    ea = acc1 * inv; eb = acc2 * inv;
+  } else {
+    ea = acc1; eb = acc2;
+  }
+  // pass 2: probabilities and JS in bits,
+  //   2 JS / ln 2 = sum p lg p + sum q lg q - sum (p + q) lg((p + q) / 2 + eps)
+  // sum p lg p comes from pass 1 (logits) and sum q lg q is separable in the Gaussian's row / column factors, so
+  // an element costs one exp2, one log2 and five FP32 instructions.  (log(. + 1e-24) of the reference differs from
+  // log(.) only where p or q < 1e-17, where p lg p and q lg q vanish in fp32 anyway.)
+  float jsp = 0.f;
+  if (want_js) {
+    float sc = 0.f, sr = 0.f;
+    for (int q = 0; q < P.wpp; ++q) { sc += gs[q * 3]; sr += gs[q * 3 + 1]; }
+    const float ginv = 1.0f / (sc * sr + KL_EPS);
+    float qc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) qc[j] = tab[w0 + j];
+    float slm = 0.f, plp = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float pv[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+      if (e0 + i * 128 < HW) {
+        const float er = tab[W + h0 + i * rpi] * ginv;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (FROM_LOGITS) pv[j] = fast_ex2(pv[j] + l2inv);
+          else plp = fmaf(pv[j], fast_lg2(pv[j] + KL_EPS), plp);
+          const float sq = fmaf(qc[j], er, pv[j]);                 // p + q
+          slm = fmaf(sq, fast_lg2(fmaf(0.5f, sq, KL_EPS)), slm);
+        }
+      } else if (FROM_LOGITS) {
+        pv[0] = pv[1] = pv[2] = pv[3] = 0.f;
+      }
+      x[i] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    }
+    jsp = plp - slm;
+    if (s == 0) {
+      // this plane's sum q lg q = lg(ginv) + ginv * (sum_w qc lqc * sum_h qr + sum_w qc * sum_h qr lqr) * log2(e)
+      // (sum q = 1 up to the 1e-24 in the normaliser), accumulated by warp 0 from the 1-D tables
+      float a = 0.f, bq = 0.f;
+      for (int i = lane; i < W; i += 32) a = fmaf(tab[i], ltab[i], a);
+      for (int i = lane; i < H; i += 32) bq = fmaf(tab[W + i], ltab[W + i], bq);
+      a = warp_sum(a); bq = warp_sum(bq);
+      if (lane == 0) jsp += fmaf(ginv * L2E, fmaf(a, sr, sc * bq), log2f(ginv) * (sc * sr * ginv));
+    }
+    jsp = warp_sum(jsp);
+    if (FROM_LOGITS && s == 0) {   // sum p lg p = (sum exp(t) t2) / sum exp(t) - log2(sum exp(t))
+      float ex = 0.f;
+      for (int q = 0; q < P.wpp; ++q) ex += gs[q * 3 + 2];
+      jsp += fmaf(ex, inv, l2inv);
+    }
+    jsp *= LN2;
+  } else if (FROM_LOGITS) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { x[i].x *= inv; x[i].y *= inv; x[i].z *= inv; x[i].w *= inv; }
+  }
+  if (active && A.prob[k]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = e0 + i * 128;
+      if (e < HW) *reinterpret_cast<float4*>(A.prob[k] + off + e) = x[i];
+    }
+  }
+  if (lane == 0) {
+    jsr[s] = jsp;
+    if (s == 0) { res[0] = ea; res[1] = eb; }
+  }
+  __syncthreads();   // #3: per-plane results complete
+  if (!active || s != 0 || lane != 0) continue;
+  float js = 0.f;
+  for (int q = 0; q < P.wpp; ++q) js += jsr[q];
+  js *= 0.5f;
+  if (A.ab[k]) { A.ab[k][bj * 2 + 0] = ea; A.ab[k][bj * 2 + 1] = eb; }
+  if (A.js[k]) A.js[k][bj] = js;
+  if (ks != P.np - 1 && P.seq) continue;     // sequential mode: combine after the last plane
+  if (ks != 0 && !P.seq) continue;
+  // one leader combines the planes (models/margipose_model.py:254-261)
+  float pa[3] = {0.f, 0.f, 0.f}, pb[3] = {0.f, 0.f, 0.f}, pj[3] = {0.f, 0.f, 0.f};
+  for (int q = 0; q < P.np; ++q) {
+    const int slot_q = g * P.np + q;
+    const float* rq = sm + nslots * 2 * (W + H) + nslots * P.wpp * 5 + slot_q * 2;
+    const float* jq = sm + nslots * 2 * (W + H) + nslots * P.wpp * 4 + slot_q * P.wpp;
+    float t = 0.f;
+    for (int u = 0; u < P.wpp; ++u) t += jq[u];
+    pa[P.pid[q]] = rq[0]; pb[P.pid[q]] = rq[1]; pj[P.pid[q]] = 0.5f * t;
+  }
+  const float px = pa[0], py = pb[0], pz = 0.5f * (pa[1] + pb[2]);
+  if (A.coords) { A.coords[bj * 3 + 0] = px; A.coords[bj * 3 + 1] = py; A.coords[bj * 3 + 2] = pz; }
+  if (A.loss && A.target) {
+    const float dx = px - tx, dy = py - ty, dz = pz - tz;
+    float l;
+    if (is3d) l = pj[0] + pj[1] + pj[2] + sqrtf(dx * dx + dy * dy + dz * dz);
+    else l = pj[0] + sqrtf(dx * dx + dy * dy);
+    A.loss[bj] = A.accumulate ? A.loss[bj] + l : l;
+  }
+  }
+}
+
+template <int NV, bool PROJECT>
+__global__ void __launch_bounds__(512, 2) tail_bwd_fast_kernel(const BwdArgs A, const WarpPlan P, const int wshift) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float sm[];
+  const int W = A.g.W, H = A.g.H, HW = A.g.HW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nslots = P.groups * P.np;
+  const int nseq = P.seq ? P.np : 1;
+  const int w0 = (lane * 4) & (W - 1);
+  const int rpi = 128 >> wshift;
+  for (int it = 0; it < nseq; ++it) {
+  const int slot = P.seq ? it : warp / P.wpp;
+  const int s = P.seq ? warp : warp - slot * P.wpp;
+  const int g = slot / P.np, ks = slot - g * P.np;
+  const int k = P.pid[ks];
+  const int bj = blockIdx.x * P.groups + g;
+  const bool active = bj < P.BJ;
+  float* tab = sm + slot * (W + H);
+  float* red = sm + nslots * (W + H) + slot * P.wpp;
+  float* gs = sm + nslots * (W + H) + nslots * P.wpp + slot * (P.wpp * 3);
+  // large planes (8 float4 of p and of the gradient per lane would not fit 64 registers): the un-projected gradient
+  // waits for the plane-wide sum in shared memory, one conflict-free float4 per lane and slot
+  constexpr bool STASH = PROJECT && NV > 4;
+  float4* stash = reinterpret_cast<float4*>(sm + ((nslots * (W + H) + nslots * P.wpp * 4 + 3) & ~3)) + threadIdx.x;
+
+  float wjs = 0.f, cc = 0.f, cr = 0.f, mc = 0.f, mr = 0.f;
+  bool want_js = false;
+  if (active) {
+    const int b = bj / A.J;
+    const bool is3d = A.valid_depth ? (A.valid_depth[b] != 0) : true;
+    if (A.coef[k]) {
+      wjs = A.coef[k][bj * 3 + 0]; cc = A.coef[k][bj * 3 + 1]; cr = A.coef[k][bj * 3 + 2];
+      mc = A.mu[k] ? A.mu[k][bj * 2 + 0] : 0.f;
+      mr = A.mu[k] ? A.mu[k][bj * 2 + 1] : 0.f;
+      want_js = A.mu[k] != nullptr;
+    } else if (A.target) {
+      const float tx = A.target[bj * 3 + 0], ty = A.target[bj * 3 + 1], tz = A.target[bj * 3 + 2];
+      const float w = A.w[bj];
+      const float dx = A.coords[bj * 3 + 0] - tx, dy = A.coords[bj * 3 + 1] - ty;
+      const float dz = is3d ? A.coords[bj * 3 + 2] - tz : 0.f;
+      const float inv = w / sqrtf(dx * dx + dy * dy + dz * dz);   // infinite at 0, like dsntnn.py:149-150
+      mc = (k == 1) ? tz : tx;
+      mr = (k == 2) ? tz : ty;
+      wjs = (A.pixelwise && (k == 0 || is3d)) ? w : 0.f;
+      cc = (k == 0) ? dx * inv : (k == 1 ? 0.5f * dz * inv : 0.f);
+      cr = (k == 0) ? dy * inv : (k == 2 ? 0.5f * dz * inv : 0.f);
+      want_js = wjs != 0.f;
+    }
+  }
+  const size_t off = (size_t)bj * HW;
+  const int e0 = (s * NV * 32 + lane) * 4;
+  const int h0 = e0 >> wshift;
+  float4 p[NV], d[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = e0 + i * 128;
+    const bool ok = active && e < HW;
+    p[i] = ok ? __ldg(reinterpret_cast<const float4*>(A.prob[k] + off + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (!STASH) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = e0 + i * 128;
+      d[i] = (active && e < HW && A.gup[k]) ? __ldg(reinterpret_cast<const float4*>(A.gup[k] + off + e))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (want_js) gauss_tables(A.g, mc, mr, s, P.wpp, lane, tab, nullptr, gs);
+  __syncthreads();   // #1
+  float ginv = 0.f;
+  float ccw[4], qc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ccw[j] = cc * centre(w0 + j, A.g.cw_step, A.g.cw_first);
+  if (want_js) {
+    float sc = 0.f, sr = 0.f;
+    for (int q = 0; q < P.wpp; ++q) { sc += gs[q * 3]; sr += gs[q * 3 + 1]; }
+    ginv = 1.0f / (sc * sr + KL_EPS);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) qc[j] = tab[w0 + j];
+  }
+  // dJS/dp = 0.5 (ln p' - ln m' + p / p' - m / m'), p' = p + eps, m' = (p + q) / 2 + eps.  eps = 1e-24 is invisible
+  // to fp32 unless p < ~1e-16 (then m may be that small too): the fast form 0.5 ln 2 (lg p - lg(p + q) + 1) is used
+  // for a float4 unless some lane of the warp sees such a p, in which case the warp evaluates the full expression.
+  const float kjs = 0.5f * wjs * LN2, hjs = 0.5f * wjs;
+  const float TINY = 2e-16f;
+  float part = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (e0 + i * 128 < HW) {
+      const int h = h0 + i * rpi;
+      const float lin_r = cr * centre(h, A.g.ch_step, A.g.ch_first);
+      const float pv[4] = {p[i].x, p[i].y, p[i].z, p[i].w};
+      if (STASH)   // the upstream gradient is fetched two slots ahead of its use (L2 / HBM latency)
+        d[i] = A.gup[k] ? __ldg(reinterpret_cast<const float4*>(A.gup[k] + off + e0 + i * 128))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      float dv[4] = {d[i].x, d[i].y, d[i].z, d[i].w};
+      if (want_js) {
+        const float er = tab[W + h] * ginv;
+        const float lin_js = lin_r + kjs;                      // the "+ 1" of lg p - lg(p + q) + 1
+        const bool tiny = fminf(fminf(pv[0], pv[1]), fminf(pv[2], pv[3])) < TINY;
+        if (!__any_sync(0xffffffffu, tiny)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float sq = fmaf(qc[j], er, pv[j]);
+            dv[j] += ccw[j] + lin_js;
+            dv[j] = fmaf(kjs, fast_lg2(pv[j]) - fast_lg2(sq), dv[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float mm = 0.5f * fmaf(qc[j], er, pv[j]);
+            dv[j] += ccw[j] + lin_r;
+            dv[j] = fmaf(kjs, fast_lg2(pv[j] + KL_EPS) - fast_lg2(mm + KL_EPS), dv[j]);
+            dv[j] = fmaf(hjs, __fdividef(pv[j], pv[j] + KL_EPS) - __fdividef(mm, mm + KL_EPS), dv[j]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dv[j] += ccw[j] + lin_r;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part = fmaf(pv[j], dv[j], part);
+      if (STASH) stash[i * blockDim.x] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+      else d[i] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    }
+  }
+  if (PROJECT) {
+    part = warp_sum(part);
+    if (lane == 0) red[s] = part;
+    __syncthreads();   // #2
+    part = 0.f;
+    for (int q = 0; q < P.wpp; ++q) part += red[q];
+    if (!STASH) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        d[i].x = p[i].x * (d[i].x - part); d[i].y = p[i].y * (d[i].y - part);
+        d[i].z = p[i].z * (d[i].z - part); d[i].w = p[i].w * (d[i].w - part);
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int e = e0 + i * 128;
+      if (e < HW) {
+        float4 o = d[i];
+        if (STASH) {
+          const float4 t = stash[i * blockDim.x];
+          o = make_float4(p[i].x * (t.x - part), p[i].y * (t.y - part), p[i].z * (t.z - part), p[i].w * (t.w - part));
+        }
+        *reinterpret_cast<float4*>(A.out[k] + off + e) = o;
+      }
+    }
+  }
+  if (P.seq) __syncthreads();   // the next plane rewrites the tables and partial sums
+  }
+}
+
+// log2(W) when the fast kernels apply (W a power of two dividing 128), else -1
+int fast_shift(int W) {
+  for (int sh = 2; sh <= 7; ++sh)
+    if (W == (1 << sh)) return sh;
+  return -1;
+}
+
 // Chooses warps per plane / pairs per CTA for the warp-sliced kernels; false -> use the block kernels.
 bool plan_warps(int HW, int np, int BJ, WarpPlan* P, int* nv) {
   if (np < 1) return false;
@@ -834,7 +1269,7 @@ bool plan_warps(int HW, int np, int BJ, WarpPlan* P, int* nv) {
 size_t warp_smem(const WarpPlan& P, int H, int W, bool fwd) {
   const int nslots = P.groups * P.np;
   return sizeof(float) * (size_t)(nslots * (fwd ? 2 : 1) * (W + H) + nslots * P.wpp * (fwd ? 5 : 1) +
-                                  (fwd ? nslots * 2 : 0));
+                                  (fwd ? nslots * 2 : 0) + nslots * P.wpp * 3);   // + normaliser / entropy partials (fast kernels)
 }
 
 Geom make_geom(int H, int W, double sigma) {
@@ -863,10 +1298,18 @@ int launch_fwd(const FwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
       const int threads = (P.seq ? 1 : P.groups * P.np) * P.wpp * 32;
       const int blocks = (BJ + P.groups - 1) / P.groups;
       const size_t smem = warp_smem(P, A.g.H, A.g.W, true);
+      const int wsh = g_tail_fast ? fast_shift(A.g.W) : -1;
+#define MP_FWDF(NV) mp_launch(tail_fwd_fast_kernel<NV, FROM_LOGITS>, dim3(blocks), dim3(threads), smem, st, A, P, wsh)
 #define MP_FWDW(NV) mp_launch(tail_fwd_warp_kernel<NV, FROM_LOGITS>, dim3(blocks), dim3(threads), smem, st, A, P)
-      if (nv == 1) MP_FWDW(1); else if (nv == 2) MP_FWDW(2); else if (nv == 4) MP_FWDW(4);
-      else if (nv == 6) MP_FWDW(6); else MP_FWDW(8);
+      if (wsh >= 0) {
+        if (nv == 1) MP_FWDF(1); else if (nv == 2) MP_FWDF(2); else if (nv == 4) MP_FWDF(4);
+        else if (nv == 6) MP_FWDF(6); else MP_FWDF(8);
+      } else {
+        if (nv == 1) MP_FWDW(1); else if (nv == 2) MP_FWDW(2); else if (nv == 4) MP_FWDW(4);
+        else if (nv == 6) MP_FWDW(6); else MP_FWDW(8);
+      }
 #undef MP_FWDW
+#undef MP_FWDF
       return MP_OK;
     }
   }
@@ -903,10 +1346,31 @@ int launch_bwd(const BwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
       const int threads = (P.seq ? 1 : P.groups * P.np) * P.wpp * 32;
       const int blocks = (BJ + P.groups - 1) / P.groups;
       const size_t smem = warp_smem(P, A.g.H, A.g.W, false);
+      const int wsh = g_tail_fast ? fast_shift(A.g.W) : -1;
+      size_t smem_f = smem;
+      if (wsh >= 0 && PROJECT && nv > 4) {   // gradient stash of the large-plane kernels (see tail_bwd_fast_kernel)
+        smem_f = ((smem + 15) & ~(size_t)15) + (size_t)nv * threads * sizeof(float4);
+        static bool attr6 = false, attr8 = false;
+        if (nv == 6 && !attr6) {
+          cudaFuncSetAttribute(tail_bwd_fast_kernel<6, PROJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+          attr6 = true;
+        }
+        if (nv == 8 && !attr8) {
+          cudaFuncSetAttribute(tail_bwd_fast_kernel<8, PROJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+          attr8 = true;
+        }
+      }
+#define MP_BWDF(NV) mp_launch(tail_bwd_fast_kernel<NV, PROJECT>, dim3(blocks), dim3(threads), smem_f, st, A, P, wsh)
 #define MP_BWDW(NV) mp_launch(tail_bwd_warp_kernel<NV, PROJECT>, dim3(blocks), dim3(threads), smem, st, A, P)
-      if (nv == 1) MP_BWDW(1); else if (nv == 2) MP_BWDW(2); else if (nv == 4) MP_BWDW(4);
-      else if (nv == 6) MP_BWDW(6); else MP_BWDW(8);
+      if (wsh >= 0) {
+        if (nv == 1) MP_BWDF(1); else if (nv == 2) MP_BWDF(2); else if (nv == 4) MP_BWDF(4);
+        else if (nv == 6) MP_BWDF(6); else MP_BWDF(8);
+      } else {
+        if (nv == 1) MP_BWDW(1); else if (nv == 2) MP_BWDW(2); else if (nv == 4) MP_BWDW(4);
+        else if (nv == 6) MP_BWDW(6); else MP_BWDW(8);
+      }
 #undef MP_BWDW
+#undef MP_BWDF
       return MP_OK;
     }
   }
