@@ -163,8 +163,8 @@ __device__ __forceinline__ void affine(const mp_bn_args& A, const mp_bn_branch& 
 }
 
 // ------------------------------------------------------------------------------------- forward
-template <bool SPLIT>
-__global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const __grid_constant__ BnGroup GRP) {
+template <bool SPLIT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) bn_fwd_kernel(const __grid_constant__ BnGroup GRP) {
   pdl_trigger();
   pdl_wait();
   const mp_bn_args& A = GRP.a[blockIdx.y];
@@ -238,10 +238,14 @@ __global__ void __launch_bounds__(MAXT, 2) bn_fwd_kernel(const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 8; ++j) z[j] += t[j];
       }
+      if (A.relu_out) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (A.relu_out) z[j] = fmaxf(z[j], 0.f);
-        if (c0 + j >= A.C) z[j] = 0.f;
+        for (int j = 0; j < 8; ++j) z[j] = fmaxf(z[j], 0.f);
+      }
+      if (c0 + 8 > A.C) {   // only the thread that owns the partially filled channel group masks its padding
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j >= A.C) z[j] = 0.f;
       }
       if (A.out) st_act<SPLIT>(A.out, off, A.lo_delta, z);
       if (A.out_nchw) {
@@ -312,17 +316,21 @@ __device__ __forceinline__ void grads_at(const mp_bn_args& A, const LoadsX<NCHW,
       if (!(o[j] > 0.f)) g[j] = 0.f;
   }
   act_unpack<SPLIT>(L.ya, ya);
+  if (c0 + 8 > A.C) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j >= A.C) g[j] = 0.f;
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    if (c0 + j >= A.C) g[j] = 0.f;
     dzb[j] = g[j];
     dza[j] = (A.relu_a && !(fmaf(ya[j], sa[j], ha[j]) > 0.f)) ? 0.f : g[j];
   }
 }
 
 // sums layout per replica: [0] sum dz_a, [1] sum dz_a * y_a, [2] sum dz_b, [3] sum dz_b * y_b
-template <bool NCHW, bool SPLIT>
-__global__ void __launch_bounds__(MAXT, 2) bn_bwd_reduce_kernel(const __grid_constant__ BnGroup GRP) {
+template <bool NCHW, bool SPLIT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) bn_bwd_reduce_kernel(const __grid_constant__ BnGroup GRP) {
   pdl_trigger();
   pdl_wait();
   const mp_bn_args& A = GRP.a[blockIdx.y];
@@ -447,8 +455,8 @@ __device__ __forceinline__ void bwd_coefs(const mp_bn_args& A, const mp_bn_branc
   }
 }
 
-template <bool NCHW, bool SPLIT>
-__global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_kernel(const __grid_constant__ BnGroup GRP) {
+template <bool NCHW, bool SPLIT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) bn_bwd_apply_kernel(const __grid_constant__ BnGroup GRP) {
   pdl_trigger();
   pdl_wait();
   const mp_bn_args& A = GRP.a[blockIdx.y];
@@ -493,13 +501,13 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_kernel(const __grid_cons
       float dza[8], dzb[8], ya[8], o[8];
       grads_at<NCHW, SPLIT>(A, L[i], sa, ha, c0, dza, dzb, ya);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (c0 + j < A.C) ? fmaf(sa[j], dza[j], fmaf(ka[j], ya[j], ca[j])) : 0.f;
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(sa[j], dza[j], fmaf(ka[j], ya[j], ca[j]));   // coefficients are 0 beyond C
       if (A.a.dy) st_act<SPLIT>(A.a.dy, off, A.lo_delta, o);
       if (has_b) {
         float yb[8];
         act_unpack<SPLIT>(L[i].yb, yb);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (c0 + j < A.C) ? fmaf(sb[j], dzb[j], fmaf(kb[j], yb[j], cb[j])) : 0.f;
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(sb[j], dzb[j], fmaf(kb[j], yb[j], cb[j]));
         if (A.b.dy) st_act<SPLIT>(A.b.dy, off, A.lo_delta, o);
       } else if (A.dres) {
         st_act<SPLIT>(A.dres, off, A.lo_delta, dzb);
@@ -615,8 +623,8 @@ int mp_bn_fwd_grouped(const mp_bn_args* args, int n, void* stream) {
   dim3 grid, block;
   launch_dims(args, &grid, &block, U, 2 * 148 / n);
   grid.y = n;
-  if (args->lo_delta) MP_CUDA(mp_launch(bn_fwd_kernel<true>, grid, block, 0, (cudaStream_t)stream, g));
-  else MP_CUDA(mp_launch(bn_fwd_kernel<false>, grid, block, 0, (cudaStream_t)stream, g));
+  if (args->lo_delta) MP_CUDA(mp_launch(bn_fwd_kernel<true, 2>, grid, block, 0, (cudaStream_t)stream, g));
+  else MP_CUDA(mp_launch(bn_fwd_kernel<false, 2>, grid, block, 0, (cudaStream_t)stream, g));
   MP_CHECK_LAUNCH("mp_bn_fwd");
   return MP_OK;
 }
@@ -629,10 +637,10 @@ int mp_bn_bwd_reduce_grouped(const mp_bn_args* args, int n, void* stream) {
   launch_dims(args, &grid, &block, U, n > 1 ? 2 * 148 / n : 148);
   grid.y = n;
   const bool split = args->lo_delta != 0;
-  if (args->dout && split) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<false, true>, grid, block, 0, (cudaStream_t)stream, g));
-  else if (args->dout) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<false, false>, grid, block, 0, (cudaStream_t)stream, g));
-  else if (split) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<true, true>, grid, block, 0, (cudaStream_t)stream, g));
-  else MP_CUDA(mp_launch(bn_bwd_reduce_kernel<true, false>, grid, block, 0, (cudaStream_t)stream, g));
+  if (args->dout && split) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<false, true, 2>, grid, block, 0, (cudaStream_t)stream, g));
+  else if (args->dout) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<false, false, 2>, grid, block, 0, (cudaStream_t)stream, g));
+  else if (split) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<true, true, 2>, grid, block, 0, (cudaStream_t)stream, g));
+  else MP_CUDA(mp_launch(bn_bwd_reduce_kernel<true, false, 2>, grid, block, 0, (cudaStream_t)stream, g));
   MP_CHECK_LAUNCH("mp_bn_bwd_reduce");
   return MP_OK;
 }
@@ -645,10 +653,10 @@ int mp_bn_bwd_apply_grouped(const mp_bn_args* args, int n, void* stream) {
   launch_dims(args, &grid, &block, UA, 2 * 148 / n);
   grid.y = n;
   const bool split = args->lo_delta != 0;
-  if (args->dout && split) MP_CUDA(mp_launch(bn_bwd_apply_kernel<false, true>, grid, block, 0, (cudaStream_t)stream, g));
-  else if (args->dout) MP_CUDA(mp_launch(bn_bwd_apply_kernel<false, false>, grid, block, 0, (cudaStream_t)stream, g));
-  else if (split) MP_CUDA(mp_launch(bn_bwd_apply_kernel<true, true>, grid, block, 0, (cudaStream_t)stream, g));
-  else MP_CUDA(mp_launch(bn_bwd_apply_kernel<true, false>, grid, block, 0, (cudaStream_t)stream, g));
+  if (args->dout && split) MP_CUDA(mp_launch(bn_bwd_apply_kernel<false, true, 2>, grid, block, 0, (cudaStream_t)stream, g));
+  else if (args->dout) MP_CUDA(mp_launch(bn_bwd_apply_kernel<false, false, 2>, grid, block, 0, (cudaStream_t)stream, g));
+  else if (split) MP_CUDA(mp_launch(bn_bwd_apply_kernel<true, true, 2>, grid, block, 0, (cudaStream_t)stream, g));
+  else MP_CUDA(mp_launch(bn_bwd_apply_kernel<true, false, 2>, grid, block, 0, (cudaStream_t)stream, g));
   MP_CHECK_LAUNCH("mp_bn_bwd_apply");
   return MP_OK;
 }

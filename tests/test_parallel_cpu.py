@@ -35,6 +35,16 @@ def _worker(rank, world, port, out):
         want = torch.arange(1000, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
         torch.testing.assert_close(g, want)
         torch.testing.assert_close(extra, torch.tensor([float(sum(range(1, world + 1))), float(world)]))
+        # bucketed path of TrainStep: async sums over the gradient ranges a bucket plan hands out, in plan order;
+        # the 1 / world factor is applied later by the SGD kernel (grad_scale)
+        n_param = 1000
+        plan = parallel.bucket_plan(bwd_marks=[3, 7], stage_ranges=[(100, 400), (400, 900)], n_param=n_param)
+        g2 = torch.arange(n_param, dtype=torch.float32) * (rank + 1)
+        works = [parallel.allreduce_sum_(g2[a:b], async_op=True) for _lo, _hi, ranges in plan for a, b in ranges]
+        for w in works:
+            if w is not None:
+                w.wait()
+        torch.testing.assert_close(g2, torch.arange(n_param, dtype=torch.float32) * sum(range(1, world + 1)))
         lo, hi = parallel.shard_batch(7)
         out.put((rank, lo, hi))
     finally:
@@ -69,3 +79,12 @@ def test_single_process_is_identity():
     g = torch.ones(8)
     assert parallel.allreduce_mean_(g) is g and torch.all(g == 1)
     assert parallel.world() == (0, 1)
+
+
+def test_bucket_plan_covers_every_gradient_once():
+    """Stages finish in reverse order; the last piece (stem backward) carries everything outside the stages."""
+    plan = parallel.bucket_plan(bwd_marks=[2, 5, 9], stage_ranges=[(10, 40), (40, 70), (70, 100)], n_param=130)
+    assert [(lo, hi) for lo, hi, _r in plan] == [(0, 2), (2, 5), (5, 9), (9, None)]
+    assert [r for _lo, _hi, r in plan] == [[(70, 100)], [(40, 70)], [(10, 40)], [(0, 10), (100, 130)]]
+    covered = sorted(i for _lo, _hi, ranges in plan for a, b in ranges for i in range(a, b))
+    assert covered == list(range(130))
