@@ -301,6 +301,38 @@ def tail_sweep(peak_bw, sizes=(32, 64, 128), batch=128):
     return out
 
 
+def precise_mode_bench(dev, batch, steps=8):
+    """The same training step in the bf16x3 arithmetic (bf16 pairs, three tensor-core passes per convolution):
+    the mode whose results match the fp32 reference to ~2e-4 (PARITY.md).  Device-resident inputs, CUDA events."""
+    import torch
+    from margipose_b200.models import create_model
+    from margipose_b200.optim import FlatSGD
+    from margipose_b200.train import TrainStep
+    torch.manual_seed(0)
+    model = create_model(DESC).set_precision('bf16x3').to(dev).train()
+    opt = FlatSGD(model, lr=1e-3, momentum=0.9)
+    step = TrainStep(model, opt, batch=batch, height=RES, width=RES)
+    data = synthetic(batch, 2, seed=300, device=dev)
+    for i in range(step.warmup + 3):
+        step.load(*data[i % 2])
+        step.run()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step.load(*data[i % 2])
+        step.run()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    out = {'precision': 'bf16x3', 'value': batch / (ms * 1e-3), 'unit': 'images/s', 'ms_per_step': ms, 'steps': steps,
+           'batch': batch, 'last_loss': step.loss.item(),
+           'note': 'matches the fp32 reference golden to ~2e-4 in the coordinates (PARITY.md section 2a)'}
+    del step, opt, model
+    torch.cuda.empty_cache()
+    return out
+
+
 def inference_bench(model, dev, batch, reps=50):
     """Eval-mode forward through InferStep (folded BatchNorm, captured graph): batch 1 latency (the reference's
     `margipose infer` / eval_3d.py batch size) and batch `batch` throughput; fp32 NCHW input copied from pinned
@@ -355,7 +387,7 @@ def run_b200(args):
     B, K, W = args.batch or CFG['batch'], args.steps, max(args.warmup, 3)
 
     torch.manual_seed(0)
-    model = create_model(DESC).to(dev).train()
+    model = create_model(DESC).set_precision(args.precision).to(dev).train()
     opt = FlatSGD(model, lr=1e-3, momentum=0.9)
     if world > 1:
         parallel.sync_model(model)
@@ -447,6 +479,9 @@ def run_b200(args):
     infer = None
     if world == 1 and not args.skip_infer:
         infer = inference_bench(model, dev, B)
+    precise = None
+    if world == 1 and not args.skip_precise and args.precision == 'bf16':
+        precise = precise_mode_bench(dev, B)
     cpu = None
     if world == 1 and not args.skip_cpu:
         cpu = cpu_reference(batch=CFG['cpu_batch'], steps=3, warmup=1, budget_s=60.0)
@@ -461,7 +496,7 @@ def run_b200(args):
     value = B * world * K / (ms * 1e-3)
     line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'bf16', 'data': 'synthetic',
+            'dtype': args.precision, 'data': 'synthetic',
             'config': {'workload': '%s, batch %d per GPU, fwd + 3D loss + bwd + SGD-momentum step'
                                    % (CFG['workload'], B),
                        'global_batch': B * world, 'parallelism': 'dp%d' % world,
@@ -470,7 +505,7 @@ def run_b200(args):
             'conv_flops_per_image': FLOPS_PER_IMAGE,
             'conv_tflops_whole_step': value / world * FLOPS_PER_IMAGE / 1e12,
             'roofline': roof, 'tail_roofline': tail, 'cpu_baseline': cpu, 'gpu_library_baseline': gpu_lib,
-            'inference': infer,
+            'inference': infer, 'precise_mode': precise,
             'e2e': {'value': B * world * K / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'last_loss': last},
             'gpu_launches': n_launches, 'clocks': clocks}
@@ -489,6 +524,9 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='images per GPU per step (default: the config\'s)')
     ap.add_argument('--skip-gpu-lib', action='store_true', help='skip the stock-PyTorch-on-GPU comparator')
     ap.add_argument('--skip-infer', action='store_true', help='skip the eval-mode inference measurement')
+    ap.add_argument('--skip-precise', action='store_true', help='skip the bf16x3 (fp32-grade) mode measurement')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3'],
+                    help='engine arithmetic of the measured step (bf16x3: bf16 pairs, fp32-grade results)')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-tail', action='store_true', help='skip the soft-argmax fusion HBM sweep (configs[3])')

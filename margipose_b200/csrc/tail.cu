@@ -16,6 +16,7 @@
 #include "../../include/margipose_b200.h"
 
 long long g_tail_fast = 1;   // tunable "tail_fast": 1 = the log2-domain kernels for row lengths dividing 128
+long long g_tail_waves = 0;  // tunable "tail_ctas_per_sm": persistent CTAs per SM of the fast kernels (0 = one CTA per group)
 
 namespace {
 
@@ -858,12 +859,16 @@ __global__ void __launch_bounds__(512, 2) tail_fwd_fast_kernel(const FwdArgs A, 
   const int nseq = P.seq ? P.np : 1;
   const int w0 = (lane * 4) & (W - 1);                 // this lane's four columns, in every slot
   const int rpi = 128 >> wshift;                       // rows a warp advances per float4 slot
+  // persistent: a CTA walks (sample, joint) groups blockIdx.x, blockIdx.x + gridDim.x, ... -- the slot / pointer
+  // set-up of a warp does not depend on the group and is paid once
+  const int ngroups = (P.BJ + P.groups - 1) / P.groups;
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
   for (int it = 0; it < nseq; ++it) {
   const int slot = P.seq ? it : warp / P.wpp;
   const int s = P.seq ? warp : warp - slot * P.wpp;
   const int g = slot / P.np, ks = slot - g * P.np;
   const int k = P.pid[ks];
-  const int bj = blockIdx.x * P.groups + g;
+  const int bj = grp * P.groups + g;
   const bool active = bj < P.BJ;
   float* tab = sm + slot * 2 * (W + H);                   // ecol[W], erow[H], then their exponents
   float* ltab = tab + (W + H);
@@ -1068,6 +1073,8 @@ __global__ void __launch_bounds__(512, 2) tail_fwd_fast_kernel(const FwdArgs A, 
     A.loss[bj] = A.accumulate ? A.loss[bj] + l : l;
   }
   }
+  __syncthreads();   // the next group rewrites the tables and partial sums the leaders may still be reading
+  }
 }
 
 template <int NV, bool PROJECT>
@@ -1081,12 +1088,14 @@ __global__ void __launch_bounds__(512, 2) tail_bwd_fast_kernel(const BwdArgs A, 
   const int nseq = P.seq ? P.np : 1;
   const int w0 = (lane * 4) & (W - 1);
   const int rpi = 128 >> wshift;
+  const int ngroups = (P.BJ + P.groups - 1) / P.groups;
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {   // persistent, see tail_fwd_fast_kernel
   for (int it = 0; it < nseq; ++it) {
   const int slot = P.seq ? it : warp / P.wpp;
   const int s = P.seq ? warp : warp - slot * P.wpp;
   const int g = slot / P.np, ks = slot - g * P.np;
   const int k = P.pid[ks];
-  const int bj = blockIdx.x * P.groups + g;
+  const int bj = grp * P.groups + g;
   const bool active = bj < P.BJ;
   float* tab = sm + slot * (W + H);
   float* red = sm + nslots * (W + H) + slot * P.wpp;
@@ -1225,8 +1234,19 @@ __global__ void __launch_bounds__(512, 2) tail_bwd_fast_kernel(const BwdArgs A, 
       }
     }
   }
-  if (P.seq) __syncthreads();   // the next plane rewrites the tables and partial sums
+  __syncthreads();   // the next plane / group rewrites the tables and partial sums
   }
+  }
+}
+
+// Grid of the fast kernels: one CTA per (sample, joint) group by default.  The kernels can also walk several groups
+// per CTA (tunable "tail_ctas_per_sm" caps the grid at that many CTAs per SM); measured equal or slower -- the fixed
+// per-plane work is not hoistable within 64 registers and a fresh CTA's loads overlap its predecessor's tail.
+int persistent_blocks(int groups, int threads) {
+  (void)threads;
+  if (g_tail_waves <= 0) return groups;
+  const int cap = 148 * (int)g_tail_waves;
+  return groups < cap ? groups : cap;
 }
 
 // log2(W) when the fast kernels apply (W a power of two dividing 128), else -1
@@ -1299,7 +1319,8 @@ int launch_fwd(const FwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
       const int blocks = (BJ + P.groups - 1) / P.groups;
       const size_t smem = warp_smem(P, A.g.H, A.g.W, true);
       const int wsh = g_tail_fast ? fast_shift(A.g.W) : -1;
-#define MP_FWDF(NV) mp_launch(tail_fwd_fast_kernel<NV, FROM_LOGITS>, dim3(blocks), dim3(threads), smem, st, A, P, wsh)
+      const int pblocks = persistent_blocks(blocks, threads);
+#define MP_FWDF(NV) mp_launch(tail_fwd_fast_kernel<NV, FROM_LOGITS>, dim3(pblocks), dim3(threads), smem, st, A, P, wsh)
 #define MP_FWDW(NV) mp_launch(tail_fwd_warp_kernel<NV, FROM_LOGITS>, dim3(blocks), dim3(threads), smem, st, A, P)
       if (wsh >= 0) {
         if (nv == 1) MP_FWDF(1); else if (nv == 2) MP_FWDF(2); else if (nv == 4) MP_FWDF(4);
@@ -1360,7 +1381,8 @@ int launch_bwd(const BwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
           attr8 = true;
         }
       }
-#define MP_BWDF(NV) mp_launch(tail_bwd_fast_kernel<NV, PROJECT>, dim3(blocks), dim3(threads), smem_f, st, A, P, wsh)
+      const int pblocks = persistent_blocks(blocks, threads);
+#define MP_BWDF(NV) mp_launch(tail_bwd_fast_kernel<NV, PROJECT>, dim3(pblocks), dim3(threads), smem_f, st, A, P, wsh)
 #define MP_BWDW(NV) mp_launch(tail_bwd_warp_kernel<NV, PROJECT>, dim3(blocks), dim3(threads), smem, st, A, P)
       if (wsh >= 0) {
         if (nv == 1) MP_BWDF(1); else if (nv == 2) MP_BWDF(2); else if (nv == 4) MP_BWDF(4);

@@ -282,3 +282,36 @@ def test_bf16x3_inference_and_layerwise():
                tolerance='every block <= 2e-3 free-running vs the fp32 oracle; eval coords 2e-3')
     assert worst[1] < 2e-3
     assert eerr < 2e-3
+
+
+def test_precision_context_stock_pytorch_on_this_gpu():
+    """Context for the tolerances above, logged (PARITY.md): the oracle module itself executed by stock PyTorch on
+    this GPU -- cuDNN fp32, cuDNN TF32 (PyTorch's default convolution arithmetic on this hardware) and bf16
+    autocast -- against the same fp32 CPU reference golden (4-stage ResNet-34, batch 4).  Shows what a reduced
+    precision costs on this randomly initialised, training-mode network independent of who wrote the kernels."""
+    case = [c for c in GOLD if c['name'] == 'r34x4'][0]
+    x, target, mask = model_inputs(case['input_seed'], case['batch'], case.get('res', 256))
+    out = {}
+    try:
+        for name in ('fp32', 'tf32', 'bf16_autocast'):
+            torch.backends.cudnn.allow_tf32 = name != 'fp32'
+            torch.backends.cuda.matmul.allow_tf32 = name != 'fp32'
+            torch.manual_seed(case['weight_seed'])
+            om = M.create_oracle(case['desc']).cuda().train()
+            with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16, enabled=name == 'bf16_autocast'):
+                coords = om(x.cuda()).float()
+                hm = [[h.float() for h in hs] for hs in (om.xy_heatmaps, om.zy_heatmaps, om.xz_heatmaps)]
+            om.xy_heatmaps, om.zy_heatmaps, om.xz_heatmaps = hm
+            loss = D.average_loss(om.forward_3d_losses(coords, target.cuda()), mask.cuda())
+            out[name] = ((coords.cpu() - case['train_coords']).abs().max().item(),
+                         abs(loss.item() - case['loss3'].item()) / case['loss3'].item())
+            del om
+    finally:
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+    for k, (c, l) in out.items():
+        print('stock PyTorch %-14s coords max err %.2e  loss rel err %.2e' % (k, c, l))
+    parity_log('context/stock_pytorch_gpu_r34x4', **{k + '_coords_max_abs_err': v[0] for k, v in out.items()},
+               **{k + '_loss_rel_err': v[1] for k, v in out.items()},
+               tolerance='logged only (fp32 asserted < 2e-3): what cuDNN fp32 / TF32 / bf16-autocast cost on the same case')
+    assert out['fp32'][0] < 2e-3
