@@ -386,6 +386,9 @@ def run_b200(args):
         dist.init_process_group('nccl', device_id=dev)
     B, K, W = args.batch or CFG['batch'], args.steps, max(args.warmup, 3)
 
+    if args.deterministic:
+        from margipose_b200 import utils
+        utils.init_algorithms(deterministic=True)
     torch.manual_seed(0)
     model = create_model(DESC).set_precision(args.precision).to(dev).train()
     opt = FlatSGD(model, lr=1e-3, momentum=0.9)
@@ -500,7 +503,7 @@ def run_b200(args):
             'config': {'workload': '%s, batch %d per GPU, fwd + 3D loss + bwd + SGD-momentum step'
                                    % (CFG['workload'], B),
                        'global_batch': B * world, 'parallelism': 'dp%d' % world,
-                       'cuda_graph': not args.no_graph,
+                       'cuda_graph': not args.no_graph, 'deterministic': bool(args.deterministic),
                        'l2': 'per-step working set (~10 GB of activations) exceeds the 126 MB L2; 4 input sets rotate'},
             'conv_flops_per_image': FLOPS_PER_IMAGE,
             'conv_tflops_whole_step': value / world * FLOPS_PER_IMAGE / 1e12,
@@ -525,6 +528,8 @@ def main():
     ap.add_argument('--skip-gpu-lib', action='store_true', help='skip the stock-PyTorch-on-GPU comparator')
     ap.add_argument('--skip-infer', action='store_true', help='skip the eval-mode inference measurement')
     ap.add_argument('--skip-precise', action='store_true', help='skip the bf16x3 (fp32-grade) mode measurement')
+    ap.add_argument('--deterministic', action='store_true',
+                    help='bit-wise reproducible mode (margipose_b200.utils.init_algorithms(deterministic=True))')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3'],
                     help='engine arithmetic of the measured step (bf16x3: bf16 pairs, fp32-grade results)')
     ap.add_argument('--no-graph', action='store_true')

@@ -277,6 +277,14 @@ MP_API int mp_bn_fwd_grouped(const mp_bn_args* args, int n_problems, void* strea
 MP_API int mp_bn_bwd_reduce_grouped(const mp_bn_args* args, int n_problems, void* stream);
 MP_API int mp_bn_bwd_apply_grouped(const mp_bn_args* args, int n_problems, void* stream);
 
+/* Deterministic mode (tunable "deterministic", mirrors the reference's `init_algorithms(deterministic=True)`,
+ * utils.py:19-24): batch statistics of y = args->a.y as a separate fixed-order pass instead of the conv epilogue's
+ * atomics.  Block r sums its share of the pixels and STORES the partial sums into replica r of a.sum / a.sq
+ * (stat_replicas copies stat_stride floats apart; mp_bn_fwd adds the replicas in order).  Uses a.y, a.sum, a.sq, M, Cp,
+ * stat_replicas, stat_stride, lo_delta. */
+MP_API int mp_bn_stats(const mp_bn_args* args, void* stream);
+MP_API int mp_bn_stats_grouped(const mp_bn_args* args, int n_problems, void* stream);
+
 /* Inference: eval-mode BatchNorm (running statistics) of n layers as per-channel affines
  *   scale[c] = gamma[c] / sqrt(running_var[c] + eps),  shift[c] = beta[c] - (running_mean[c] - conv_bias[c]) * scale[c]
  * (zeros for C <= c < Cp), which mp_conv_igemm applies in its epilogue (ep_scale / ep_shift) -- BatchNorm folded
@@ -383,6 +391,10 @@ MP_API int mp_sgd_step_hp(float* param, const float* grad, float* momentum_buf, 
  *   "igemm_dbg"   : experiment switches, timing only -- results are garbage (1 = no TMA loads, 2 = no MMA, 4 = no epilogue)
  *   "igemm_trace" : device pointer to 64 uint64: CTA (0,0,0) stamps %globaltimer at its phase boundaries (tools/trace_igemm.py)
  *   "pdl"         : 1 (default) = programmatic dependent launch for the kernels of the network chain
+ *   "deterministic": 1 = bit-wise run-to-run reproducible results: mp_conv_wgrad runs without split-K, mp_bn_bwd_reduce
+ *                   launches one block per replica of its sums, mp_combiner_bwd adds its weight-gradient partials in block
+ *                   order; the caller additionally uses mp_bn_stats instead of mp_conv_igemm's stat_sum / bn arguments
+ *                   (the engine does: MargiPoseModel.deterministic / MARGIPOSE_B200_DETERMINISTIC=1).  Default 0.
  *   "wgrad_ctas"  : target CTA count of mp_conv_wgrad (default 148)
  *   "wgrad_halo"  : 1 = up to three row-shifted taps per CTA share the A tile and one halo box of B; 0 (default) = one tap per CTA
  *   "wgrad_slice" : widest column slice of B per CTA when taps are grouped (default 256; 64 or 128 narrow it)

@@ -107,6 +107,8 @@ def _signatures():
         'mp_conv_wgrad_grouped': (I, [ctypes.POINTER(WgradArgs), I, P]),
         'mp_set_tunable': (I, [ctypes.c_char_p, ctypes.c_int64]),
         'mp_bn_fold_eval': (I, [P, I, P]),
+        'mp_bn_stats': (I, [ctypes.POINTER(BnArgs), P]),
+        'mp_bn_stats_grouped': (I, [ctypes.POINTER(BnArgs), I, P]),
         'mp_bn_fwd': (I, [ctypes.POINTER(BnArgs), P]),
         'mp_bn_bwd_reduce': (I, [ctypes.POINTER(BnArgs), P]),
         'mp_bn_bwd_apply': (I, [ctypes.POINTER(BnArgs), P]),

@@ -518,6 +518,44 @@ __global__ void __launch_bounds__(MAXT, MINB) bn_bwd_apply_kernel(const __grid_c
   }
 }
 
+// Batch statistics of one conv output as a separate, run-to-run deterministic pass (deterministic mode: the conv
+// epilogue's atomically accumulated sums are not used).  Block r of a problem sums pixels [r*M/R, (r+1)*M/R) in a
+// fixed order and STORES its partial sums into replica r of sum / sq; mp_bn_fwd adds the replicas in order.
+template <bool SPLIT>
+__global__ void __launch_bounds__(MAXT) bn_stats_kernel(const __grid_constant__ BnGroup GRP) {
+  pdl_trigger();
+  pdl_wait();
+  const mp_bn_args& A = GRP.a[blockIdx.y];
+  __shared__ float red[16 * MAXT];
+  const int cg = threadIdx.x, c0 = cg * 8;
+  const int G = blockDim.x, PY = blockDim.y;
+  const int R = gridDim.x;
+  const long long lo = (long long)blockIdx.x * A.M / R, hi = (long long)(blockIdx.x + 1) * A.M / R;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (long long pix = lo + threadIdx.y; pix < hi; pix += PY) {
+    float v[8];
+    act_unpack<SPLIT>(ld_act<SPLIT>(A.a.y, pix * A.Cp + c0, A.lo_delta), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] += v[j];
+      acc[8 + j] = fmaf(v[j], v[j], acc[8 + j]);
+    }
+  }
+  const int tid = threadIdx.y * G + cg;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) red[j * MAXT + tid] = acc[j];
+  __syncthreads();
+  float* sum = const_cast<float*>(A.a.sum) + (long long)blockIdx.x * A.stat_stride;
+  float* sq = const_cast<float*>(A.a.sq) + (long long)blockIdx.x * A.stat_stride;
+  for (int j = threadIdx.y; j < 16; j += PY) {
+    float s = 0.f;
+    for (int y = 0; y < PY; ++y) s += red[j * MAXT + y * G + cg];
+    (j < 8 ? sum : sq)[c0 + (j & 7)] = s;
+  }
+}
+
 // Eval-mode BatchNorm as a per-channel affine (folded into the producing conv's epilogue, igemm.cu): one block
 // per BatchNorm of the network.
 __global__ void bn_fold_eval_kernel(const mp_bn_fold_entry* __restrict__ table) {
@@ -629,12 +667,39 @@ int mp_bn_fwd_grouped(const mp_bn_args* args, int n, void* stream) {
   return MP_OK;
 }
 
+int mp_bn_stats_grouped(const mp_bn_args* args, int n, void* stream) {
+  MP_CHECK_ARG(args, "mp_bn_stats: null args");
+  MP_CHECK_ARG(n >= 1 && n <= MP_MAX_GROUP, "mp_bn_stats: %d problems (1..%d)", n, MP_MAX_GROUP);
+  BnGroup g;
+  for (int i = 0; i < n; ++i) {
+    const mp_bn_args* a = &args[i];
+    MP_CHECK_ARG(a->a.y && a->a.sum && a->a.sq && a->M > 0 && a->Cp % 8 == 0 && a->Cp / 8 <= MAXT && a->stat_replicas >= 1 &&
+                     a->stat_replicas <= 64 && (a->stat_replicas == 1 || a->stat_stride >= a->Cp),
+                 "mp_bn_stats: bad arguments");
+    MP_CHECK_ARG(i == 0 || (a->M == args[0].M && a->Cp == args[0].Cp && a->stat_replicas == args[0].stat_replicas &&
+                            a->lo_delta == args[0].lo_delta), "mp_bn_stats: problem %d differs in shape", i);
+  }
+  for (int i = 0; i < MP_MAX_GROUP; ++i) g.a[i] = args[i < n ? i : 0];
+  const int G = args->Cp / 8;
+  int py = MAXT / G;
+  if (py < 1) py = 1;
+  dim3 grid((unsigned)args->stat_replicas, (unsigned)n), block(G, py);
+  if (args->lo_delta) MP_CUDA(mp_launch(bn_stats_kernel<true>, grid, block, 0, (cudaStream_t)stream, g));
+  else MP_CUDA(mp_launch(bn_stats_kernel<false>, grid, block, 0, (cudaStream_t)stream, g));
+  MP_CHECK_LAUNCH("mp_bn_stats");
+  return MP_OK;
+}
+int mp_bn_stats(const mp_bn_args* a, void* stream) { return mp_bn_stats_grouped(a, 1, stream); }
+
 int mp_bn_bwd_reduce_grouped(const mp_bn_args* args, int n, void* stream) {
   BnGroup g;
   int rc = make_group(args, n, "mp_bn_bwd_reduce", true, &g);
   if (rc != MP_OK) return rc;
   dim3 grid, block;
-  launch_dims(args, &grid, &block, U, n > 1 ? 2 * 148 / n : 148);
+  int cap = n > 1 ? 2 * 148 / n : 148;
+  // deterministic mode: one block per replica of the sums, so no two blocks ever add into the same address
+  if (mp_deterministic() && cap > args->stat_replicas) cap = args->stat_replicas;
+  launch_dims(args, &grid, &block, U, cap);
   grid.y = n;
   const bool split = args->lo_delta != 0;
   if (args->dout && split) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<false, true, 2>, grid, block, 0, (cudaStream_t)stream, g));

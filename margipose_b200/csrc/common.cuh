@@ -43,6 +43,9 @@ void mp_set_error(const char* fmt, ...);
 // prologue early -- and must call pdl_wait() before it touches memory the predecessor writes or reads;
 // pdl_trigger() lets the NEXT kernel do the same.  Both are no-ops in a normally launched kernel.
 int mp_pdl_enabled();
+// Tunable "deterministic": kernels that combine partial sums with floating-point atomics switch to a fixed order
+// (see include/margipose_b200.h); the launchers read it at launch time.
+int mp_deterministic();
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #ifdef __CUDACC__

@@ -34,10 +34,13 @@ extern long long g_tail_waves;
 
 static long long g_pdl = 1;
 int mp_pdl_enabled() { return g_pdl != 0; }
+static long long g_deterministic = 0;
+int mp_deterministic() { return g_deterministic != 0; }
 
 extern "C" int mp_set_tunable(const char* name, int64_t value) {
   if (!name) { mp_set_error("mp_set_tunable: null name"); return MP_ERR_ARG; }
   if (!strcmp(name, "pdl")) { g_pdl = value; return MP_OK; }
+  if (!strcmp(name, "deterministic")) { g_deterministic = value; return MP_OK; }
   if (!strcmp(name, "igemm_smem")) { mp_set_igemm_smem(value); return MP_OK; }
   if (!strcmp(name, "igemm_split_n")) { mp_set_igemm_split_n(value); return MP_OK; }
   if (!strcmp(name, "igemm_halo")) { mp_set_igemm_halo(value); return MP_OK; }

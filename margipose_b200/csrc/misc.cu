@@ -10,6 +10,27 @@
 
 namespace {
 
+// Deterministic mode of the combiner backward: blocks add their weight-gradient partial sums in block order.
+// A block waits for its turn; every earlier block has been scheduled before it, so the wait cannot deadlock.
+__device__ unsigned int g_combiner_turn = 0;
+__device__ __forceinline__ void ordered_begin(int det) {
+  if (!det) return;
+  if (threadIdx.x == 0) {
+    const unsigned me = blockIdx.y * gridDim.x + blockIdx.x;
+    while (atomicAdd(&g_combiner_turn, 0u) != me) __nanosleep(64);
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void ordered_end(int det) {
+  if (!det) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned me = blockIdx.y * gridDim.x + blockIdx.x;
+    atomicExch(&g_combiner_turn, me + 1 == gridDim.x * gridDim.y ? 0u : me + 1);
+  }
+}
+
 __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
   float2 f;
   f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
@@ -195,7 +216,8 @@ __global__ void __launch_bounds__(256) combiner_bwd_tiled_kernel(const __nv_bflo
                                                                const float* __restrict__ p2, const float* __restrict__ w,
                                                                float* __restrict__ dp0, float* __restrict__ dp1,
                                                                float* __restrict__ dp2, float* __restrict__ dw,
-                                                               int accumulate, int J, int HW, int C, long long lo_delta) {
+                                                               int accumulate, int J, int HW, int C, long long lo_delta,
+                                                               int det) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) float smt[];
@@ -286,6 +308,7 @@ __global__ void __launch_bounds__(256) combiner_bwd_tiled_kernel(const __nv_bflo
       }
     }
   }
+  ordered_begin(det);
   if (dw_active) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -295,6 +318,7 @@ __global__ void __launch_bounds__(256) combiner_bwd_tiled_kernel(const __nv_bflo
         if (k < K) atomicAdd(dw + (cg * 8 + i) * K + k, wacc[i][j]);
       }
   }
+  ordered_end(det);
 }
 
 constexpr int CMB_PIX = 32;
@@ -351,7 +375,8 @@ __global__ void __launch_bounds__(256) combiner_bwd_kernel(const __nv_bfloat16* 
                                                          const float* __restrict__ p2, const float* __restrict__ w,
                                                          float* __restrict__ dp0, float* __restrict__ dp1,
                                                          float* __restrict__ dp2, float* __restrict__ dw,
-                                                         int accumulate, int J, int HW, int C, long long lo_delta) {
+                                                         int accumulate, int J, int HW, int C, long long lo_delta,
+                                                         int det) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
@@ -405,11 +430,13 @@ __global__ void __launch_bounds__(256) combiner_bwd_kernel(const __nv_bfloat16* 
       }
     }
   }
+  ordered_begin(det);
 #pragma unroll
   for (int q = 0; q < CMB_WPT; ++q) {
     const int i = threadIdx.x + q * 256;
     if (i < C * K) atomicAdd(dw + i, wacc[q]);
   }
+  ordered_end(det);
 }
 
 // -------------------------------------------------------------------------------- stem im2col
@@ -667,7 +694,7 @@ int mp_combiner_bwd(const void* dout, const float* const p[3], const float* w, f
     dim3 grid_t((HW + CT_PIX * CT_TILES - 1) / (CT_PIX * CT_TILES), N);
     MP_CUDA(mp_launch(combiner_bwd_tiled_kernel, grid_t, dim3(256), smem_t, (cudaStream_t)stream,
                       (const __nv_bfloat16*)dout, p[0], p[1], p[2], w, dp[0], dp[1], dp[2], dw, accumulate, J, HW, C,
-                      (long long)lo_delta));
+                      (long long)lo_delta, mp_deterministic()));
     MP_CHECK_LAUNCH("mp_combiner_bwd");
     return MP_OK;
   }
@@ -681,7 +708,7 @@ int mp_combiner_bwd(const void* dout, const float* const p[3], const float* w, f
   dim3 grid((HW + CMB_PIX * CMB_TILES - 1) / (CMB_PIX * CMB_TILES), N);
   MP_CUDA(mp_launch(combiner_bwd_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const __nv_bfloat16*)dout, p[0], p[1], p[2], w,
                                                                  dp[0], dp[1], dp[2], dw, accumulate, J, HW, C,
-                                                                 (long long)lo_delta));
+                                                                 (long long)lo_delta, mp_deterministic()));
   MP_CHECK_LAUNCH("mp_combiner_bwd");
   return MP_OK;
 }

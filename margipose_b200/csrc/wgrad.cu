@@ -343,6 +343,9 @@ extern "C" int mp_conv_wgrad_grouped(const mp_wgrad_args* args, int n_problems, 
   int split = (int)(g_wgrad_ctas / (gx * m_tiles * n_problems));
   if (split < 1) split = 1;
   if (split > P.chunks_total) split = P.chunks_total;
+  // deterministic mode: no split-K, every gradient element receives exactly one add per launch (launches that
+  // accumulate into the same tensor are ordered by their stream)
+  if (mp_deterministic()) split = 1;
 
   WgradMaps TM;
   const uint32_t box[5] = {64, (uint32_t)P.kp_w, 1, (uint32_t)P.kp_rows, 1};

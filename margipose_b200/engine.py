@@ -355,9 +355,15 @@ class Engine:
         # (R = 1: the conv epilogue pre-reduces in shared memory and its last CTA finalises the
         # BatchNorm coefficients, so consumers never sum replicas.)  The zeroed-every-step arena also
         # holds the ticket counters: one per BatchNorm (forward) and one per backward reduction.
-        self.R = 1       # forward statistics
-        self.RB = 4      # backward reductions: 148 blocks spread over 4 copies of the sums
-        n_stat = (1 + 2 * self.RB) * self.L.bn_floats
+        # deterministic mode (MargiPoseModel.deterministic, mirrors utils.py:19-24 `init_algorithms(deterministic=True)`):
+        # no floating-point atomics between thread blocks anywhere in the step -- batch statistics come from a
+        # separate fixed-order pass (mp_bn_stats) into R replicas that mp_bn_fwd adds in order, the backward
+        # reductions get one replica per block, weight gradients run without split-K (tunable "deterministic")
+        self.det = bool(getattr(model, 'deterministic', False)) or \
+            os.environ.get('MARGIPOSE_B200_DETERMINISTIC', '0') == '1'
+        self.R = 32 if self.det else 1     # forward statistics
+        self.RB = 32 if self.det else 4    # backward reductions: the blocks spread over RB copies of the sums
+        n_stat = (self.R + 2 * self.RB) * self.L.bn_floats
         self.stats = torch.zeros(n_stat + 2 * self.L.n_bn + 8, device=device)
         self._counter_base = n_stat
         self._n_bwd_ops = 0
@@ -438,7 +444,7 @@ class Engine:
         return captured
 
     # C-ABI entry points with a grouped variant (<name>_grouped(args[], n, stream))
-    GROUPABLE = ('mp_conv_igemm', 'mp_conv_wgrad', 'mp_bn_fwd', 'mp_bn_bwd_reduce', 'mp_bn_bwd_apply')
+    GROUPABLE = ('mp_conv_igemm', 'mp_conv_wgrad', 'mp_bn_fwd', 'mp_bn_bwd_reduce', 'mp_bn_bwd_apply', 'mp_bn_stats')
 
     def _grouped(self, ops):
         """One launch for the same op of the three columns (identical geometry, different tensors)."""
@@ -622,9 +628,10 @@ class Engine:
             br.running_mean, br.running_var = bn.rm.data.data_ptr(), bn.rv.data.data_ptr()
             br.save_mean = vbase + 4 * bn.slot
             br.save_invstd = vbase + 4 * (bn.slot + bn.Cp)
-            if self.training:
+            if self.training and not self.det:      # finalised by the producing conv's last CTA
                 br.scale = self.affine.data_ptr() + 4 * bn.slot
                 br.shift = self.affine.data_ptr() + 4 * (bn.slot + bn.Cp)
+            if self.training:
                 # each BatchNorm is the a- or b-branch of exactly one backward op: 3*Cp coefficients
                 br.coef = self.coefs.data_ptr() + 4 * (3 * bn.slot // 2)
             br.conv_bias = bn.conv_bias.data.data_ptr() if bn.conv_bias is not None else None
@@ -657,7 +664,7 @@ class Engine:
         ho, wo = g.out_hw(h, w)
         y = self.act(n, ho, wo, g.cout_p)
         stats = fin = None
-        if self.training and bn is not None:
+        if self.training and bn is not None and not self.det:
             stats = self.stats_of(bn)
             branch = BnBranch()
             probe = self.bn_args(bn, y)
@@ -665,6 +672,8 @@ class Engine:
             fin = dict(branch=branch, counter=self.stats.data_ptr() + 4 * (self._counter_base + bn.index),
                        channels=bn.C, count=n * ho * wo, momentum=probe.momentum, eps=probe.eps)
         prog += self.conv_ops(lambda: C.conv_forward(g, x, conv.fwd.t, y, stats=stats, bn=fin))
+        if self.training and bn is not None and self.det:    # fixed-order statistics pass over the finished output
+            prog.append(self._launch('mp_bn_stats', self.bn_args(bn, y)))
         return y
 
     def bn_bwd(self, prog, fwd_args, dout=None, dout_nchw=None, dya=None, dyb=None, dres=None):
@@ -1058,6 +1067,7 @@ class Engine:
                 self.x_in.copy_(x)
             self._u8 = False
         self.generation += 1
+        lib().mp_set_tunable(b'deterministic', int(self.det))
         self._fused = bool(fused)
         if fused and self.loss_ctx is None:
             raise MargiposeB200Error('forward(fused=True) needs enable_fused_loss() first')
@@ -1075,6 +1085,7 @@ class Engine:
         """grads[t][k]: fp32 (N, J, h, w) gradient w.r.t. the stage-t plane-k heatmap, or None; grads=None on
         the fused loss path (the tail backward derives the loss gradient itself).  [lo, hi) selects a slice of
         the backward program (see bwd_marks) so a caller can start all-reducing finished parameter ranges."""
+        lib().mp_set_tunable(b'deterministic', int(self.det))
         if lo == 0:
             # backward reductions are atomically accumulated: zero them per backward (a second backward over
             # the same forward -- retain_graph, separate 2D / 3D loss backwards -- must not see the first's sums)

@@ -219,6 +219,11 @@ class MargiPoseModelInner(_Holder):
             self.xz_hm_cnns.append(HeatmapColumn(n_joints, heatmap_space=xz))
 
 
+def utils_default_deterministic():
+    from .. import utils
+    return utils.DETERMINISTIC
+
+
 class _Body(torch.autograd.Function):
     """The whole network body as ONE autograd node: image -> 3 * n_stages probability heatmaps.
     Parameter gradients are accumulated by the engine straight into the flat gradient buffer
@@ -258,6 +263,9 @@ class MargiPoseModel(nn.Module):
         #           convolution is three tensor-core passes over one fp32 accumulator -- results agree with the
         #           reference's fp32 arithmetic to ~1e-4 (PARITY.md) at roughly a third of the speed
         self.precision = precision
+        # run-to-run bit-wise reproducible training steps (the reference's `deterministic` flag, utils.py:19-24):
+        # set before the first forward, or call drop_engines() after changing it
+        self.deterministic = utils_default_deterministic()
         self.data_specs = DataSpecs(
             ImageSpecs(256, mean=ImageSpecs.IMAGENET_MEAN, stddev=ImageSpecs.IMAGENET_STDDEV),
             JointsSpecs(skel_desc, n_dims=3),
