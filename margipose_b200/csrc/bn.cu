@@ -8,8 +8,10 @@
 // is a single pass.  The backward is two passes (per-channel reductions, then the gradient), the
 // minimum for training-mode BatchNorm.  Algorithmic bytes per pixel-channel: forward 2 per input
 // tensor + 2 out; backward reduce 2 per tensor read; apply 2 per tensor read + 2 per gradient.
-#include "common.cuh"
+#include "tc.cuh"
 #include "../../include/margipose_b200.h"
+
+long long g_bn_tma = 1;   // tunable "bn_tma": 1 = the TMA-staged BatchNorm kernels where they apply (plain bf16 NHWC)
 
 namespace {
 
@@ -556,6 +558,328 @@ __global__ void __launch_bounds__(MAXT) bn_stats_kernel(const __grid_constant__ 
   }
 }
 
+
+// =====================================================================================================
+// TMA-staged variants (plain bf16 NHWC tensors, no NCHW side input / output, no split pairs).
+//
+// The register-staged kernels above keep at most two pixel groups per thread in flight (126 registers, 16 warps per
+// SM): ncu shows them latency-bound at 0.4-0.56 of the HBM peak with the same ~20 us per launch for 50 and for 75 MB
+// (profiles/r02_bn_ncu.md).  Here the bytes in flight do not live in registers: every input tensor is streamed
+// through a ring of shared-memory tiles by cp.async.bulk (1-D TMA, a tile = `tp` whole pixel rows = tp * Cp * 2
+// contiguous bytes) completing on mbarriers; one thread issues the copy of tile t + S - 1 while the block consumes
+// tile t (128-bit conflict-free shared-memory reads, results stored straight to global memory), one block barrier per
+// tile hands the slot back.  A block owns a contiguous range of tiles of one problem.
+constexpr int TS_MAX_IN = 4;
+struct TileStreams {
+  const __nv_bfloat16* src[TS_MAX_IN];
+  int n;
+};
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+
+struct TileRing {
+  uint64_t* full;
+  uint8_t* buf;
+  int stages, tile_bytes, tp, Cp;
+  long long M, t_lo, t_hi;
+  __device__ __forceinline__ void init(uint8_t* sm, int stages_, int tp_, const mp_bn_args& A) {
+    full = reinterpret_cast<uint64_t*>(sm);
+    buf = sm + 128;
+    stages = stages_; tp = tp_; Cp = A.Cp; M = A.M;
+    tile_bytes = tp * Cp * 2;
+    const long long tiles = (M + tp - 1) / tp;
+    t_lo = (long long)blockIdx.x * tiles / gridDim.x;
+    t_hi = (long long)(blockIdx.x + 1) * tiles / gridDim.x;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      for (int i = 0; i < stages; ++i) tc::mbar_init(&full[i], 1);
+      tc::mbar_fence_init();
+    }
+  }
+  __device__ __forceinline__ int npix(long long t) const {
+    const long long left = M - t * tp;
+    return left < tp ? (int)left : tp;
+  }
+  __device__ __forceinline__ void issue(long long t, const TileStreams& S) {   // one thread
+    const int s = (int)((t - t_lo) % stages);
+    const uint32_t bytes = (uint32_t)npix(t) * (uint32_t)Cp * 2u;
+    tc::mbar_arrive_expect_tx(&full[s], bytes * (uint32_t)S.n);
+    for (int i = 0; i < S.n; ++i)
+      bulk_load(buf + (size_t)(s * S.n + i) * tile_bytes, S.src[i] + t * tp * Cp, bytes, &full[s]);
+  }
+  __device__ __forceinline__ const __nv_bfloat16* tile(long long t, int n_in, int i) const {
+    const int s = (int)((t - t_lo) % stages);
+    return reinterpret_cast<const __nv_bfloat16*>(buf + (size_t)(s * n_in + i) * tile_bytes);
+  }
+  __device__ __forceinline__ void wait(long long t) {
+    const long long i = t - t_lo;
+    tc::mbar_wait(&full[(int)(i % stages)], (uint32_t)((i / stages) & 1));
+  }
+};
+
+__device__ __forceinline__ void lds8(const __nv_bfloat16* p, float (&v)[8]) {
+  unpack8(*reinterpret_cast<const uint4*>(p), v);
+}
+
+__global__ void __launch_bounds__(MAXT, 2) bn_fwd_tma_kernel(const __grid_constant__ BnGroup GRP, int tp, int stages) {
+  extern __shared__ __align__(128) uint8_t ts_smem[];
+  const mp_bn_args& A = GRP.a[blockIdx.y];
+  TileRing R;
+  R.init(ts_smem, stages, tp, A);
+  pdl_trigger();
+  __syncthreads();
+  pdl_wait();
+  const int c0 = threadIdx.x * 8;
+  const bool has_b = A.b.y != nullptr;
+  const bool lead = threadIdx.x == 0 && threadIdx.y == 0;
+  TileStreams S;
+  S.n = (has_b || A.res) ? 2 : 1;
+  S.src[0] = reinterpret_cast<const __nv_bfloat16*>(A.a.y);
+  S.src[1] = reinterpret_cast<const __nv_bfloat16*>(has_b ? A.b.y : A.res);
+  if (lead)
+    for (long long t = R.t_lo; t < R.t_hi && t < R.t_lo + stages - 1; ++t) R.issue(t, S);
+  float sa[8], ha[8], sb[8], hb[8];
+  affine(A, A.a, c0, false, sa, ha);
+  if (has_b) affine(A, A.b, c0, false, sb, hb);
+  if (blockIdx.x == 0 && threadIdx.y == 0) {   // bookkeeping: saved statistics + running buffers
+    for (int which = 0; which < (has_b ? 2 : 1); ++which) {
+      const mp_bn_branch& br = which ? A.b : A.a;
+      if (br.scale && A.training) continue;     // the producing conv already did it
+      float mean[8], invstd[8], var[8];
+      channel_stats8(A, br, c0, false, mean, invstd, var);
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        if (c >= A.C) continue;
+        if (br.save_mean) {
+          br.save_mean[c] = mean[i];
+          br.save_invstd[c] = invstd[i];
+        }
+        if (A.training && br.running_mean) {
+          const float unbiased = A.M > 1 ? var[i] * ((float)A.M / (float)(A.M - 1)) : var[i];
+          const float bias = br.conv_bias ? br.conv_bias[c] : 0.f;
+          br.running_mean[c] = (1.f - A.momentum) * br.running_mean[c] + A.momentum * (mean[i] + bias);
+          br.running_var[c] = (1.f - A.momentum) * br.running_var[c] + A.momentum * unbiased;
+        }
+      }
+    }
+  }
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(A.out);
+  for (long long t = R.t_lo; t < R.t_hi; ++t) {
+    if (lead && t + stages - 1 < R.t_hi) R.issue(t + stages - 1, S);
+    R.wait(t);
+    const __nv_bfloat16* ta = R.tile(t, S.n, 0);
+    const __nv_bfloat16* tb = R.tile(t, S.n, 1);
+    const int np = R.npix(t);
+    for (int p = threadIdx.y; p < np; p += blockDim.y) {
+      float z[8], u[8];
+      lds8(ta + p * A.Cp + c0, z);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) z[j] = fmaf(z[j], sa[j], ha[j]);
+      if (A.relu_a) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = fmaxf(z[j], 0.f);
+      }
+      if (has_b) {
+        lds8(tb + p * A.Cp + c0, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] += fmaf(u[j], sb[j], hb[j]);
+      } else if (A.res) {
+        lds8(tb + p * A.Cp + c0, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] += u[j];
+      }
+      if (A.relu_out) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[j] = fmaxf(z[j], 0.f);
+      }
+      if (c0 + 8 > A.C) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j >= A.C) z[j] = 0.f;
+      }
+      *reinterpret_cast<uint4*>(out + (t * tp + p) * A.Cp + c0) = pack8(z);
+    }
+    __syncthreads();   // the slot of tile t is free for tile t + stages (issued at the top of the next iteration)
+  }
+}
+
+// Streams of the backward kernels: 0 = dout, 1 = y_a, then y_b (second branch) and the forward output (post-ReLU mask).
+__device__ __forceinline__ void bwd_streams(const mp_bn_args& A, TileStreams& S, int& i_yb, int& i_out) {
+  S.n = 2;
+  S.src[0] = reinterpret_cast<const __nv_bfloat16*>(A.dout);
+  S.src[1] = reinterpret_cast<const __nv_bfloat16*>(A.a.y);
+  i_yb = i_out = -1;
+  if (A.b.y) { i_yb = S.n; S.src[S.n++] = reinterpret_cast<const __nv_bfloat16*>(A.b.y); }
+  if (A.relu_out) { i_out = S.n; S.src[S.n++] = reinterpret_cast<const __nv_bfloat16*>(A.out); }
+}
+
+// dz of both branches at one pixel from the shared-memory tiles (same masks as grads_at)
+__device__ __forceinline__ void grads_smem(const mp_bn_args& A, const __nv_bfloat16* tg, const __nv_bfloat16* tya,
+                                           const __nv_bfloat16* tout, int off, int c0, const float (&sa)[8],
+                                           const float (&ha)[8], float (&dza)[8], float (&dzb)[8], float (&ya)[8]) {
+  float g[8];
+  lds8(tg + off, g);
+  if (tout) {
+    float o[8];
+    lds8(tout + off, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!(o[j] > 0.f)) g[j] = 0.f;
+  }
+  lds8(tya + off, ya);
+  if (c0 + 8 > A.C) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j >= A.C) g[j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    dzb[j] = g[j];
+    dza[j] = (A.relu_a && !(fmaf(ya[j], sa[j], ha[j]) > 0.f)) ? 0.f : g[j];
+  }
+}
+
+__global__ void __launch_bounds__(MAXT, 2) bn_bwd_reduce_tma_kernel(const __grid_constant__ BnGroup GRP, int tp, int stages) {
+  extern __shared__ __align__(128) uint8_t ts_smem[];
+  const mp_bn_args& A = GRP.a[blockIdx.y];
+  TileRing R;
+  R.init(ts_smem, stages, tp, A);
+  pdl_trigger();
+  __syncthreads();
+  pdl_wait();
+  const int cg = threadIdx.x, c0 = cg * 8;
+  const bool has_b = A.b.y != nullptr;
+  const bool lead = threadIdx.x == 0 && threadIdx.y == 0;
+  TileStreams S;
+  int i_yb, i_out;
+  bwd_streams(A, S, i_yb, i_out);
+  if (lead)
+    for (long long t = R.t_lo; t < R.t_hi && t < R.t_lo + stages - 1; ++t) R.issue(t, S);
+  float sa[8], ha[8];
+  affine(A, A.a, c0, true, sa, ha);
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  for (long long t = R.t_lo; t < R.t_hi; ++t) {
+    if (lead && t + stages - 1 < R.t_hi) R.issue(t + stages - 1, S);
+    R.wait(t);
+    const __nv_bfloat16* tg = R.tile(t, S.n, 0);
+    const __nv_bfloat16* tya = R.tile(t, S.n, 1);
+    const __nv_bfloat16* tyb = has_b ? R.tile(t, S.n, i_yb) : nullptr;
+    const __nv_bfloat16* tout = i_out >= 0 ? R.tile(t, S.n, i_out) : nullptr;
+    const int np = R.npix(t);
+    for (int p = threadIdx.y; p < np; p += blockDim.y) {
+      const int off = p * A.Cp + c0;
+      float dza[8], dzb[8], ya[8], yb[8];
+      grads_smem(A, tg, tya, tout, off, c0, sa, ha, dza, dzb, ya);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] += dza[j];
+        acc[8 + j] = fmaf(dza[j], ya[j], acc[8 + j]);
+      }
+      if (has_b) {
+        lds8(tyb + off, yb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[16 + j] += dzb[j];
+          acc[24 + j] = fmaf(dzb[j], yb[j], acc[24 + j]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // block reduction over the pixel rows in the (now idle) tile ring, then one atomic per (sum, channel)
+  float* red = reinterpret_cast<float*>(R.buf);
+  const int G = blockDim.x, PY = blockDim.y;
+  const int tid = threadIdx.y * G + cg;
+  const int nsum = has_b ? 32 : 16;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < nsum) red[j * MAXT + tid] = acc[j];
+  __syncthreads();
+  float* dst = A.sums + (long long)(blockIdx.x % A.stat_replicas) * 4 * A.Cp;
+  for (int j = threadIdx.y; j < nsum; j += PY) {
+    float s = 0.f;
+    for (int y = 0; y < PY; ++y) s += red[j * MAXT + y * G + cg];
+    atomicAdd(dst + (j >> 3) * A.Cp + c0 + (j & 7), s);
+  }
+}
+
+__global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_tma_kernel(const __grid_constant__ BnGroup GRP, int tp, int stages) {
+  extern __shared__ __align__(128) uint8_t ts_smem[];
+  const mp_bn_args& A = GRP.a[blockIdx.y];
+  TileRing R;
+  R.init(ts_smem, stages, tp, A);
+  pdl_trigger();
+  __syncthreads();
+  pdl_wait();
+  const int c0 = threadIdx.x * 8;
+  const bool has_b = A.b.y != nullptr;
+  const bool lead = threadIdx.x == 0 && threadIdx.y == 0;
+  TileStreams S;
+  int i_yb, i_out;
+  bwd_streams(A, S, i_yb, i_out);
+  if (lead)
+    for (long long t = R.t_lo; t < R.t_hi && t < R.t_lo + stages - 1; ++t) R.issue(t, S);
+  const bool first = blockIdx.x == 0 && threadIdx.y == 0;
+  float sa[8], ha[8], ka[8], ca[8], sb[8], kb[8], cb[8];
+  affine(A, A.a, c0, true, sa, ha);
+  float sa2[8];
+  bwd_coefs(A, A.a, 0, c0, sa2, ka, ca, first);
+  if (has_b) bwd_coefs(A, A.b, 1, c0, sb, kb, cb, first);
+  __nv_bfloat16* dya = reinterpret_cast<__nv_bfloat16*>(A.a.dy);
+  __nv_bfloat16* dyb = reinterpret_cast<__nv_bfloat16*>(A.b.dy);
+  __nv_bfloat16* dres = reinterpret_cast<__nv_bfloat16*>(A.dres);
+  for (long long t = R.t_lo; t < R.t_hi; ++t) {
+    if (lead && t + stages - 1 < R.t_hi) R.issue(t + stages - 1, S);
+    R.wait(t);
+    const __nv_bfloat16* tg = R.tile(t, S.n, 0);
+    const __nv_bfloat16* tya = R.tile(t, S.n, 1);
+    const __nv_bfloat16* tyb = has_b ? R.tile(t, S.n, i_yb) : nullptr;
+    const __nv_bfloat16* tout = i_out >= 0 ? R.tile(t, S.n, i_out) : nullptr;
+    const int np = R.npix(t);
+    for (int p = threadIdx.y; p < np; p += blockDim.y) {
+      const int off = p * A.Cp + c0;
+      const long long goff = (t * tp + p) * A.Cp + c0;
+      float dza[8], dzb[8], ya[8], o[8];
+      grads_smem(A, tg, tya, tout, off, c0, sa, ha, dza, dzb, ya);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(sa2[j], dza[j], fmaf(ka[j], ya[j], ca[j]));
+      if (dya) *reinterpret_cast<uint4*>(dya + goff) = pack8(o);
+      if (has_b) {
+        float yb[8];
+        lds8(tyb + off, yb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(sb[j], dzb[j], fmaf(kb[j], yb[j], cb[j]));
+        if (dyb) *reinterpret_cast<uint4*>(dyb + goff) = pack8(o);
+      } else if (dres) {
+        *reinterpret_cast<uint4*>(dres + goff) = pack8(dzb);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Tile size / ring depth of the TMA-staged kernels: ~4 pixels per thread and tile (~16 KB per input tensor; half that
+// with three or four inputs), as many stages as fit ~100 KB (two blocks per SM).
+bool tma_plan(const mp_bn_args* a, int n_in, dim3 block, int* tp, int* stages, size_t* smem) {
+  if (!g_bn_tma || a->lo_delta != 0 || a->out_nchw || a->dout_nchw) return false;
+  const int per_thread = n_in >= 3 ? 2 : 4;
+  *tp = (int)block.y * per_thread;
+  const size_t tile = (size_t)*tp * a->Cp * 2;
+  int s = (int)((100 * 1024) / (tile * n_in));
+  if (s > 8) s = 8;
+  if (s < 2) return false;
+  *stages = s;
+  size_t need = 128 + (size_t)s * n_in * tile;
+  const size_t red = 128 + 32 * MAXT * sizeof(float);   // the reduce kernel reuses the ring for its block reduction
+  *smem = need > red ? need : red;
+  return true;
+}
+
 // Eval-mode BatchNorm as a per-channel affine (folded into the producing conv's epilogue, igemm.cu): one block
 // per BatchNorm of the network.
 __global__ void bn_fold_eval_kernel(const mp_bn_fold_entry* __restrict__ table) {
@@ -661,6 +985,22 @@ int mp_bn_fwd_grouped(const mp_bn_args* args, int n, void* stream) {
   dim3 grid, block;
   launch_dims(args, &grid, &block, U, 2 * 148 / n);
   grid.y = n;
+  {
+    int tp, stages;
+    size_t smem;
+    if (args->out && tma_plan(args, (args->b.y || args->res) ? 2 : 1, block, &tp, &stages, &smem)) {
+      static bool attr = false;
+      if (!attr) {
+        MP_CUDA(cudaFuncSetAttribute(bn_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        attr = true;
+      }
+      const long long tiles = (args->M + tp - 1) / tp;
+      if (grid.x > tiles) grid.x = (unsigned)tiles;
+      MP_CUDA(mp_launch(bn_fwd_tma_kernel, grid, block, smem, (cudaStream_t)stream, g, tp, stages));
+      MP_CHECK_LAUNCH("mp_bn_fwd");
+      return MP_OK;
+    }
+  }
   if (args->lo_delta) MP_CUDA(mp_launch(bn_fwd_kernel<true, 2>, grid, block, 0, (cudaStream_t)stream, g));
   else MP_CUDA(mp_launch(bn_fwd_kernel<false, 2>, grid, block, 0, (cudaStream_t)stream, g));
   MP_CHECK_LAUNCH("mp_bn_fwd");
@@ -701,6 +1041,23 @@ int mp_bn_bwd_reduce_grouped(const mp_bn_args* args, int n, void* stream) {
   if (mp_deterministic() && cap > args->stat_replicas) cap = args->stat_replicas;
   launch_dims(args, &grid, &block, U, cap);
   grid.y = n;
+  {
+    int tp, stages;
+    size_t smem;
+    const int n_in = 2 + (args->b.y ? 1 : 0) + (args->relu_out ? 1 : 0);
+    if (args->dout && tma_plan(args, n_in, block, &tp, &stages, &smem)) {
+      static bool attr = false;
+      if (!attr) {
+        MP_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        attr = true;
+      }
+      const long long tiles = (args->M + tp - 1) / tp;
+      if (grid.x > tiles) grid.x = (unsigned)tiles;
+      MP_CUDA(mp_launch(bn_bwd_reduce_tma_kernel, grid, block, smem, (cudaStream_t)stream, g, tp, stages));
+      MP_CHECK_LAUNCH("mp_bn_bwd_reduce");
+      return MP_OK;
+    }
+  }
   const bool split = args->lo_delta != 0;
   if (args->dout && split) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<false, true, 2>, grid, block, 0, (cudaStream_t)stream, g));
   else if (args->dout) MP_CUDA(mp_launch(bn_bwd_reduce_kernel<false, false, 2>, grid, block, 0, (cudaStream_t)stream, g));
@@ -717,6 +1074,23 @@ int mp_bn_bwd_apply_grouped(const mp_bn_args* args, int n, void* stream) {
   dim3 grid, block;
   launch_dims(args, &grid, &block, UA, 2 * 148 / n);
   grid.y = n;
+  {
+    int tp, stages;
+    size_t smem;
+    const int n_in = 2 + (args->b.y ? 1 : 0) + (args->relu_out ? 1 : 0);
+    if (args->dout && !args->bwd_counter && tma_plan(args, n_in, block, &tp, &stages, &smem)) {
+      static bool attr = false;
+      if (!attr) {
+        MP_CUDA(cudaFuncSetAttribute(bn_bwd_apply_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        attr = true;
+      }
+      const long long tiles = (args->M + tp - 1) / tp;
+      if (grid.x > tiles) grid.x = (unsigned)tiles;
+      MP_CUDA(mp_launch(bn_bwd_apply_tma_kernel, grid, block, smem, (cudaStream_t)stream, g, tp, stages));
+      MP_CHECK_LAUNCH("mp_bn_bwd_apply");
+      return MP_OK;
+    }
+  }
   const bool split = args->lo_delta != 0;
   if (args->dout && split) MP_CUDA(mp_launch(bn_bwd_apply_kernel<false, true, 2>, grid, block, 0, (cudaStream_t)stream, g));
   else if (args->dout) MP_CUDA(mp_launch(bn_bwd_apply_kernel<false, false, 2>, grid, block, 0, (cudaStream_t)stream, g));
