@@ -401,8 +401,9 @@ MP_API int mp_sgd_step_hp(float* param, const float* grad, float* momentum_buf, 
  *   "wgrad_kp"    : pixels per pipeline stage of mp_conv_wgrad (default 128)
  *   "wgrad_smem"  : shared-memory budget of mp_conv_wgrad's pipeline stages in bytes (default 204800)
  *   "wgrad_dbg"   : experiment switches (1 = skip the gradient atomics, 4 = no MMA)
- *   "bn_tma"      : 1 (default) = mp_bn_fwd / mp_bn_bwd_reduce / mp_bn_bwd_apply stream their inputs through shared-memory
- *                   tile rings filled by cp.async.bulk (TMA) where the tensors are plain bf16 NHWC; 0 = register-staged kernels
+ *   "bn_tma"      : bit mask (1 = mp_bn_fwd, 2 = mp_bn_bwd_reduce, 4 = mp_bn_bwd_apply) of the BatchNorm kernels that stream their
+ *                   inputs through shared-memory tile rings filled by cp.async.bulk (TMA) where the tensors are plain bf16
+ *                   NHWC; default 1 (the backward kernels share SMs with the weight-gradient kernels, see csrc/bn.cu)
  *   "tail_fast"   : 1 (default) = mp_tail_fwd / mp_tail_bwd use the log2-domain kernels when the heatmap width divides 128;
  *                   0 = the general warp-sliced kernels
  *   "tail_ctas_per_sm": > 0 caps their grid at that many (persistent) CTAs per SM (default 0 = one CTA per (sample, joint) group) */

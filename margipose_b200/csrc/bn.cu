@@ -11,7 +11,12 @@
 #include "tc.cuh"
 #include "../../include/margipose_b200.h"
 
-long long g_bn_tma = 1;   // tunable "bn_tma": 1 = the TMA-staged BatchNorm kernels where they apply (plain bf16 NHWC)
+// tunable "bn_tma": bit mask of the kernels that use their TMA-staged variant where it applies (plain bf16 NHWC):
+// 1 = forward, 2 = backward reduce, 4 = backward apply.  Default 1: in the training step the backward kernels run
+// beside the weight-gradient kernels of the auxiliary stream (200 KB of shared memory per CTA), and a 100 KB tile ring
+// cannot share an SM with those -- measured: backward program 7.80 ms register-staged vs 8.13 ms TMA-staged, although
+// each TMA kernel alone is 2-5 % faster (tools/step_time.py, tools/bn_time.py).
+long long g_bn_tma = 1;
 
 namespace {
 
@@ -865,8 +870,8 @@ __global__ void __launch_bounds__(MAXT, 2) bn_bwd_apply_tma_kernel(const __grid_
 
 // Tile size / ring depth of the TMA-staged kernels: ~4 pixels per thread and tile (~16 KB per input tensor; half that
 // with three or four inputs), as many stages as fit ~100 KB (two blocks per SM).
-bool tma_plan(const mp_bn_args* a, int n_in, dim3 block, int* tp, int* stages, size_t* smem) {
-  if (!g_bn_tma || a->lo_delta != 0 || a->out_nchw || a->dout_nchw) return false;
+bool tma_plan(const mp_bn_args* a, int which, int n_in, dim3 block, int* tp, int* stages, size_t* smem) {
+  if (!(g_bn_tma & which) || a->lo_delta != 0 || a->out_nchw || a->dout_nchw) return false;
   const int per_thread = n_in >= 3 ? 2 : 4;
   *tp = (int)block.y * per_thread;
   const size_t tile = (size_t)*tp * a->Cp * 2;
@@ -988,7 +993,7 @@ int mp_bn_fwd_grouped(const mp_bn_args* args, int n, void* stream) {
   {
     int tp, stages;
     size_t smem;
-    if (args->out && tma_plan(args, (args->b.y || args->res) ? 2 : 1, block, &tp, &stages, &smem)) {
+    if (args->out && tma_plan(args, 1, (args->b.y || args->res) ? 2 : 1, block, &tp, &stages, &smem)) {
       static bool attr = false;
       if (!attr) {
         MP_CUDA(cudaFuncSetAttribute(bn_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -1045,7 +1050,7 @@ int mp_bn_bwd_reduce_grouped(const mp_bn_args* args, int n, void* stream) {
     int tp, stages;
     size_t smem;
     const int n_in = 2 + (args->b.y ? 1 : 0) + (args->relu_out ? 1 : 0);
-    if (args->dout && tma_plan(args, n_in, block, &tp, &stages, &smem)) {
+    if (args->dout && tma_plan(args, 2, n_in, block, &tp, &stages, &smem)) {
       static bool attr = false;
       if (!attr) {
         MP_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -1078,7 +1083,7 @@ int mp_bn_bwd_apply_grouped(const mp_bn_args* args, int n, void* stream) {
     int tp, stages;
     size_t smem;
     const int n_in = 2 + (args->b.y ? 1 : 0) + (args->relu_out ? 1 : 0);
-    if (args->dout && !args->bwd_counter && tma_plan(args, n_in, block, &tp, &stages, &smem)) {
+    if (args->dout && !args->bwd_counter && tma_plan(args, 4, n_in, block, &tp, &stages, &smem)) {
       static bool attr = false;
       if (!attr) {
         MP_CUDA(cudaFuncSetAttribute(bn_bwd_apply_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
