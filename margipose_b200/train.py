@@ -76,6 +76,11 @@ class TrainStep:
         if self.world > 1 and hasattr(optimizer, 'grad_scale'):
             optimizer.grad_scale = 1.0 / self.world      # the all-reduce sums; the SGD kernel scales
         self._scale_in_opt = self.world > 1 and hasattr(optimizer, 'grad_scale')
+        # host -> device double buffering (prefetch()): two staging slots filled on a copy stream
+        self._copy_stream = None
+        self._slots = []
+        self._staged = {}          # id(images tensor) -> slot index
+        self._next_slot = 0
         # backward program slices [lo, hi) and the flat-gradient ranges that are final after each
         self._pieces = parallel.bucket_plan(self.eng.bwd_marks, self.eng.L.stage_ranges,
                                             model._bank.flat_grad.numel())
@@ -199,11 +204,63 @@ class TrainStep:
                 raise ValueError('per-sample valid_depth flags need the fused loss path')
             self.valid_depth.copy_(torch.as_tensor(valid_depth).to(torch.int32), non_blocking=True)
 
+    def prefetch(self, images, targets, mask=None, valid_depth=None):
+        """Starts the host -> device copy of a LATER batch (pinned host tensors) on a copy stream, so it overlaps
+        the step that is running; the `__call__` that is given the same `images` tensor picks the staged copy up
+        with a device-to-device copy instead of waiting for PCIe.  What a prefetching data loader does; at most
+        two batches can be staged at a time."""
+        dev = self.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            for _ in range(2):
+                slot = dict(x=torch.empty_like(self.x), target=torch.empty_like(self.target),
+                            mask=torch.empty_like(self.mask),
+                            vd=torch.empty_like(self.valid_depth) if self.valid_depth is not None else None,
+                            ready=torch.cuda.Event(), free=torch.cuda.Event(), has_mask=False, has_vd=False)
+                slot['free'].record(torch.cuda.current_stream(dev))
+                self._slots.append(slot)
+        k = self._next_slot
+        self._next_slot ^= 1
+        self._staged = {key: v for key, v in self._staged.items() if v != k}
+        slot = self._slots[k]
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(slot['free'])       # the step that consumed this slot has copied it out
+            slot['x'].copy_(images, non_blocking=True)
+            slot['target'].copy_(targets[..., :3], non_blocking=True)
+            slot['has_mask'] = mask is not None
+            if mask is not None:
+                slot['mask'].copy_(mask, non_blocking=True)
+            slot['has_vd'] = valid_depth is not None
+            if valid_depth is not None:
+                if not self.fused:
+                    raise ValueError('per-sample valid_depth flags need the fused loss path')
+                slot['vd'].copy_(torch.as_tensor(valid_depth).to(torch.int32), non_blocking=True)
+            slot['ready'].record(self._copy_stream)
+        self._staged[id(images)] = k
+
+    def _take_staged(self, images):
+        k = self._staged.pop(id(images), None)
+        if k is None:
+            return False
+        slot = self._slots[k]
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(slot['ready'])
+        self.x.copy_(slot['x'])
+        self.target.copy_(slot['target'])
+        if slot['has_mask']:
+            self.mask.copy_(slot['mask'])
+        if slot['has_vd']:
+            self.valid_depth.copy_(slot['vd'])
+        slot['free'].record(cur)
+        return True
+
     def __call__(self, images, targets, mask=None, valid_depth=None):
-        """Copies one batch in (pinned host tensors copy asynchronously), runs the step and returns
-        the loss as a Python float (a 4-byte device-to-host read, like train_3d.py:167).
+        """Copies one batch in (pinned host tensors copy asynchronously; a batch announced with `prefetch` is
+        already on the device), runs the step and returns the loss as a Python float (a 4-byte device-to-host
+        read, like train_3d.py:167).
         valid_depth: optional per-sample flags, 1 = 3D loss, 0 = 2D loss (bin/train_3d.py:126-142)."""
-        self.load(images, targets, mask, valid_depth)
+        if not self._take_staged(images):
+            self.load(images, targets, mask, valid_depth)
         self.run()
         return self.loss.item()
 

@@ -571,3 +571,36 @@ def test_one_forward_one_backward_contract():
     g2 = model.flat_grads.clone()
     print('second backward over the same forward: rel diff', rel(g2, g1))
     assert rel(g2, g1) < 2e-2            # same sums (atomics reorder them slightly); not doubled
+
+
+def test_train_step_prefetch_is_equivalent_to_direct_loading():
+    """TrainStep.prefetch stages a later batch on a copy stream; the step that is then given the same tensors must
+    see exactly the same data as a step that loads them directly (deterministic mode: bit-identical losses)."""
+    from margipose_b200 import utils
+    from margipose_b200.models import create_model
+    from margipose_b200.optim import FlatSGD
+    from margipose_b200.train import TrainStep
+    desc = {'type': 'margipose', 'version': '6.0.1', 'settings': dict(n_stages=1, feature_extractor='resnet18')}
+    torch.manual_seed(131)
+    state = create_model(desc).state_dict()
+    batches = [tuple(t.pin_memory() for t in model_inputs(140 + i, 2)) for i in range(3)]
+
+    def run(prefetch):
+        utils.init_algorithms(deterministic=True)
+        try:
+            model = create_model(desc)
+        finally:
+            utils.init_algorithms(deterministic=False)
+        model.load_state_dict(state)
+        model = model.cuda().train()
+        step = TrainStep(model, FlatSGD(model, lr=1e-2, momentum=0.9), batch=2, warmup=1)
+        losses = []
+        if prefetch:
+            step.prefetch(*batches[0])
+        for i in range(6):
+            if prefetch and i + 1 < 6:
+                step.prefetch(*batches[(i + 1) % 3])
+            losses.append(step(*batches[i % 3]))
+        return losses
+
+    assert run(True) == run(False)
