@@ -27,12 +27,22 @@ def _nchw(t, c):
     return t[..., :c].float().cpu().permute(0, 3, 1, 2).contiguous()
 
 
+@pytest.fixture(params=[0, 7], ids=['register-staged', 'tma-staged'])
+def bn_tma(request):
+    """Both implementations of the BatchNorm kernels: register-staged and TMA-staged (cp.async.bulk tile rings;
+    tunable "bn_tma" bit mask: forward / backward reduce / backward apply)."""
+    from margipose_b200._lib import lib
+    assert lib().mp_set_tunable(b'bn_tma', request.param) == 0
+    yield request.param
+    lib().mp_set_tunable(b'bn_tma', 1)
+
+
 @pytest.mark.parametrize('C,Cp,mode', [(128, 128, 'rb'), (17, 64, 'rb_logits'), (192, 192, 'act'),
                                        (64, 64, 'basic_id'), (128, 128, 'basic_down')])
-def test_bn_forward_backward(C, Cp, mode):
+def test_bn_forward_backward(C, Cp, mode, bn_tma):
     from margipose_b200 import ops
     gen = torch.Generator().manual_seed(C)
-    n, h, w = 3, 8, 8
+    n, h, w = 3, 24, 24      # 1728 pixels: several tiles per block, a ragged last tile
     ya = _bf(torch.randn(n, C, h, w, generator=gen) * 2 + 0.5)
     yb = _bf(torch.randn(n, C, h, w, generator=gen))
     res = _bf(torch.randn(n, C, h, w, generator=gen))

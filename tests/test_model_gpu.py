@@ -604,3 +604,55 @@ def test_train_step_prefetch_is_equivalent_to_direct_loading():
         return losses
 
     assert run(True) == run(False)
+
+
+def test_forward_loss_mixed_2d_3d_batches_match_the_reference_loop():
+    """bin/train_3d.py:126-142: samples with valid_depth == 1 get the 3D loss, the others the 2D loss; the reference
+    stacks them in a per-sample Python loop.  `train.forward_loss` (flag inside the fused tail kernels) and
+    `TrainStep(..., valid_depth)` against that loop evaluated with the oracle's loss functions on the SAME heatmaps."""
+    from margipose_b200.models import create_model
+    from margipose_b200.optim import FlatSGD
+    from margipose_b200.train import TrainStep, forward_loss
+    desc = {'type': 'margipose', 'version': '6.0.1',
+            'settings': dict(n_stages=2, feature_extractor='resnet18', axis_permutation=True, pixelwise_loss='jsd')}
+    torch.manual_seed(151)
+    model = create_model(desc).cuda().train()
+    x, target, mask = model_inputs(152, 4)
+    mask[1, 5:9] = 0
+    target4 = torch.cat([target, torch.ones(4, 17, 1)], -1)        # the loaders hand over homogeneous (x, y, z, 1)
+    for vd in ([1, 0, 1, 0], [1, 1, 1, 1], [0, 0, 0, 0]):
+        out = model(x.cuda())
+        got = forward_loss(model, out, target4.cuda(), mask.cuda(), vd)
+        hm = [[h.detach().cpu() for h in hs] for hs in (model.xy_heatmaps, model.zy_heatmaps, model.xz_heatmaps)]
+        l3 = D.losses_3d(hm[0], hm[1], hm[2], target, 'jsd')
+        l2 = D.losses_2d(hm[0], hm[1], hm[2], target, 'jsd')
+        want = D.average_loss(torch.stack([l3[i] if vd[i] == 1 else l2[i] for i in range(4)]), mask)
+        print('valid_depth', vd, 'forward_loss', got.item(), 'reference loop', want.item())
+        torch.testing.assert_close(got.detach().cpu(), want, rtol=2e-5, atol=1e-6)
+    # the same flags through the captured training step: first-step loss equals forward_loss on the same weights
+    out = model(x.cuda())
+    want = forward_loss(model, out, target4.cuda(), mask.cuda(), [1, 0, 1, 0]).item()
+    step = TrainStep(model, FlatSGD(model, lr=0.0, momentum=0.9), batch=4, warmup=1)
+    got = [step(x, target4, mask, torch.tensor([1, 0, 1, 0])) for _ in range(3)]
+    print('TrainStep mixed-batch loss', got, 'forward_loss', want)
+    for g in got:      # lr = 0: the parameters never move; training-mode BatchNorm makes every step the same function
+        assert abs(g - want) / want < 2e-3
+
+
+def test_bf16x3_uint8_input_matches_normalised_float_input():
+    """The fused input step (uint8 NHWC -> /255 -> ImageNet normalisation inside the stem gather) in the bf16x3 mode."""
+    from margipose_b200.models import create_model
+    desc = {'type': 'margipose', 'version': '6.0.1',
+            'settings': dict(n_stages=1, feature_extractor='resnet18', precision='bf16x3')}
+    torch.manual_seed(161)
+    model = create_model(desc).cuda().train()
+    g = torch.Generator().manual_seed(7)
+    img = torch.randint(0, 256, (2, 256, 256, 3), generator=g, dtype=torch.uint8)
+    specs = model.data_specs.input_specs
+    mean, std = torch.tensor(specs.mean).view(1, 3, 1, 1), torch.tensor(specs.stddev).view(1, 3, 1, 1)
+    norm = (img.permute(0, 3, 1, 2).float() / 255 - mean) / std
+    with torch.no_grad():
+        a = model(norm.cuda()).clone()
+        b = model(img.cuda()).clone()
+    print('bf16x3: uint8 fused normalisation vs fp32 normalised input: %.3e' % (a - b).abs().max())
+    torch.testing.assert_close(b, a, rtol=0, atol=2e-4)
