@@ -171,7 +171,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    warm = max(1, min(args.warmup, 3))
+    warm = max(1, min(args.warmup, 10))      # the warm-up the driver asks for (a CPU step takes ~1 s)
     base = cpu_reference(batch=CFG['cpu_batch'], steps=max(1, args.steps), warmup=warm, budget_s=150.0)
     line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'images/s', 'n_gpus': args.gpus,
             'steps': base['steps'], 'warmup': warm, 'ms_per_step': base['ms_per_step'], 'higher_is_better': True,
