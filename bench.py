@@ -368,6 +368,63 @@ def inference_bench(model, dev, batch, reps=50):
     return out
 
 
+def cpu_forward_baseline():
+    """BASELINE.json configs[0] / BASELINE.md section 4.4: batch-1 eval forward of the reference algorithm on CPU."""
+    import torch
+    from oracle import model_oracle as M
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    om = M.create_oracle(DESC).eval()
+    x = torch.randn(1, 3, RES, RES)
+    with torch.no_grad():
+        om(x)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            om(x)
+        ms = 1e3 * (time.perf_counter() - t0) / 3
+    return {'batch_1_forward_ms': ms, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '3 eval forwards of batch 1 after 1 warm-up, fp32 oracle port on CPU'}
+
+
+def cpu_tail_baseline(sizes=(32, 64, 128), batch=128):
+    """the reference's tail (flat_softmax + heatmaps_to_coords + 3 x js_reg_losses +
+    euclidean_losses, and its autograd backward) on the host cores at the sweep's shapes, as effective GB/s with the
+    GPU sweep's accounting (8 B per heatmap element forward, 8 + 12 = 20 B forward + backward)."""
+    import torch
+    from oracle import dsnt_oracle as D
+    torch.set_num_threads(os.cpu_count() or 1)
+    out = {'cores': torch.get_num_threads(), 'kind': 'port', 'unit': 'GB/s',
+           'note': 'fp32 oracle port of dsntnn.py on CPU, batch %d x %d joints x 3 planes, best of two calls after one '
+                   'warm-up' % (batch, JOINTS)}
+    g = torch.Generator().manual_seed(0)
+    for S in sizes:
+        z = [torch.randn(batch, JOINTS, S, S, generator=g).requires_grad_() for _ in range(3)]
+        target = torch.rand(batch, JOINTS, 3, generator=g) * 1.6 - 0.8
+        mask = torch.ones(batch, JOINTS)
+
+        def fwd():
+            p = [D.flat_softmax(t) for t in z]
+            return D.average_loss(D.losses_3d([p[0]], [p[1]], [p[2]], target, 'jsd'), mask)
+        fwd()
+        tf = 1e9
+        for _ in range(2):       # (with the autograd graph being recorded, as in the reference's training loop)
+            t0 = time.perf_counter()
+            fwd()
+            tf = min(tf, time.perf_counter() - t0)
+        row = {'fwd_ms': 1e3 * tf, 'fwd_GB/s': 3 * batch * JOINTS * S * S * 8 / tf / 1e9}
+        if S <= 64:     # the autograd graph of the reference tail holds ~10 full-size temporaries per plane
+            fwd().backward()
+            tb = 1e9
+            for _ in range(2):
+                t0 = time.perf_counter()
+                fwd().backward()
+                tb = min(tb, time.perf_counter() - t0)
+            row.update({'fwd_bwd_ms': 1e3 * tb, 'fwd_bwd_GB/s': 3 * batch * JOINTS * S * S * 20 / tb / 1e9})
+        out['heatmap_%d' % S] = row
+        del z
+    return out
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def run_b200(args):
     import torch
@@ -484,9 +541,13 @@ def run_b200(args):
         tail = {'bound': 'hbm', 'unit': 'GB/s', 'peak': peak_bw, 'peak_source': src + ' copy bandwidth (MEASURED_PEAKS.json)',
                 'workload': 'configs[3]: heatmap 32/64/128, 17 joints, batch 128, three planes',
                 'sweep': tail_sweep(peak_bw)}
+        if not args.skip_cpu:
+            tail['cpu_baseline'] = cpu_tail_baseline()
     infer = None
     if world == 1 and not args.skip_infer:
         infer = inference_bench(model, dev, B)
+        if not args.skip_cpu:
+            infer['cpu_baseline'] = cpu_forward_baseline()
     precise = None
     if world == 1 and not args.skip_precise and args.precision == 'bf16':
         precise = precise_mode_bench(dev, B)
