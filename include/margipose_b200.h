@@ -388,6 +388,8 @@ MP_API int mp_sgd_step_hp(float* param, const float* grad, float* momentum_buf, 
  *   "igemm_split_n": mp_conv_igemm halves its N tile when a launch has fewer tiles than this (default 0 = the CTA count)
  *   "igemm_resident": 1 (default) = a CTA keeps its whole weight operand in shared memory across its tiles when it fits
  *   "igemm_astages": activation (halo box) slots in flight when the weights stream (default 3)
+ *   "igemm_prefetch_b": 1 = a CTA requests the first weight tiles of its first work unit before griddepcontrol.wait (the
+ *                   packed weights do not depend on the stream predecessor); 0 (default, faster as measured) = after it
  *   "igemm_dbg"   : experiment switches, timing only -- results are garbage (1 = no TMA loads, 2 = no MMA, 4 = no epilogue)
  *   "igemm_trace" : device pointer to 64 uint64: CTA (0,0,0) stamps %globaltimer at its phase boundaries (tools/trace_igemm.py)
  *   "pdl"         : 1 (default) = programmatic dependent launch for the kernels of the network chain

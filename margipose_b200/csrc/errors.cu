@@ -24,6 +24,7 @@ void mp_set_igemm_split_n(long long v);
 void mp_set_igemm_halo(long long v);
 void mp_set_igemm_pair(long long v);
 void mp_set_igemm_dbg(long long v);
+void mp_set_igemm_prefetch_b(long long v);
 void mp_set_igemm_resident(long long v);
 void mp_set_igemm_astages(long long v);
 void mp_set_igemm_trace(long long v);
@@ -47,6 +48,7 @@ extern "C" int mp_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "igemm_halo")) { mp_set_igemm_halo(value); return MP_OK; }
   if (!strcmp(name, "igemm_pair")) { mp_set_igemm_pair(value); return MP_OK; }
   if (!strcmp(name, "igemm_dbg")) { mp_set_igemm_dbg(value); return MP_OK; }
+  if (!strcmp(name, "igemm_prefetch_b")) { mp_set_igemm_prefetch_b(value); return MP_OK; }
   if (!strcmp(name, "igemm_resident")) { mp_set_igemm_resident(value); return MP_OK; }
   if (!strcmp(name, "igemm_astages")) { mp_set_igemm_astages(value); return MP_OK; }
   if (!strcmp(name, "igemm_trace")) { mp_set_igemm_trace(value); return MP_OK; }

@@ -66,6 +66,7 @@ struct IgemmParams {
   int a_tx_plain, a_tx_halo, row_bytes;
   int resident;  // 1: the CTA's whole weight operand stays in shared memory (one slot per tap and channel block,
                  // loaded with the first tile); later tiles stream activations only
+  int prefetch_b;   // 1: request the first weight tiles before griddepcontrol.wait (tunable igemm_prefetch_b)
   int dbg;       // experiment switches (tunable igemm_dbg): 1 = no TMA loads, 2 = no MMA, 4 = no epilogue
   unsigned long long* trace;   // tunable igemm_trace: device buffer of 64 timestamps written by CTA (0,0,0), or NULL
   long long out_sn, out_sh, out_sw;
@@ -201,12 +202,38 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
   if (PAIR) tc::cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_holder;
+  // The packed weights are not produced by the stream predecessor (mp_pack_weights ran long before), so the first
+  // weight tiles of this CTA's first work unit may be requested BEFORE the dependency wait: they land while the
+  // previous kernel drains.  pre_b = weight-tile loads already issued, in the producer loop's (group, block, tap) order.
+  int pre_b = 0;
+  if (warp == 0 && u_begin < u_end && P.prefetch_b && !(P.dbg & 1)) {
+    const TileCoord T = decode_tile(P, u_begin * STEP + (int)crank);
+    const int b_row0 = T.n0 + (int)crank * (P.b_slot_bytes >> 7);
+    for (int g = 0; g < P.n_groups && pre_b < P.b_stages; ++g) {
+      const TapGroup& G = P.groups[g];
+      for (int cb = 0; cb < P.cblocks && pre_b < P.b_stages; ++cb) {
+        for (int i = 0; i < G.n && pre_b < P.b_stages; ++i) {
+          uint8_t* dstB = sB + (size_t)pre_b * P.b_slot_bytes;
+          if (tc::elect_one()) {
+            if (PAIR) {
+              if (crank == 0) tc::mbar_arrive_expect_tx(&fullB[pre_b], 2u * (uint32_t)P.b_slot_bytes);
+              tc::tma_load_2d_pair(&tmB, &fullB[pre_b], dstB, G.koff[i] + cb * 64, b_row0);
+            } else {
+              tc::mbar_arrive_expect_tx(&fullB[pre_b], (uint32_t)P.b_slot_bytes);
+              tc::tma_load_2d(&tmB, &fullB[pre_b], dstB, G.koff[i] + cb * 64, b_row0);
+            }
+          }
+          ++pre_b;
+        }
+      }
+    }
+  }
   pdl_wait();   // everything above overlapped the previous kernel's tail; its results are visible from here on
   if (threadIdx.x == 0) trace_at(P, 1);
 
   if (warp == 0) {
     {   // ------------------------------------------- TMA producer: warp-uniform loops, one elected lane issues
-      int sa = 0, sb = 0;
+      int sa = 0, sb = 0, b_issued = 0;
       uint32_t pha = 0, phb = 0;
       for (int u = u_begin; u < u_end; ++u) {
         const TileCoord T = decode_tile(P, u * STEP + (int)crank);
@@ -232,6 +259,11 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
             }
             if (++sa == P.a_stages) { sa = 0; pha ^= 1; }
             for (int i = 0; i < G.n && load_b; ++i) {
+              if (b_issued < pre_b) {   // requested before the dependency wait (first ring pass: the slot was free)
+                ++b_issued;
+                if (++sb == P.b_stages) { sb = 0; phb ^= 1; }
+                continue;
+              }
               if (!P.resident) tc::mbar_wait(&emptyB[sb], phb ^ 1);
               uint8_t* dstB = sB + (size_t)sb * P.b_slot_bytes;
               if (!tc::elect_one()) {
@@ -487,6 +519,9 @@ long long g_igemm_resident = 1;    // keep the weight operand in shared memory a
 long long g_igemm_ctas = 0;        // CTAs per launch (0 = the device's SM count)
 long long g_igemm_halo = 1;        // group taps that differ only in their row shift (one halo box per group)
 long long g_igemm_dbg = 0;
+// first weight tiles requested before the programmatic-dependency wait: measured 2 % SLOWER in the step (serial igemm
+// 5.39 -> 5.50 ms; the early loads compete with the predecessor's tail and lengthen the prologue), hence off
+long long g_igemm_prefetch_b = 0;
 long long g_igemm_trace = 0;
 long long g_igemm_pair = 1;        // CTA pairs (cta_group::2) when the M tiles pair up
 long long g_igemm_split_n = 0;     // split N in two when a launch has fewer tiles than this (0 = the CTA count)
@@ -577,6 +612,7 @@ void mp_set_igemm_smem(long long v) { g_igemm_smem = v; }
 void mp_set_igemm_halo(long long v) { g_igemm_halo = v; }
 void mp_set_igemm_pair(long long v) { g_igemm_pair = v; }
 void mp_set_igemm_dbg(long long v) { g_igemm_dbg = v; }
+void mp_set_igemm_prefetch_b(long long v) { g_igemm_prefetch_b = v; }
 void mp_set_igemm_trace(long long v) { g_igemm_trace = v; }
 void mp_set_igemm_resident(long long v) { g_igemm_resident = v; }
 void mp_set_igemm_astages(long long v) { g_igemm_astages = v < 2 ? 2 : v; }
@@ -738,6 +774,7 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
   }
   P.b_slot_bytes = (P.n_tile / (pair ? 2 : 1)) * 128;
   P.dbg = (int)g_igemm_dbg;
+  P.prefetch_b = (int)g_igemm_prefetch_b;
   P.trace = reinterpret_cast<unsigned long long*>(g_igemm_trace);
 
   // shared-memory rings: with halo groups each activation box feeds up to three weight tiles
