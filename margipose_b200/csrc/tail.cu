@@ -828,6 +828,24 @@ __device__ __forceinline__ float fast_lg2(float x) {
   return y;
 }
 
+// Sum / max of the `wpp` per-warp partials p[0], p[stride], ...: a short serial loop, or -- many warps per plane --
+// one partial per lane and a shuffle tree (10 instead of ~4 * wpp instructions).  Both orders are fixed.
+__device__ __forceinline__ float cross_warp_sum(const float* p, int stride, int wpp, int lane) {
+  if (wpp <= 4) {
+    float s = 0.f;
+    for (int q = 0; q < wpp; ++q) s += p[q * stride];
+    return s;
+  }
+  return warp_sum(lane < wpp ? p[lane * stride] : 0.f);
+}
+__device__ __forceinline__ float cross_warp_max(const float* p, int stride, int wpp, int lane, float m) {
+  if (wpp <= 4) {
+    for (int q = 0; q < wpp; ++q) m = fmaxf(m, p[q * stride]);
+    return m;
+  }
+  return warp_max(lane < wpp ? p[lane * stride] : -INFINITY);
+}
+
 // Gaussian factor tables of one plane, computed ONCE by the plane's warps together (entry i by warp i / 32):
 // tab[0..W) = column factors, tab[W..W+H) = row factors, ltab = their exponents (natural log), and per-warp partial
 // sums for the normaliser in gs[warp * 3 + {0, 1}] (slot 2: the forward kernel's entropy partial).
@@ -917,9 +935,7 @@ __global__ void __launch_bounds__(512, 2) tail_fwd_fast_kernel(const FwdArgs A, 
   }
   __syncthreads();   // #1: Gaussian factors + per-warp maxima visible
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accx = 0.f;
-  if (FROM_LOGITS) {
-    for (int q = 0; q < P.wpp; ++q) m = fmaxf(m, red[q * 4 + 3]);
-  }
+  if (FROM_LOGITS) m = cross_warp_max(red + 3, 4, P.wpp, lane, m);
   const float m2 = m * L2E;
   {
     float cw[4];
@@ -970,8 +986,10 @@ __global__ void __launch_bounds__(512, 2) tail_fwd_fast_kernel(const FwdArgs A, 
     if (FROM_LOGITS) gs[s * 3 + 2] = accx;
   }
   __syncthreads();   // #2
-  acc0 = acc1 = acc2 = accx = 0.f;
-  for (int q = 0; q < P.wpp; ++q) { acc0 += red[q * 4 + 0]; acc1 += red[q * 4 + 1]; acc2 += red[q * 4 + 2]; }
+  accx = 0.f;
+  acc0 = cross_warp_sum(red + 0, 4, P.wpp, lane);
+  acc1 = cross_warp_sum(red + 1, 4, P.wpp, lane);
+  acc2 = cross_warp_sum(red + 2, 4, P.wpp, lane);
   float ea, eb;
   float inv = 1.f, l2inv = 0.f;
   if (FROM_LOGITS) {
@@ -988,8 +1006,7 @@ __global__ void __launch_bounds__(512, 2) tail_fwd_fast_kernel(const FwdArgs A, 
   // log(.) only where p or q < 1e-17, where p lg p and q lg q vanish in fp32 anyway.)
   float jsp = 0.f;
   if (want_js) {
-    float sc = 0.f, sr = 0.f;
-    for (int q = 0; q < P.wpp; ++q) { sc += gs[q * 3]; sr += gs[q * 3 + 1]; }
+    const float sc = cross_warp_sum(gs + 0, 3, P.wpp, lane), sr = cross_warp_sum(gs + 1, 3, P.wpp, lane);
     const float ginv = 1.0f / (sc * sr + KL_EPS);
     float qc[4];
 #pragma unroll
@@ -1024,9 +1041,7 @@ __global__ void __launch_bounds__(512, 2) tail_fwd_fast_kernel(const FwdArgs A, 
     }
     jsp = warp_sum(jsp);
     if (FROM_LOGITS && s == 0) {   // sum p lg p = (sum exp(t) t2) / sum exp(t) - log2(sum exp(t))
-      float ex = 0.f;
-      for (int q = 0; q < P.wpp; ++q) ex += gs[q * 3 + 2];
-      jsp += fmaf(ex, inv, l2inv);
+      jsp += fmaf(cross_warp_sum(gs + 2, 3, P.wpp, lane), inv, l2inv);
     }
     jsp *= LN2;
   } else if (FROM_LOGITS) {
@@ -1154,8 +1169,7 @@ __global__ void __launch_bounds__(512, 2) tail_bwd_fast_kernel(const BwdArgs A, 
 #pragma unroll
   for (int j = 0; j < 4; ++j) ccw[j] = cc * centre(w0 + j, A.g.cw_step, A.g.cw_first);
   if (want_js) {
-    float sc = 0.f, sr = 0.f;
-    for (int q = 0; q < P.wpp; ++q) { sc += gs[q * 3]; sr += gs[q * 3 + 1]; }
+    const float sc = cross_warp_sum(gs + 0, 3, P.wpp, lane), sr = cross_warp_sum(gs + 1, 3, P.wpp, lane);
     ginv = 1.0f / (sc * sr + KL_EPS);
 #pragma unroll
     for (int j = 0; j < 4; ++j) qc[j] = tab[w0 + j];
@@ -1210,8 +1224,7 @@ __global__ void __launch_bounds__(512, 2) tail_bwd_fast_kernel(const BwdArgs A, 
     part = warp_sum(part);
     if (lane == 0) red[s] = part;
     __syncthreads();   // #2
-    part = 0.f;
-    for (int q = 0; q < P.wpp; ++q) part += red[q];
+    part = cross_warp_sum(red, 1, P.wpp, lane);
     if (!STASH) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
