@@ -112,7 +112,7 @@ MP_API int mp_make_gauss(const float* mu, float* out, int normalize, double sigm
  *   stride 2:  dims (2C, W/2, 2, H/2, N) over the same memory; a tap picks the column parity
  *              through c0 (0 or C) and the row parity through p.
  */
-#define MP_MAX_TAPS 10
+#define MP_MAX_TAPS 30   /* a 3x3 conv in split (bf16x3) mode: 9 taps x (hi*hi, lo*hi, hi*lo) */
 #define MP_MAX_GROUP 3   /* problems per grouped launch (the three HeatmapColumns of a stage) */
 
 typedef struct mp_view5 {
@@ -177,10 +177,10 @@ typedef struct mp_igemm_args {
   int32_t ep_relu;
   /* Split ("bf16x3") precision mode, lo_delta > 0: every activation VALUE is a pair of bf16 tensors, hi = bf16(v) and
    * lo = bf16(v - hi) stored lo_delta ELEMENTS after hi (~16 significant bits; see DESIGN.md "Precision modes").
-   * out, res and acc_in are such pairs.  A convolution is then three launches over the same accumulator,
-   *   x_hi * W_hi,   x_lo * W_hi (acc_in = out),   x_hi * W_lo (acc_in = out; + res, statistics, affine)
-   * i.e. the epilogue computes  out = relu2?( relu1?((acc + acc_in) * scale + shift) + res )  on fp32 values and
-   * stores the pair.  The BatchNorm statistics are those of the stored pair sums.  lo_delta == 0: plain bf16. */
+   * out, res and acc_in are such pairs.  A convolution accumulates x_hi * W_hi + x_lo * W_hi + x_hi * W_lo: in ONE launch
+   * when the tripled tap list fits MP_MAX_TAPS (src[0] = x_hi, src[1] = x_lo, wmat = [rows][K_hi | K_lo]), otherwise in
+   * three launches chained through acc_in; the epilogue computes
+   *   out = relu2?( relu1?((acc + acc_in) * scale + shift) + res )  on fp32 values and stores the pair.  The BatchNorm statistics are those of the stored pair sums.  lo_delta == 0: plain bf16. */
   const void* acc_in;
   int64_t lo_delta;
 } mp_igemm_args;
@@ -347,8 +347,8 @@ MP_API int mp_add_bf16(const void* const in[4], int n, void* out, int64_t count,
  * zero-filled.  Entry e fills the [rows_p][taps][cols_p] block
  *   packed[dst_off + r*dst_row_stride + t*cols_p + c] = transpose ? src[c][t][r] : src[r][t][c]
  * (src = master + src_off, fp32 [A][taps][B]); a row stride larger than taps*cols_p lets two layers
- * share one matrix along K (fused data gradient of a residual block).  lo_delta > 0 (split mode): the rounding
- * residual bf16(w - bf16(w)) of every element is written lo_delta elements after it (the W_lo operand). */
+ * share one matrix along K (fused data gradient of a residual block).  lo_off > 0 (split mode): the rounding
+ * residual bf16(w - bf16(w)) of every element is written lo_off elements after it (the W_lo operand). */
 typedef struct mp_pack_entry {
   int64_t src_off;         /* elements into `master` */
   int64_t dst_off;         /* elements into `packed` */
@@ -358,9 +358,11 @@ typedef struct mp_pack_entry {
   int32_t A, B, taps;      /* source extents */
   int32_t transpose;
   int32_t rows_p, cols_p;  /* padded destination extents (cols_p % 8 == 0) */
+  int64_t lo_off;          /* > 0: also write the rounding residual bf16(w - bf16(w)) lo_off elements after every element
+                              (split mode: the matrix is [rows][K_hi | K_lo], lo_off = K of that matrix); 0 = none */
 } mp_pack_entry;
 MP_API int mp_pack_weights(const float* master, void* packed, const mp_pack_entry* table,
-                           int n_entries, int64_t total_work, int64_t lo_delta, void* stream);
+                           int n_entries, int64_t total_work, void* stream);
 
 /* torch.optim.SGD step over flat fp32 buffers (momentum buffer initialised on first_step):
  *   g = grad*grad_scale + wd*p;  buf = first ? g : mom*buf + (1-dampening)*g;

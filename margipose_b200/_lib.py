@@ -17,7 +17,7 @@ c_void_p = ctypes.c_void_p
 c_size_t = ctypes.c_size_t
 PlaneTable = ctypes.c_void_p * 3
 
-MP_MAX_TAPS = 10
+MP_MAX_TAPS = 30
 
 
 class View5(ctypes.Structure):
@@ -79,7 +79,7 @@ class PackEntry(ctypes.Structure):
                 ('dst_row_stride', ctypes.c_int64), ('work_off', ctypes.c_int64),
                 ('work_end', ctypes.c_int64), ('A', ctypes.c_int32), ('B', ctypes.c_int32),
                 ('taps', ctypes.c_int32), ('transpose', ctypes.c_int32), ('rows_p', ctypes.c_int32),
-                ('cols_p', ctypes.c_int32)]
+                ('cols_p', ctypes.c_int32), ('lo_off', ctypes.c_int64)]
 
 
 _lib = None
@@ -124,7 +124,7 @@ def _signatures():
         'mp_stem_im2col_u8': (I, [P, P, ctypes.POINTER(ctypes.c_float * 3), ctypes.POINTER(ctypes.c_float * 3),
                                   I, I, I, ctypes.c_int64, P]),
         'mp_add_bf16': (I, [ctypes.POINTER(c_void_p * 4), I, P, ctypes.c_int64, ctypes.c_int64, P]),
-        'mp_pack_weights': (I, [P, P, P, I, ctypes.c_int64, ctypes.c_int64, P]),
+        'mp_pack_weights': (I, [P, P, P, I, ctypes.c_int64, P]),
         'mp_sgd_step': (I, [P, P, P, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                             ctypes.c_float, I, I, ctypes.c_float, P]),
         'mp_sgd_step_hp': (I, [P, P, P, ctypes.c_int64, ctypes.c_float, ctypes.c_float, ctypes.c_float,

@@ -152,27 +152,41 @@ def _fill_taps(args, taps):
 
 def _igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_c, res=None,
            stats=None, out_offset=0, bn=None, defer=None, ep=None):
-    """One convolution accumulation: a single launch, or -- split precision mode -- three passes
-    x_hi * W_hi, x_lo * W_hi, x_hi * W_lo chained through `acc_in`; residual, statistics, BatchNorm
-    finalize and epilogue affine belong to the last one."""
+    """One convolution accumulation.  Split precision mode: x_hi * W_hi + x_lo * W_hi + x_hi * W_lo, where `wmat` is
+    [rows][K_hi | K_lo] (the W_lo taps read K columns further).  With one source and a tripled tap list that fits
+    MP_MAX_TAPS it is ONE launch over the sources (x_hi, x_lo); otherwise (the fused data gradient of a residual
+    block has two sources already) three passes chained through `acc_in`, with residual, statistics, BatchNorm
+    finalize and epilogue affine on the last one."""
     S = SPLIT
     if S is None:
         return _igemm_one(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_c, res=res,
                           stats=stats, out_offset=out_offset, bn=bn, defer=defer, ep=ep)
-    common = (taps, cblocks, n_img, out_h, out_w, out, out_strides, out_c)
+    assert wmat.shape[1] % 2 == 0
+    k_half = wmat.shape[1] // 2
+    common = (cblocks, n_img, out_h, out_w, out, out_strides, out_c)
     out_lo = S.lo(out)
     res_lo = S.lo(res) if res is not None else None
+    lo_taps = [(src, c0, dw, p, dh, koff + k_half) for (src, c0, dw, p, dh, koff) in taps]
+    if len(srcs) == 1 and 3 * len(taps) <= MP_MAX_TAPS:
+        (x, par), = srcs
+        fused = list(taps) + [(1, c0, dw, p, dh, koff) for (_s, c0, dw, p, dh, koff) in taps] + lo_taps
+        flop_channels = _FLOP_CHANNELS[0]
+        _FLOP_CHANNELS[0] = flop_channels / 3.0        # algorithmic FLOPs: the convolution once
+        _igemm_one([(x, par), (S.lo(x), par)], wmat, fused, *common, res=res, res_lo=res_lo, stats=stats,
+                   out_offset=out_offset, bn=bn, defer=defer, ep=ep, out_lo=out_lo)
+        _FLOP_CHANNELS[0] = flop_channels
+        return
     # a residual that aliases the output (in-place accumulation) must be read before the first pass overwrites it
     first = dict(res=res, res_lo=res_lo) if (res is not None and res.data_ptr() == out.data_ptr()) else {}
     assert not (first and ep is not None), 'an in-place residual cannot be combined with an epilogue affine'
     last = {} if first else dict(res=res, res_lo=res_lo)
     flop_channels = _FLOP_CHANNELS[0]
     _FLOP_CHANNELS[0] = 0          # algorithmic FLOPs are counted once, on the last pass
-    _igemm_one(srcs, wmat, *common, out_offset=out_offset, defer=defer, out_lo=out_lo, **first)
-    _igemm_one([(S.lo(t), par) for t, par in srcs], wmat, *common, out_offset=out_offset, defer=defer,
+    _igemm_one(srcs, wmat, taps, *common, out_offset=out_offset, defer=defer, out_lo=out_lo, **first)
+    _igemm_one([(S.lo(t), par) for t, par in srcs], wmat, taps, *common, out_offset=out_offset, defer=defer,
                out_lo=out_lo, acc_in=out)
     _FLOP_CHANNELS[0] = flop_channels
-    _igemm_one(srcs, S.lo(wmat), *common, stats=stats, out_offset=out_offset, bn=bn, defer=defer, ep=ep,
+    _igemm_one(srcs, wmat, lo_taps, *common, stats=stats, out_offset=out_offset, bn=bn, defer=defer, ep=ep,
                out_lo=out_lo, acc_in=out, **last)
 
 
@@ -288,7 +302,8 @@ def conv_forward(g, x, wpack, out, stats=None, res=None, bn=None, ep=None):
     statistics (optionally `replicas` copies `stride` floats apart to spread the atomics)."""
     n, h, w, _ = x.shape
     ho, wo = g.out_hw(h, w)
-    assert tuple(out.shape) == (n, ho, wo, g.cout_p) and tuple(wpack.shape) == g.fwd_pack_shape()
+    assert tuple(out.shape) == (n, ho, wo, g.cout_p)
+    assert tuple(wpack.shape) == (g.cout_p, g.taps * g.cin_p * (2 if SPLIT is not None else 1))
     cb = g.cin_p // 64
     _FLOP_CHANNELS[0] = g.cin * g.cout
     if not g.transposed:

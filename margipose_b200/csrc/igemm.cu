@@ -51,7 +51,7 @@ struct TapGroup {
 };
 
 struct alignas(64) IgemmMaps {   // TMA descriptors per problem: activation sources (plain / halo box) and weights
-  CUtensorMap a0[MP_MAX_GROUP], a0h[MP_MAX_GROUP], a1[MP_MAX_GROUP], b[MP_MAX_GROUP];
+  CUtensorMap a0[MP_MAX_GROUP], a0h[MP_MAX_GROUP], a1[MP_MAX_GROUP], a1h[MP_MAX_GROUP], b[MP_MAX_GROUP];
 };
 
 struct IgemmParams {
@@ -141,6 +141,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
   const CUtensorMap& tmA0 = TM.a0[blockIdx.z];
   const CUtensorMap& tmA0h = TM.a0h[blockIdx.z];
   const CUtensorMap& tmA1 = TM.a1[blockIdx.z];
+  const CUtensorMap& tmA1h = TM.a1h[blockIdx.z];
   const CUtensorMap& tmB = TM.b[blockIdx.z];
   const IgemmParams::Problem& Q = P.q[blockIdx.z];
   extern __shared__ __align__(1024) uint8_t smem[];   // swizzle atoms need 1024-byte alignment (checked below)
@@ -243,7 +244,7 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
         for (int g = 0; g < P.n_groups; ++g) {
           const TapGroup& G = P.groups[g];
           const bool halo = G.n > 1;
-          const CUtensorMap* tmA = halo ? &tmA0h : (G.src ? &tmA1 : &tmA0);
+          const CUtensorMap* tmA = halo ? (G.src ? &tmA1h : &tmA0h) : (G.src ? &tmA1 : &tmA0);
           for (int cb = 0; cb < P.cblocks; ++cb) {
             tc::mbar_wait(&emptyA[sa], pha ^ 1);
             uint8_t* dstA = sA + (size_t)sa * P.a_slot_bytes;
@@ -556,8 +557,9 @@ int view_to_tmap(CUtensorMap* tm, const mp_view5& v, const uint32_t box[5], cons
   return tc::encode_tmap(tm, v.ptr, 5, dims, strides, box);
 }
 
-// Partition the taps into groups of up to three that share (src 0, c0, dw, p) and have consecutive
-// row shifts; everything else becomes a group of one.  Returns the number of groups.
+// Partition the taps into groups of up to three that share (src, c0, dw, p) and have consecutive row shifts (taken
+// in list order, so the hi*hi / lo*hi / hi*lo blocks of a split-mode tap list group among themselves); everything else
+// becomes a group of one.  Returns the number of groups.
 int group_taps(const mp_igemm_args* a, bool allow_halo, TapGroup* out) {
   bool used[MP_MAX_TAPS] = {};
   int n_groups = 0;
@@ -567,13 +569,13 @@ int group_taps(const mp_igemm_args* a, bool allow_halo, TapGroup* out) {
     used[i] = true;
     int dh[3] = {t.dh, 0, 0}, koff[3] = {t.koff, 0, 0}, n = 1;
     int lo = t.dh, hi = t.dh;
-    if (allow_halo && t.src == 0) {
+    if (allow_halo) {
       bool grew = true;
       while (grew && n < 3) {
         grew = false;
         for (int j = 0; j < a->n_taps && n < 3; ++j) {
           const mp_tap& u = a->taps[j];
-          if (used[j] || u.src != 0 || u.c0 != t.c0 || u.dw != t.dw || u.p != t.p) continue;
+          if (used[j] || u.src != t.src || u.c0 != t.c0 || u.dw != t.dw || u.p != t.p) continue;
           if (u.dh != hi + 1 && u.dh != lo - 1) continue;
           if (u.dh > hi) hi = u.dh; else lo = u.dh;
           dh[n] = u.dh; koff[n] = u.koff; ++n;
@@ -861,8 +863,15 @@ extern "C" int mp_conv_igemm_grouped(const mp_igemm_args* args, int n_problems, 
     if (use_src1) {
       rc = view_to_tmap(&TM.a1[i], x->src[1], boxA, "mp_conv_igemm src[1]");
       if (rc != MP_OK) return rc;
+      if (any_halo) {
+        rc = view_to_tmap(&TM.a1h[i], x->src[1], boxH, "mp_conv_igemm src[1] (halo box)");
+        if (rc != MP_OK) return rc;
+      } else {
+        TM.a1h[i] = TM.a1[i];
+      }
     } else {
       TM.a1[i] = TM.a0[i];
+      TM.a1h[i] = TM.a0h[i];
     }
     const uint64_t dims[2] = {(uint64_t)x->w_k, (uint64_t)x->w_rows};
     const uint64_t strides[2] = {2, (uint64_t)x->w_k * 2};

@@ -531,8 +531,7 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, 
 
 // ------------------------------------------------------------------------------- weight packing
 __global__ void pack_weights_kernel(const float* __restrict__ master, __nv_bfloat16* __restrict__ packed,
-                                    const mp_pack_entry* __restrict__ table, int n_entries, long long groups,
-                                    long long lo_delta) {
+                                    const mp_pack_entry* __restrict__ table, int n_entries, long long groups) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= groups) return;
   const long long e0 = i * 8;   // first work element of this thread's 8
@@ -568,7 +567,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ master, __nv_bfloa
     }
     v[j] = val;
   }
-  mp_st8(packed + E.dst_off + (long long)r * E.dst_row_stride + (long long)t * E.cols_p + c0, lo_delta, v);
+  mp_st8(packed + E.dst_off + (long long)r * E.dst_row_stride + (long long)t * E.cols_p + c0, E.lo_off, v);
 }
 
 // ------------------------------------------------------------------------------------------ SGD
@@ -753,13 +752,12 @@ int mp_add_bf16(const void* const in[4], int n, void* out, int64_t count, int64_
 }
 
 int mp_pack_weights(const float* master, void* packed, const mp_pack_entry* table, int n_entries,
-                    int64_t total_work, int64_t lo_delta, void* stream) {
-  MP_CHECK_DELTA("mp_pack_weights");
+                    int64_t total_work, void* stream) {
   MP_CHECK_ARG(master && packed && table && n_entries > 0 && total_work > 0 && total_work % 8 == 0,
                "mp_pack_weights: bad arguments");
   const long long groups = total_work / 8;
   pack_weights_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      master, (__nv_bfloat16*)packed, table, n_entries, groups, (long long)lo_delta);
+      master, (__nv_bfloat16*)packed, table, n_entries, groups);
   MP_CHECK_LAUNCH("mp_pack_weights");
   return MP_OK;
 }

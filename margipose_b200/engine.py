@@ -91,19 +91,22 @@ class ParamBank:
         """A bf16 GEMM operand [rows_p][sum of taps*cols_p]; parts = [(slot, transpose, A, B, taps,
         cols_p)] laid side by side along K.  Returns a handle with .t (tensor) after finalize()."""
         k_total = sum(taps * cols_p for (_s, _tr, _a, _b, taps, cols_p) in parts)
+        # split (bf16x3) mode: every row holds the hi halves of all K columns, then their lo halves -- ONE matrix, so a
+        # convolution's hi*hi, lo*hi and hi*lo products can share a launch (the W_lo taps read at K offset + k_total)
+        row = k_total * (2 if self.split else 1)
         mat = type('Mat', (), {})()
-        mat.rows, mat.k, mat.off, mat.koffs, mat.t = rows_p, k_total, self.n_pack, [], None
+        mat.rows, mat.k, mat.off, mat.koffs, mat.t, mat.row = rows_p, k_total, self.n_pack, [], None, row
         koff = 0
         for slot, transpose, a, b, taps, cols_p in parts:
             work = rows_p * taps * cols_p
-            self.pack_entries.append(dict(slot=slot, dst_off=self.n_pack + koff, row_stride=k_total,
+            self.pack_entries.append(dict(slot=slot, dst_off=self.n_pack + koff, row_stride=row,
                                           work_off=self.n_work, work_end=self.n_work + work, A=a, B=b,
                                           taps=taps, transpose=int(transpose), rows_p=rows_p,
-                                          cols_p=cols_p))
+                                          cols_p=cols_p, lo_off=k_total if self.split else 0))
             self.n_work += work
             mat.koffs.append(koff)
             koff += taps * cols_p
-        self.n_pack += rows_p * k_total
+        self.n_pack += rows_p * row
         self._mats.append(mat)
         return mat
 
@@ -112,9 +115,7 @@ class ParamBank:
         self.flat_grad = torch.zeros_like(self.flat)
         self.flat_buf = torch.zeros(max(self.n_buffer, 8), device=device)
         self.flat_cnt = torch.zeros(max(len(self.counters), 1), dtype=torch.int64, device=device)
-        n_pack = (max(self.n_pack, 8) + 7) // 8 * 8
-        self.packs = torch.zeros((2 if self.split else 1) * n_pack, dtype=torch.bfloat16, device=device)
-        self.pack_lo_delta = n_pack if self.split else 0
+        self.packs = torch.zeros(max(self.n_pack, 8), dtype=torch.bfloat16, device=device)
         for s in self.params:
             p = getattr(s.mod, s.name)
             s.data = self.flat[s.off:s.off + s.numel]
@@ -149,13 +150,11 @@ class ParamBank:
             t.work_off, t.work_end = e['work_off'], e['work_end']
             t.A, t.B, t.taps, t.transpose = e['A'], e['B'], e['taps'], e['transpose']
             t.rows_p, t.cols_p = e['rows_p'], e['cols_p']
+            t.lo_off = e['lo_off']
         raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8)
         self.pack_table = raw.to(device)
         for m in self._mats:
-            m.t = self.packs[m.off:m.off + m.rows * m.k].view(m.rows, m.k)
-            if self.split:
-                lo = self.pack_lo_delta + m.off
-                self.pairs.register(m.t, self.packs[lo:lo + m.rows * m.k].view(m.rows, m.k))
+            m.t = self.packs[m.off:m.off + m.rows * m.row].view(m.rows, m.row)
         self.device = device
 
     def linked(self):
@@ -177,8 +176,8 @@ class ParamBank:
         if not self.pack_entries:
             return
         check(lib().mp_pack_weights(self.flat.data_ptr(), self.packs.data_ptr(), self.pack_table.data_ptr(),
-                                    len(self.pack_entries), self.n_work, self.pack_lo_delta,
-                                    stream_ptr(self.device)), 'mp_pack_weights')
+                                    len(self.pack_entries), self.n_work, stream_ptr(self.device)),
+              'mp_pack_weights')
 
     def attach_grads(self):
         """Makes p.grad a view of the flat gradient buffer; zeroes the buffer when the caller has

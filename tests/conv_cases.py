@@ -162,10 +162,10 @@ def _pair(x, cp):
 
 
 def _pack_pair(packed_fp32):
+    """Split-mode weight operand: [rows][K_hi | K_lo] in ONE matrix (what mp_pack_weights writes with lo_off = K)."""
     from margipose_b200 import convops as C
     hi, lo = C.split_bf16(packed_fp32)
-    buf = torch.stack([hi, lo]).contiguous()
-    return buf
+    return torch.cat([hi, lo], 1).contiguous()
 
 
 def _pack_fp32(g, master, bwd):
@@ -203,7 +203,7 @@ def check_split_conv(case):
     def reg(buf):
         return pairs.register(buf[0], buf[1])
     xg, dyg, resg = reg(_pair(x, g.cin_p)), reg(_pair(dy, g.cout_p)), reg(_pair(res, g.cin_p))
-    wf, wb = reg(_pack_pair(_pack_fp32(g, master, False))), reg(_pack_pair(_pack_fp32(g, master, True)))
+    wf, wb = _pack_pair(_pack_fp32(g, master, False)), _pack_pair(_pack_fp32(g, master, True))
     out = reg(torch.zeros(2, n, ho, wo, g.cout_p, dtype=torch.bfloat16, device=DEV))
     dx = reg(torch.zeros(2, n, h, w, g.cin_p, dtype=torch.bfloat16, device=DEV))
     dx2 = reg(torch.zeros(2, n, h, w, g.cin_p, dtype=torch.bfloat16, device=DEV))
