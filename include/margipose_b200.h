@@ -206,6 +206,10 @@ typedef struct mp_wgrad_args {
   int32_t n_img, grid_h, grid_w;
   int32_t n_off;
   float* dw;
+  /* Split (bf16x3) mode: low halves of the two operand pairs, same view geometry as a / b (ptr NULL = plain bf16).  The
+   * launch then accumulates a * b + a_lo * b + a * b_lo per pixel chunk into the same accumulator (one flush). */
+  mp_view5 a_lo;
+  mp_view5 b_lo;
 } mp_wgrad_args;
 
 MP_API int mp_conv_wgrad(const mp_wgrad_args* args, void* stream);

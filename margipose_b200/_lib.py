@@ -48,7 +48,8 @@ class WgradArgs(ctypes.Structure):
     _fields_ = [('a', View5), ('b', View5), ('n_taps', ctypes.c_int32), ('taps', Tap * MP_MAX_TAPS),
                 ('m_real', ctypes.c_int32), ('n_real', ctypes.c_int32), ('n_cols', ctypes.c_int32),
                 ('n_slots', ctypes.c_int32), ('n_img', ctypes.c_int32), ('grid_h', ctypes.c_int32),
-                ('grid_w', ctypes.c_int32), ('n_off', ctypes.c_int32), ('dw', c_void_p)]
+                ('grid_w', ctypes.c_int32), ('n_off', ctypes.c_int32), ('dw', c_void_p),
+                ('a_lo', View5), ('b_lo', View5)]
 
 
 class BnBranch(ctypes.Structure):

@@ -250,31 +250,31 @@ def _wgrad_launch(a, device):
 
 
 def _wgrad(a_t, b_t, b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, grid_h, grid_w, dw):
-    """One weight gradient: a single accumulation, or -- split precision mode -- a_hi*b_hi + a_lo*b_hi +
-    a_hi*b_lo accumulated into the same fp32 gradient."""
+    """One weight gradient.  Split precision mode: a_hi*b_hi + a_lo*b_hi + a_hi*b_lo per pixel chunk, accumulated
+    by ONE launch into the same accumulator (mp_wgrad_args.a_lo / b_lo)."""
     S = SPLIT
     rest = (b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, grid_h, grid_w, dw)
     if S is None:
         return _wgrad_one(a_t, b_t, *rest)
-    _wgrad_one(a_t, b_t, *rest)
-    _wgrad_one(S.lo(a_t), b_t, *rest, count_flops=False)
-    _wgrad_one(a_t, S.lo(b_t), *rest, count_flops=False)
+    _wgrad_one(a_t, b_t, *rest, a_lo=S.lo(a_t), b_lo=S.lo(b_t))
 
 
 def _wgrad_one(a_t, b_t, b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, grid_h, grid_w, dw,
-               count_flops=True):
+               a_lo=None, b_lo=None):
     """See mp_conv_wgrad in include/margipose_b200.h; wide b operands go in 256-channel slices."""
     for n_off in range(0, n_cols, 256):
         a = WgradArgs()
         a.a = _view(a_t)
         a.b = _view(b_t, b_parity)
+        if a_lo is not None:
+            a.a_lo = _view(a_lo)
+            a.b_lo = _view(b_lo, b_parity)
         _fill_taps(a, taps)
         a.m_real, a.n_real, a.n_slots = m_real, n_real, n_slots
         a.n_cols, a.n_off = min(256, n_cols - n_off), n_off
         a.n_img, a.grid_h, a.grid_w = n_img, grid_h, grid_w
         a.dw = dw.data_ptr()
-        a._flops = 2.0 * n_img * grid_h * grid_w * len(taps) * m_real * min(a.n_cols, n_real - n_off) \
-            if count_flops else 0.0
+        a._flops = 2.0 * n_img * grid_h * grid_w * len(taps) * m_real * min(a.n_cols, n_real - n_off)
         if n_off < n_real:
             _wgrad_launch(a, dw.device)
 

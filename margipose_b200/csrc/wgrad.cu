@@ -46,19 +46,35 @@ struct WgradParams {
   int vec_ok;
   int dbg;   // experiment switches (tunable wgrad_dbg): 1 = no epilogue atomics, 4 = no MMA
   int m_tiles;
+  int n_pass;   // 1, or 3 in split (bf16x3) mode: every pixel chunk is accumulated as a_hi*b_hi + a_lo*b_hi + a_hi*b_lo
   float* dw[MP_MAX_GROUP];   // per problem of a grouped launch (blockIdx.z / m_tiles)
 };
 
+template <int NPASS>
 struct alignas(64) WgradMaps {
   CUtensorMap a[MP_MAX_GROUP], b[MP_MAX_GROUP], bh[MP_MAX_GROUP];
 };
+template <>
+struct alignas(64) WgradMaps<3> {
+  CUtensorMap a[MP_MAX_GROUP], b[MP_MAX_GROUP], bh[MP_MAX_GROUP];
+  CUtensorMap a2[MP_MAX_GROUP], b2[MP_MAX_GROUP], bh2[MP_MAX_GROUP];   // low halves of the operand pairs (split mode)
+};
 
+template <int NPASS>
 __global__ void __launch_bounds__(NTHREADS)
-wgrad_kernel(const __grid_constant__ WgradMaps TM, const __grid_constant__ WgradParams P) {
+wgrad_kernel(const __grid_constant__ WgradMaps<NPASS> TM, const __grid_constant__ WgradParams P) {
   const int prob = blockIdx.z / P.m_tiles;
   const CUtensorMap& tmA = TM.a[prob];
   const CUtensorMap& tmB = TM.b[prob];
   const CUtensorMap& tmBh = TM.bh[prob];
+  const CUtensorMap* tmA2 = &tmA;
+  const CUtensorMap* tmB2 = &tmB;
+  const CUtensorMap* tmBh2 = &tmBh;
+  if constexpr (NPASS == 3) {
+    tmA2 = &TM.a2[prob];
+    tmB2 = &TM.b2[prob];
+    tmBh2 = &TM.bh2[prob];
+  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stages = P.stages;
@@ -103,7 +119,10 @@ wgrad_kernel(const __grid_constant__ WgradMaps TM, const __grid_constant__ Wgrad
       uint32_t ph = 0;
       const int per_img = P.chunks_w * P.chunks_h;
       const uint32_t tx = (uint32_t)(2 * P.a_box_bytes + (halo ? 1 : G.n) * b_boxes * b_box_bytes);
-      for (int i = 0; i < my_chunks; ++i) {
+      for (int it = 0; it < my_chunks * NPASS; ++it) {
+        const int i = it / NPASS, pass = it - i * NPASS;   // pass 1 reads a_lo, pass 2 reads b_lo
+        const CUtensorMap* mA = pass == 1 ? tmA2 : &tmA;
+        const CUtensorMap* mB = pass == 2 ? (halo ? tmBh2 : tmB2) : (halo ? &tmBh : &tmB);
         const int chunk = blockIdx.y + i * gridDim.y;
         const int img = chunk / per_img;
         const int rem = chunk - img * per_img;
@@ -114,10 +133,10 @@ wgrad_kernel(const __grid_constant__ WgradMaps TM, const __grid_constant__ Wgrad
         if (tc::elect_one()) {
           tc::mbar_arrive_expect_tx(&full[s], tx);
           for (int j = 0; j < 2; ++j)
-            tc::tma_load_5d(&tmA, &full[s], st + (size_t)j * P.a_box_bytes, m0 + j * 64, w0, 0, h0, img);
+            tc::tma_load_5d(mA, &full[s], st + (size_t)j * P.a_box_bytes, m0 + j * 64, w0, 0, h0, img);
           uint8_t* sb = st + 2 * (size_t)P.a_box_bytes;
           for (int j = 0; j < b_boxes; ++j)
-            tc::tma_load_5d(halo ? &tmBh : &tmB, &full[s], sb + (size_t)j * b_box_bytes, G.c0 + n_off + j * 64,
+            tc::tma_load_5d(mB, &full[s], sb + (size_t)j * b_box_bytes, G.c0 + n_off + j * 64,
                             w0 + G.dw, G.p, h0 + G.dh0, img);
         }
         if (++s == stages) { s = 0; ph ^= 1; }
@@ -128,7 +147,7 @@ wgrad_kernel(const __grid_constant__ WgradMaps TM, const __grid_constant__ Wgrad
       const uint32_t idesc = tc::idesc_bf16(128, n_cols, true, true);
       int s = 0;
       uint32_t ph = 0;
-      for (int i = 0; i < my_chunks; ++i) {
+      for (int i = 0; i < my_chunks * NPASS; ++i) {
         tc::mbar_wait(&full[s], ph);
         tc::tc_fence_after();
         const uint32_t st = tc::smem_u32(smem + (size_t)s * P.stage_bytes);
@@ -250,6 +269,7 @@ void mp_set_wgrad_tunable(int which, long long v) {
 static int check_one(const mp_wgrad_args* a) {
   MP_CHECK_ARG(a->n_taps >= 1 && a->n_taps <= MP_MAX_TAPS, "mp_conv_wgrad: n_taps %d out of range", a->n_taps);
   MP_CHECK_ARG(a->a.ptr && a->b.ptr && a->dw, "mp_conv_wgrad: null tensor");
+  MP_CHECK_ARG((a->a_lo.ptr == nullptr) == (a->b_lo.ptr == nullptr), "mp_conv_wgrad: a_lo and b_lo go together");
   MP_CHECK_ARG(a->n_cols >= 64 && a->n_cols % 64 == 0 && a->n_cols <= 256,
                "mp_conv_wgrad: n_cols %d must be 64, 128, 192 or 256", a->n_cols);
   MP_CHECK_ARG(a->m_real > 0 && a->n_real > 0 && a->n_off >= 0 && a->n_off % 64 == 0 && a->n_off < a->n_real,
@@ -270,6 +290,7 @@ static bool same_geometry(const mp_wgrad_args* x, const mp_wgrad_args* y) {
   return x->n_taps == y->n_taps && x->m_real == y->m_real && x->n_real == y->n_real && x->n_cols == y->n_cols &&
          x->n_slots == y->n_slots && x->n_img == y->n_img && x->grid_h == y->grid_h && x->grid_w == y->grid_w &&
          x->n_off == y->n_off && same_view(x->a, y->a) && same_view(x->b, y->b) &&
+         (x->a_lo.ptr == nullptr) == (y->a_lo.ptr == nullptr) &&
          (((uintptr_t)x->dw ^ (uintptr_t)y->dw) & 15) == 0 && memcmp(x->taps, y->taps, sizeof(mp_tap) * x->n_taps) == 0;
 }
 
@@ -339,6 +360,7 @@ extern "C" int mp_conv_wgrad_grouped(const mp_wgrad_args* args, int n_problems, 
 
   const int m_tiles = (a->m_real + 127) / 128;
   P.m_tiles = m_tiles;
+  P.n_pass = a->a_lo.ptr ? 3 : 1;
   const int gx = P.n_groups * P.n_slices;
   int split = (int)(g_wgrad_ctas / (gx * m_tiles * n_problems));
   if (split < 1) split = 1;
@@ -347,7 +369,7 @@ extern "C" int mp_conv_wgrad_grouped(const mp_wgrad_args* args, int n_problems, 
   // accumulate into the same tensor are ordered by their stream)
   if (mp_deterministic()) split = 1;
 
-  WgradMaps TM;
+  WgradMaps<3> TM;   // (the single-pass kernel receives the first three arrays only)
   const uint32_t box[5] = {64, (uint32_t)P.kp_w, 1, (uint32_t)P.kp_rows, 1};
   const uint32_t boxh[5] = {64, (uint32_t)P.kp_w, 1, (uint32_t)(P.kp_rows + 2), 1};
   for (int i = 0; i < MP_MAX_GROUP; ++i) {
@@ -363,16 +385,35 @@ extern "C" int mp_conv_wgrad_grouped(const mp_wgrad_args* args, int n_problems, 
     } else {
       TM.bh[i] = TM.b[i];
     }
+    TM.a2[i] = TM.a[i]; TM.b2[i] = TM.b[i]; TM.bh2[i] = TM.bh[i];
+    if (P.n_pass > 1) {
+      rc = view_to_tmap(&TM.a2[i], x->a_lo, box, "mp_conv_wgrad a_lo");
+      if (rc != MP_OK) return rc;
+      rc = view_to_tmap(&TM.b2[i], x->b_lo, box, "mp_conv_wgrad b_lo");
+      if (rc != MP_OK) return rc;
+      TM.bh2[i] = TM.b2[i];
+      if (max_n > 1) {
+        rc = view_to_tmap(&TM.bh2[i], x->b_lo, boxh, "mp_conv_wgrad b_lo (halo box)");
+        if (rc != MP_OK) return rc;
+      }
+    }
   }
 
   const size_t smem = (size_t)stages * P.stage_bytes + overhead;
   MP_CHECK_ARG(smem <= 227 * 1024, "mp_conv_wgrad: stage too large (%zu bytes of shared memory)", smem);
   if (!g_attr_set) {
-    MP_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MP_CUDA(cudaFuncSetAttribute(wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MP_CUDA(cudaFuncSetAttribute(wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr_set = true;
   }
   dim3 grid((unsigned)gx, (unsigned)split, (unsigned)(m_tiles * n_problems));
-  MP_CUDA(mp_launch(wgrad_kernel, grid, dim3(NTHREADS), smem, (cudaStream_t)stream, TM, P));
+  if (P.n_pass > 1) {
+    MP_CUDA(mp_launch(wgrad_kernel<3>, grid, dim3(NTHREADS), smem, (cudaStream_t)stream, TM, P));
+  } else {
+    WgradMaps<1> T1;
+    memcpy(&T1, &TM, sizeof(T1));
+    MP_CUDA(mp_launch(wgrad_kernel<1>, grid, dim3(NTHREADS), smem, (cudaStream_t)stream, T1, P));
+  }
   MP_CHECK_LAUNCH("mp_conv_wgrad");
   return MP_OK;
 }

@@ -261,7 +261,7 @@ class MargiPoseModel(nn.Module):
         # 'bf16'  : bf16 tensor-core operands and bf16 activation storage, fp32 accumulation (the fast path)
         # 'bf16x3': every activation / weight is a pair of bf16 values (hi + lo, ~16 significant bits) and every
         #           convolution is three tensor-core passes over one fp32 accumulator -- results agree with the
-        #           reference's fp32 arithmetic to ~1e-4 (PARITY.md) at roughly a third of the speed
+        #           reference's fp32 arithmetic to ~2e-4 (PARITY.md) at a bit under half the speed
         self.precision = precision
         # run-to-run bit-wise reproducible training steps (the reference's `deterministic` flag, utils.py:19-24):
         # set before the first forward, or call drop_engines() after changing it

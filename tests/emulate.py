@@ -73,13 +73,15 @@ def igemm(srcs, wmat, taps, cblocks, n_img, out_h, out_w, out, out_strides, out_
         stats[1][:out_c] += (r * r).sum(0)
 
 
-def wgrad(a_t, b_t, b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, grid_h, grid_w, dw, count_flops=True):
-    va = _view5(a_t, False)
-    vb = _view5(b_t, b_parity)
-    a = _gather(va, 0, va.shape[-1], 0, 0, 0, grid_h, grid_w)[..., :m_real].reshape(-1, m_real)
-    for _src, c0, ddw, p, dh, slot in taps:
-        b = _gather(vb, c0, n_cols, ddw, p, dh, grid_h, grid_w)[..., :n_real].reshape(-1, n_real)
-        dw[:, slot, :] += a.t() @ b
+def wgrad(a_t, b_t, b_parity, taps, m_real, n_real, n_cols, n_slots, n_img, grid_h, grid_w, dw, a_lo=None, b_lo=None):
+    # split mode: a * b + a_lo * b + a * b_lo (the lo * lo term is dropped, as on the GPU)
+    for at, bt in [(a_t, b_t)] + ([(a_lo, b_t), (a_t, b_lo)] if a_lo is not None else []):
+        va = _view5(at, False)
+        vb = _view5(bt, b_parity)
+        a = _gather(va, 0, va.shape[-1], 0, 0, 0, grid_h, grid_w)[..., :m_real].reshape(-1, m_real)
+        for _src, c0, ddw, p, dh, slot in taps:
+            b = _gather(vb, c0, n_cols, ddw, p, dh, grid_h, grid_w)[..., :n_real].reshape(-1, n_real)
+            dw[:, slot, :] += a.t() @ b
 
 
 def install(monkeypatch):
