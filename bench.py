@@ -482,10 +482,13 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = ms.item()
+    # the clock / throttle sampler covers the device-timed region; it is stopped here because a polling nvidia-smi
+    # takes driver locks that delay launches, which the per-step synchronisation of the end-to-end loop below exposes
+    clocks = sampler.stop() if rank == 0 else None
 
     # end to end: pinned host inputs every step, loss read back every step.  As a prefetching loader would, the copy of
-    # batch i + 1 is started (TrainStep.prefetch: copy stream, staging slot) before step i is waited for; every step's
-    # inputs still cross PCIe inside the timed region.
+    # batch i + 1 is started (TrainStep.__call__(..., prefetch=next batch): copy stream, staging slot) once step i has been
+    # queued and before its loss is waited for; every step's inputs still cross PCIe inside the timed region.
     for i in range(2):
         step(*host_sets[i % len(host_sets)])
     barrier()
@@ -493,12 +496,10 @@ def run_b200(args):
     last = None
     step.prefetch(*host_sets[0])
     for i in range(K):
-        if i + 1 < K:
-            step.prefetch(*host_sets[(i + 1) % len(host_sets)])
-        last = step(*host_sets[i % len(host_sets)])
+        nxt = host_sets[(i + 1) % len(host_sets)] if i + 1 < K else None
+        last = step(*host_sets[i % len(host_sets)], prefetch=nxt)
     torch.cuda.synchronize(dev)
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
-    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = e2e_s.item()

@@ -54,6 +54,7 @@ class ParamBank:
         self.n_param = self.n_buffer = 0
         self.pack_entries = []          # dicts; turned into a device table by finalize()
         self.n_pack = self.n_work = 0
+        self.pack_head = None           # (entries, work) of the ResNet stem's packs: pack(part=...) can refresh them apart
         self._seen = {}
         self.flat = self.flat_grad = self.flat_buf = self.flat_cnt = self.packs = None
         self._mats = []
@@ -110,6 +111,10 @@ class ParamBank:
         self._mats.append(mat)
         return mat
 
+    def mark_pack_head(self):
+        """Everything packed so far belongs to the feature extractor (needed first in a forward pass)."""
+        self.pack_head = (len(self.pack_entries), self.n_work)
+
     def finalize(self, device):
         self.flat = torch.zeros(max(self.n_param, 8), device=device)
         self.flat_grad = torch.zeros_like(self.flat)
@@ -144,10 +149,13 @@ class ParamBank:
             self.flat_cnt[s.off] = int(b)
             s.mod._buffers[s.name] = self.flat_cnt[s.off]
         table = (PackEntry * max(len(self.pack_entries), 1))()
+        head_n, head_work = self.pack_head if self.pack_head else (0, 0)
         for i, e in enumerate(self.pack_entries):
             t = table[i]
             t.src_off, t.dst_off, t.dst_row_stride = e['slot'].off, e['dst_off'], e['row_stride']
-            t.work_off, t.work_end = e['work_off'], e['work_end']
+            # two tables in one array: [0, head_n) counts its work from 0, and so does [head_n, n)
+            base = head_work if i >= head_n else 0
+            t.work_off, t.work_end = e['work_off'] - base, e['work_end'] - base
             t.A, t.B, t.taps, t.transpose = e['A'], e['B'], e['taps'], e['transpose']
             t.rows_p, t.cols_p = e['rows_p'], e['cols_p']
             t.lo_off = e['lo_off']
@@ -172,12 +180,21 @@ class ParamBank:
         finalize() detaches them from the flat buffer's -- so the bf16 weight-pack cache keys on their sum."""
         return self.flat._version + sum(s.mod._parameters[s.name]._version for s in self.params)
 
-    def pack(self):
+    def pack(self, part=None):
+        """fp32 master weights -> bf16 GEMM operands.  part=None: everything; 0: the feature extractor's packs only;
+        1: the rest (TrainStep runs that one beside the stem's forward pass)."""
         if not self.pack_entries:
             return
-        check(lib().mp_pack_weights(self.flat.data_ptr(), self.packs.data_ptr(), self.pack_table.data_ptr(),
-                                    len(self.pack_entries), self.n_work, stream_ptr(self.device)),
-              'mp_pack_weights')
+        head_n, head_work = self.pack_head if self.pack_head else (0, 0)
+        n = len(self.pack_entries)
+        spans = {None: [(0, head_n, head_work), (head_n, n - head_n, self.n_work - head_work)],
+                 0: [(0, head_n, head_work)], 1: [(head_n, n - head_n, self.n_work - head_work)]}[part]
+        entry_bytes = ctypes.sizeof(PackEntry)
+        for first, count, work in spans:
+            if count > 0:
+                check(lib().mp_pack_weights(self.flat.data_ptr(), self.packs.data_ptr(),
+                                            self.pack_table.data_ptr() + first * entry_bytes, count, work,
+                                            stream_ptr(self.device)), 'mp_pack_weights')
 
     def attach_grads(self):
         """Makes p.grad a view of the flat gradient buffer; zeroes the buffer when the caller has
@@ -305,6 +322,7 @@ def build_layers(model, bank):
         r.fused = bank.add_matrix(r.conv1.g.cin_p, [r.conv1.bwd_part(), r.convs.bwd_part()])
         return r
 
+    bank.mark_pack_head()
     L.columns = []
     L.stage_ranges = []      # [lo, hi) of stage t's parameters in the flat buffers (all-reduce buckets)
     for t in range(L.n_stages):
@@ -1046,9 +1064,10 @@ class Engine:
                 out += len(body) if kind == 'serial' else sum(len(o) for o in body)
         return out
 
-    def forward(self, x, fused=False):
+    def forward(self, x, fused=False, join_after_stem=None):
         """x: fp32 (N, 3, H, W) on the device.  Returns probs[t][k], fp32 (N, J, h, w).  fused=True (after
         enable_fused_loss): the stage tails also compute the losses of the loss context.  The returned
+        join_after_stem: a stream the pass waits for between the feature extractor and the first stage.  The returned
         tensors (and everything a backward reads) are the engine's static buffers: the next forward of this
         engine overwrites them, and a backward is only valid for the most recent forward (checked through
         `generation`)."""
@@ -1077,7 +1096,12 @@ class Engine:
         if self.fold:   # running statistics -> per-channel affines for every BatchNorm of the network, one launch
             check(lib().mp_bn_fold_eval(self._fold_table.data_ptr(), self._n_fold, stream_ptr(self.device)),
                   'mp_bn_fold_eval')
-        self._run(self.fwd)
+        if join_after_stem is None:
+            self._run(self.fwd)
+        else:   # the columns' weight packs are being refreshed on another stream while the feature extractor runs
+            self._run(self.fwd[:1])
+            torch.cuda.current_stream(self.device).wait_stream(join_after_stem)
+            self._run(self.fwd[1:])
         return self.probs
 
     def backward(self, grads=None, lo=0, hi=None):

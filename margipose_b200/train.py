@@ -90,8 +90,15 @@ class TrainStep:
         model, eng = self.model, self.eng
         self.opt.zero_grad()
         if self.fused:
-            model._refresh_packs()
-            probs = eng.forward(self.x, fused=True)
+            # bf16 operand refresh: the feature extractor's packs first, the columns' (95 % of the weights) on the
+            # auxiliary stream beside the feature extractor's forward pass
+            bank, cur, aux = model._bank, torch.cuda.current_stream(self.device), eng.aux[0]
+            bank.pack(part=0)
+            aux.wait_stream(cur)
+            with torch.cuda.stream(aux):
+                bank.pack(part=1)
+            model._packed_version = None
+            probs = eng.forward(self.x, fused=True, join_after_stem=aux)
             model.xy_heatmaps = [row[0] for row in probs]
             model.zy_heatmaps = [row[1] for row in probs]
             model.xz_heatmaps = [row[2] for row in probs]
@@ -254,14 +261,18 @@ class TrainStep:
         slot['free'].record(cur)
         return True
 
-    def __call__(self, images, targets, mask=None, valid_depth=None):
+    def __call__(self, images, targets, mask=None, valid_depth=None, prefetch=None):
         """Copies one batch in (pinned host tensors copy asynchronously; a batch announced with `prefetch` is
         already on the device), runs the step and returns the loss as a Python float (a 4-byte device-to-host
         read, like train_3d.py:167).
-        valid_depth: optional per-sample flags, 1 = 3D loss, 0 = 2D loss (bin/train_3d.py:126-142)."""
+        valid_depth: optional per-sample flags, 1 = 3D loss, 0 = 2D loss (bin/train_3d.py:126-142).
+        prefetch: the NEXT batch as a tuple (images, targets[, mask[, valid_depth]]): its host -> device copy is
+        started after this step's launches have been queued and before its loss is waited for."""
         if not self._take_staged(images):
             self.load(images, targets, mask, valid_depth)
         self.run()
+        if prefetch is not None:
+            self.prefetch(*prefetch)
         return self.loss.item()
 
     def launches_per_step(self):
