@@ -414,6 +414,8 @@ MP_API int mp_sgd_step_hp(float* param, const float* grad, float* momentum_buf, 
  *                   NHWC; default 1 (the backward kernels share SMs with the weight-gradient kernels, see csrc/bn.cu)
  *   "tail_fast"   : 1 (default) = mp_tail_fwd / mp_tail_bwd use the log2-domain kernels when the heatmap width divides 128;
  *                   0 = the general warp-sliced kernels
+ *   "tail_wpj"    : 1 (default) = planes of at most 1024 elements (the model's 32 x 32 heatmaps) use the warp-per-joint
+ *                   kernels (a whole plane in one warp's registers, no shared memory, no block barriers)
  *   "tail_ctas_per_sm": > 0 caps their grid at that many (persistent) CTAs per SM (default 0 = one CTA per (sample, joint) group) */
 MP_API int mp_set_tunable(const char* name, int64_t value);
 

@@ -32,6 +32,9 @@ void mp_set_igemm_mt(int which, long long v);
 void mp_set_wgrad_tunable(int which, long long v);
 extern long long g_tail_fast;
 extern long long g_tail_waves;
+extern long long g_tail_wpj;
+extern long long g_tail_cap;
+extern long long g_tail_wpj_max;
 extern long long g_bn_tma;
 
 static long long g_pdl = 1;
@@ -63,6 +66,9 @@ extern "C" int mp_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "wgrad_smem")) { mp_set_wgrad_tunable(5, value); return MP_OK; }
   if (!strcmp(name, "tail_fast")) { g_tail_fast = value; return MP_OK; }
   if (!strcmp(name, "tail_ctas_per_sm")) { g_tail_waves = value; return MP_OK; }
+  if (!strcmp(name, "tail_wpj")) { g_tail_wpj = value; return MP_OK; }
+  if (!strcmp(name, "tail_wpj_max")) { g_tail_wpj_max = value; return MP_OK; }
+  if (!strcmp(name, "tail_cap")) { g_tail_cap = value == 8 ? 8 : 4; return MP_OK; }
   if (!strcmp(name, "bn_tma")) { g_bn_tma = value; return MP_OK; }
   mp_set_error("mp_set_tunable: unknown tunable '%s'", name);
   return MP_ERR_ARG;

@@ -16,6 +16,9 @@
 #include "../../include/margipose_b200.h"
 
 long long g_tail_fast = 1;   // tunable "tail_fast": 1 = the log2-domain kernels for row lengths dividing 128
+long long g_tail_wpj_max = 32;   // tunable "tail_wpj_max": largest plane (in float4 per lane) of the forward warp-per-joint kernel
+long long g_tail_cap = 4;    // tunable "tail_cap": float4 slots per lane the warp plan tries first (4 or 8)
+long long g_tail_wpj = 1;    // tunable "tail_wpj": 1 = warp-per-joint kernels for planes of at most 1024 elements
 long long g_tail_waves = 0;  // tunable "tail_ctas_per_sm": persistent CTAs per SM of the fast kernels (0 = one CTA per group)
 
 namespace {
@@ -1252,6 +1255,306 @@ __global__ void __launch_bounds__(512, 2) tail_bwd_fast_kernel(const BwdArgs A, 
   }
 }
 
+
+// =====================================================================================================
+// Warp-per-joint kernels for small planes (H * W <= 1024 and a multiple of 128, W dividing 128: the 32 x 32 heatmaps
+// of the MargiPose model itself, 16 x 16, ...).  ONE warp owns a (sample, joint) and walks its three planes, a whole
+// plane lives in the warp's registers (NV float4 per lane), so there is no shared memory and no block barrier at all:
+// every reduction is a shuffle tree, and the separable Gaussian's column / row factors are evaluated directly by the
+// lanes that need them (4 columns + NV rows per lane) instead of going through a table.  The per-plane fixed cost
+// drops from ~800 instructions per warp (fast kernels above) to ~200.
+template <int NV, bool FROM_LOGITS>
+__global__ void __launch_bounds__(NV > 8 ? 128 : 256, 2) tail_fwd_wpj_kernel(const FwdArgs A, const int BJ, const int wshift) {
+  pdl_trigger();
+  pdl_wait();
+  const int W = A.g.W, H = A.g.H, HW = A.g.HW;
+  const int lane = threadIdx.x & 31;
+  const int bj = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (bj >= BJ) return;
+  const int w0 = (lane * 4) & (W - 1);
+  const int rpi = 128 >> wshift;                 // rows between a lane's consecutive float4 slots
+  const int h0 = (lane * 4) >> wshift;
+  const float col_mult = (float)W * (1.0f / 128.0f);   // a column is held by 128 / W lanes, a row by W / 4
+  const float row_mult = 4.0f / (float)W;
+  float cw[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cw[j] = centre(w0 + j, A.g.cw_step, A.g.cw_first);
+  const int b = bj / A.J;
+  const bool is3d = A.valid_depth ? (A.valid_depth[b] != 0) : true;
+  float tx = 0.f, ty = 0.f, tz = 0.f;
+  if (A.target) { tx = A.target[bj * 3 + 0]; ty = A.target[bj * 3 + 1]; tz = A.target[bj * 3 + 2]; }
+  const size_t off = (size_t)bj * HW;
+  float pa[3] = {0.f, 0.f, 0.f}, pb[3] = {0.f, 0.f, 0.f}, pj[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (!A.in[k]) continue;
+    float4 x[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) x[i] = __ldg(reinterpret_cast<const float4*>(A.in[k] + off + (i * 32 + lane) * 4));
+    float mc, mr;
+    bool want_js;
+    if (A.mu[k]) {
+      mc = A.mu[k][bj * 2 + 0]; mr = A.mu[k][bj * 2 + 1];
+      want_js = A.js[k] != nullptr;
+    } else {
+      mc = (k == 1) ? tz : tx;
+      mr = (k == 2) ? tz : ty;
+      want_js = A.target && A.pixelwise && (A.loss || A.js[k]) && (k == 0 || is3d);
+    }
+    float m = 0.f;
+    if (FROM_LOGITS) {
+      m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) m = fmaxf(m, fmaxf(fmaxf(x[i].x, x[i].y), fmaxf(x[i].z, x[i].w)));
+      m = warp_max(m);
+    }
+    const float m2 = m * L2E;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accx = 0.f;
+    if (FROM_LOGITS && want_js) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float v[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+        float rowsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j] = fmaxf(fmaf(v[j], L2E, -m2), -1e30f);
+          const float ev = fast_ex2(v[j]);
+          accx = fmaf(ev, v[j], accx);
+          rowsum += ev;
+          acc1 = fmaf(ev, cw[j], acc1);
+        }
+        acc0 += rowsum;
+        acc2 = fmaf(rowsum, centre(h0 + i * rpi, A.g.ch_step, A.g.ch_first), acc2);
+        x[i] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float v[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+        float rowsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (FROM_LOGITS) v[j] = fast_ex2(fmaf(v[j], L2E, -m2));
+          rowsum += v[j];
+          acc1 = fmaf(v[j], cw[j], acc1);
+        }
+        acc0 += rowsum;
+        acc2 = fmaf(rowsum, centre(h0 + i * rpi, A.g.ch_step, A.g.ch_first), acc2);
+        x[i] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    acc0 = warp_sum(acc0); acc1 = warp_sum(acc1); acc2 = warp_sum(acc2);
+    float inv = 1.f, l2inv = 0.f, ea, eb;
+    if (FROM_LOGITS) {
+      inv = 1.0f / acc0;
+      l2inv = -log2f(acc0);
+      ea = acc1 * inv; eb = acc2 * inv;
+    } else {
+      ea = acc1; eb = acc2;
+    }
+    float js = 0.f;
+    if (want_js) {
+      // separable Gaussian, evaluated by the lanes that need it: 4 column factors, NV row factors (log2-domain exponents;
+      // the row factors are re-evaluated in the JS pass -- one exp2 per float4 -- rather than kept in NV registers)
+      float qc[4];
+      float sc = 0.f, sr = 0.f, ac = 0.f, ar = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d = cw[j] - mc;
+        const float lg = __fmul_rn(__fmul_rn(d, d), A.g.kw) * L2E;
+        qc[j] = fast_ex2(lg);
+        sc += qc[j];
+        ac = fmaf(qc[j], lg, ac);
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float d = centre(h0 + i * rpi, A.g.ch_step, A.g.ch_first) - mr;
+        const float lg = __fmul_rn(__fmul_rn(d, d), A.g.kh) * L2E;
+        const float qri = fast_ex2(lg);
+        sr += qri;
+        ar = fmaf(qri, lg, ar);
+      }
+      sc = warp_sum(sc) * col_mult; ac = warp_sum(ac) * col_mult;
+      sr = warp_sum(sr) * row_mult; ar = warp_sum(ar) * row_mult;
+      const float ginv = 1.0f / (sc * sr + KL_EPS);
+      float slm = 0.f, plp = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float pv[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+        const float dr = centre(h0 + i * rpi, A.g.ch_step, A.g.ch_first) - mr;
+        const float er = fast_ex2(__fmul_rn(__fmul_rn(dr, dr), A.g.kh) * L2E) * ginv;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (FROM_LOGITS) pv[j] = fast_ex2(pv[j] + l2inv);
+          else plp = fmaf(pv[j], fast_lg2(pv[j] + KL_EPS), plp);
+          const float sq = fmaf(qc[j], er, pv[j]);
+          slm = fmaf(sq, fast_lg2(fmaf(0.5f, sq, KL_EPS)), slm);
+        }
+        x[i] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      }
+      float jsp = warp_sum(plp - slm);
+      if (FROM_LOGITS) jsp += fmaf(warp_sum(accx), inv, l2inv);        // sum p lg p
+      jsp += fmaf(ginv, fmaf(ac, sr, sc * ar), log2f(ginv) * (sc * sr * ginv));   // sum q lg q (exponents are log2 already)
+      js = 0.5f * jsp * LN2;
+    } else if (FROM_LOGITS) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) { x[i].x *= inv; x[i].y *= inv; x[i].z *= inv; x[i].w *= inv; }
+    }
+    if (A.prob[k]) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(A.prob[k] + off + (i * 32 + lane) * 4) = x[i];
+    }
+    pa[k] = ea; pb[k] = eb; pj[k] = js;
+    if (lane == 0) {
+      if (A.ab[k]) { A.ab[k][bj * 2 + 0] = ea; A.ab[k][bj * 2 + 1] = eb; }
+      if (A.js[k]) A.js[k][bj] = js;
+    }
+  }
+  if (lane != 0) return;
+  const float px = pa[0], py = pb[0], pz = 0.5f * (pa[1] + pb[2]);   // models/margipose_model.py:254-261
+  if (A.coords) { A.coords[bj * 3 + 0] = px; A.coords[bj * 3 + 1] = py; A.coords[bj * 3 + 2] = pz; }
+  if (A.loss && A.target) {
+    const float dx = px - tx, dy = py - ty, dz = pz - tz;
+    float l;
+    if (is3d) l = pj[0] + pj[1] + pj[2] + sqrtf(dx * dx + dy * dy + dz * dz);
+    else l = pj[0] + sqrtf(dx * dx + dy * dy);
+    A.loss[bj] = A.accumulate ? A.loss[bj] + l : l;
+  }
+}
+
+template <int NV, bool PROJECT>
+__global__ void __launch_bounds__(256, 2) tail_bwd_wpj_kernel(const BwdArgs A, const int BJ, const int wshift) {
+  pdl_trigger();
+  pdl_wait();
+  const int W = A.g.W, HW = A.g.HW;
+  const int lane = threadIdx.x & 31;
+  const int bj = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (bj >= BJ) return;
+  const int w0 = (lane * 4) & (W - 1);
+  const int rpi = 128 >> wshift;
+  const int h0 = (lane * 4) >> wshift;
+  const float col_mult = (float)W * (1.0f / 128.0f), row_mult = 4.0f / (float)W;
+  float cw[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cw[j] = centre(w0 + j, A.g.cw_step, A.g.cw_first);
+  const int b = bj / A.J;
+  const bool is3d = A.valid_depth ? (A.valid_depth[b] != 0) : true;
+  const size_t off = (size_t)bj * HW;
+  float tx = 0.f, ty = 0.f, tz = 0.f, w = 0.f, ddx = 0.f, ddy = 0.f, ddz = 0.f;
+  if (A.target) {
+    tx = A.target[bj * 3 + 0]; ty = A.target[bj * 3 + 1]; tz = A.target[bj * 3 + 2];
+    w = A.w[bj];
+    const float dx = A.coords[bj * 3 + 0] - tx, dy = A.coords[bj * 3 + 1] - ty;
+    const float dz = is3d ? A.coords[bj * 3 + 2] - tz : 0.f;
+    const float inv = w / sqrtf(dx * dx + dy * dy + dz * dz);   // infinite at 0, like dsntnn.py:149-150
+    ddx = dx * inv; ddy = dy * inv; ddz = dz * inv;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (!A.out[k]) continue;
+    float4 p[NV], d[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      p[i] = __ldg(reinterpret_cast<const float4*>(A.prob[k] + off + (i * 32 + lane) * 4));
+      d[i] = A.gup[k] ? __ldg(reinterpret_cast<const float4*>(A.gup[k] + off + (i * 32 + lane) * 4))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float wjs, cc, cr, mc, mr;
+    bool want_js;
+    if (A.coef[k]) {
+      wjs = A.coef[k][bj * 3 + 0]; cc = A.coef[k][bj * 3 + 1]; cr = A.coef[k][bj * 3 + 2];
+      mc = A.mu[k] ? A.mu[k][bj * 2 + 0] : 0.f;
+      mr = A.mu[k] ? A.mu[k][bj * 2 + 1] : 0.f;
+      want_js = A.mu[k] != nullptr;
+    } else if (A.target) {
+      mc = (k == 1) ? tz : tx;
+      mr = (k == 2) ? tz : ty;
+      wjs = (A.pixelwise && (k == 0 || is3d)) ? w : 0.f;
+      cc = (k == 0) ? ddx : (k == 1 ? 0.5f * ddz : 0.f);
+      cr = (k == 0) ? ddy : (k == 2 ? 0.5f * ddz : 0.f);
+      want_js = wjs != 0.f;
+    } else {
+      wjs = cc = cr = mc = mr = 0.f;
+      want_js = false;
+    }
+    float ccw[4], qc[4] = {0.f, 0.f, 0.f, 0.f}, qr[NV];
+    float ginv = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ccw[j] = cc * cw[j];
+    if (want_js) {
+      float sc = 0.f, sr = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float dd = cw[j] - mc;
+        qc[j] = fast_ex2(__fmul_rn(__fmul_rn(dd, dd), A.g.kw) * L2E);
+        sc += qc[j];
+      }
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float dd = centre(h0 + i * rpi, A.g.ch_step, A.g.ch_first) - mr;
+        qr[i] = fast_ex2(__fmul_rn(__fmul_rn(dd, dd), A.g.kh) * L2E);
+        sr += qr[i];
+      }
+      ginv = 1.0f / (warp_sum(sc) * col_mult * (warp_sum(sr) * row_mult) + KL_EPS);
+    }
+    const float kjs = 0.5f * wjs * LN2, hjs = 0.5f * wjs;
+    const float TINY = 2e-16f;
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float lin_r = cr * centre(h0 + i * rpi, A.g.ch_step, A.g.ch_first);
+      const float pv[4] = {p[i].x, p[i].y, p[i].z, p[i].w};
+      float dv[4] = {d[i].x, d[i].y, d[i].z, d[i].w};
+      if (want_js) {
+        const float er = qr[i] * ginv;
+        const float lin_js = lin_r + kjs;
+        const bool tiny = fminf(fminf(pv[0], pv[1]), fminf(pv[2], pv[3])) < TINY;
+        if (!__any_sync(0xffffffffu, tiny)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float sq = fmaf(qc[j], er, pv[j]);
+            dv[j] += ccw[j] + lin_js;
+            dv[j] = fmaf(kjs, fast_lg2(pv[j]) - fast_lg2(sq), dv[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float mm = 0.5f * fmaf(qc[j], er, pv[j]);
+            dv[j] += ccw[j] + lin_r;
+            dv[j] = fmaf(kjs, fast_lg2(pv[j] + KL_EPS) - fast_lg2(mm + KL_EPS), dv[j]);
+            dv[j] = fmaf(hjs, __fdividef(pv[j], pv[j] + KL_EPS) - __fdividef(mm, mm + KL_EPS), dv[j]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dv[j] += ccw[j] + lin_r;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part = fmaf(pv[j], dv[j], part);
+      d[i] = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    }
+    if (PROJECT) {
+      part = warp_sum(part);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        d[i].x = p[i].x * (d[i].x - part); d[i].y = p[i].y * (d[i].y - part);
+        d[i].z = p[i].z * (d[i].z - part); d[i].w = p[i].w * (d[i].w - part);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(A.out[k] + off + (i * 32 + lane) * 4) = d[i];
+  }
+}
+
+// float4 slots per lane of the warp-per-joint kernels (at most max_nv), or 0 when they do not apply
+int wpj_slots(int H, int W, int wshift, int max_nv) {
+  const int HW = H * W;
+  if (wshift < 0 || HW % 128 != 0) return 0;
+  const int nv = HW / 128;
+  if (nv > max_nv) return 0;
+  return (nv == 1 || nv == 2 || nv == 4 || nv == 8 || nv == 16 || nv == 32) ? nv : 0;
+}
+
 // Grid of the fast kernels: one CTA per (sample, joint) group by default.  The kernels can also walk several groups
 // per CTA (tunable "tail_ctas_per_sm" caps the grid at that many CTAs per SM); measured equal or slower -- the fixed
 // per-plane work is not hoistable within 64 registers and a fresh CTA's loads overlap its predecessor's tail.
@@ -1277,7 +1580,7 @@ bool plan_warps(int HW, int np, int BJ, WarpPlan* P, int* nv) {
   P->BJ = BJ;
   // Few float4 per lane (NV <= 4) keeps the register count low enough for ~30 resident warps per SM;
   // planes run side by side when np * wpp fits in 16 warps, otherwise one plane at a time.
-  for (int cap = 4; cap <= 8; cap += 4) {
+  for (int cap = (int)g_tail_cap; cap <= 8; cap += 4) {
     for (int wpp = 1; wpp <= 16; ++wpp) {
       const int need = (vecs + wpp * 32 - 1) / (wpp * 32);
       if (need > cap) continue;
@@ -1321,6 +1624,23 @@ Geom make_geom(int H, int W, double sigma) {
 template <bool FROM_LOGITS>
 int launch_fwd(const FwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
   const int HW = A.g.HW;
+  if (vec4 && g_tail_fast && g_tail_wpj) {
+    const int wsh = fast_shift(A.g.W);
+    // softmax + expectations only: a plane of up to 4096 elements (64 x 64) still fits one warp's registers (32 float4 per
+    // lane, 4 warps per block: 0.93 of the HBM peak at 64 x 64).  With the JS term that variant is latency-bound at 255
+    // registers (0.31), so the fused loss keeps the block kernels above 1024 elements.
+    const bool with_js = (A.target && A.pixelwise && A.loss) || A.js[0] || A.js[1] || A.js[2];
+    const int nv = wpj_slots(A.g.H, A.g.W, wsh, with_js ? 8 : (int)g_tail_wpj_max);
+    if (nv) {
+      const int wpb = nv > 8 ? 4 : 8;
+      const dim3 grid((BJ + wpb - 1) / wpb), block(32 * wpb);
+#define MP_FWDJ(NV) mp_launch(tail_fwd_wpj_kernel<NV, FROM_LOGITS>, grid, block, 0, st, A, BJ, wsh)
+      if (nv == 1) MP_FWDJ(1); else if (nv == 2) MP_FWDJ(2); else if (nv == 4) MP_FWDJ(4); else if (nv == 8) MP_FWDJ(8);
+      else if (nv == 16) MP_FWDJ(16); else MP_FWDJ(32);
+#undef MP_FWDJ
+      return MP_OK;
+    }
+  }
   if (vec4) {
     WarpPlan P;
     int np = 0, nv = 0;
@@ -1370,6 +1690,17 @@ int launch_fwd(const FwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
 template <bool PROJECT>
 int launch_bwd(const BwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
   const int HW = A.g.HW;
+  if (vec4 && g_tail_fast && g_tail_wpj) {
+    const int wsh = fast_shift(A.g.W);
+    const int nv = wpj_slots(A.g.H, A.g.W, wsh, 8);   // backward holds p AND the gradient: 1024 elements per warp at most
+    if (nv) {
+      const dim3 grid((BJ + 7) / 8), block(256);
+#define MP_BWDJ(NV) mp_launch(tail_bwd_wpj_kernel<NV, PROJECT>, grid, block, 0, st, A, BJ, wsh)
+      if (nv == 1) MP_BWDJ(1); else if (nv == 2) MP_BWDJ(2); else if (nv == 4) MP_BWDJ(4); else MP_BWDJ(8);
+#undef MP_BWDJ
+      return MP_OK;
+    }
+  }
   if (vec4) {
     WarpPlan P;
     int np = 0, nv = 0;
