@@ -1263,17 +1263,48 @@ __global__ void __launch_bounds__(512, 2) tail_bwd_fast_kernel(const BwdArgs A, 
 // every reduction is a shuffle tree, and the separable Gaussian's column / row factors are evaluated directly by the
 // lanes that need them (4 columns + NV rows per lane) instead of going through a table.  The per-plane fixed cost
 // drops from ~800 instructions per warp (fast kernels above) to ~200.
-template <int NV, bool FROM_LOGITS>
-__global__ void __launch_bounds__(NV > 8 ? 128 : 256, 2) tail_fwd_wpj_kernel(const FwdArgs A, const int BJ, const int wshift) {
+// WPP > 1 (softmax + expectations only, no JS term): WPP warps = one block share a plane of up to 16384 elements (128 x 128),
+// 32 float4 per lane each; their partial maxima / sums meet in 16 floats of shared memory (two block barriers per plane).
+template <int WPP>
+__device__ __forceinline__ float wpj_sum(float v, float* red, int warp) {
+  v = warp_sum(v);
+  if (WPP == 1) return v;
+  __syncthreads();                       // the previous use of `red` has been read by everyone
+  if ((threadIdx.x & 31) == 0) red[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < WPP; ++q) s += red[q];
+  return s;
+}
+template <int WPP>
+__device__ __forceinline__ float wpj_max(float v, float* red, int warp) {
+  v = warp_max(v);
+  if (WPP == 1) return v;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[warp] = v;
+  __syncthreads();
+  float m = red[0];
+#pragma unroll
+  for (int q = 1; q < WPP; ++q) m = fmaxf(m, red[q]);
+  return m;
+}
+
+template <int NV, bool FROM_LOGITS, int WPP>
+__global__ void __launch_bounds__(WPP > 1 ? 32 * WPP : (NV > 8 ? 128 : 256), 2)
+tail_fwd_wpj_kernel(const FwdArgs A, const int BJ, const int wshift) {
   pdl_trigger();
   pdl_wait();
+  __shared__ float red[4];
   const int W = A.g.W, H = A.g.H, HW = A.g.HW;
   const int lane = threadIdx.x & 31;
-  const int bj = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5;
+  const int sl = WPP > 1 ? warp : 0;             // this warp's slice of the plane (WPP > 1: one (sample, joint) per block)
+  const int bj = WPP > 1 ? (int)blockIdx.x : blockIdx.x * (blockDim.x >> 5) + warp;
   if (bj >= BJ) return;
   const int w0 = (lane * 4) & (W - 1);
   const int rpi = 128 >> wshift;                 // rows between a lane's consecutive float4 slots
-  const int h0 = (lane * 4) >> wshift;
+  const int h0 = ((sl * NV * 32 + lane) * 4) >> wshift;
   const float col_mult = (float)W * (1.0f / 128.0f);   // a column is held by 128 / W lanes, a row by W / 4
   const float row_mult = 4.0f / (float)W;
   float cw[4];
@@ -1290,7 +1321,8 @@ __global__ void __launch_bounds__(NV > 8 ? 128 : 256, 2) tail_fwd_wpj_kernel(con
     if (!A.in[k]) continue;
     float4 x[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) x[i] = __ldg(reinterpret_cast<const float4*>(A.in[k] + off + (i * 32 + lane) * 4));
+    for (int i = 0; i < NV; ++i)
+      x[i] = __ldg(reinterpret_cast<const float4*>(A.in[k] + off + ((sl * NV + i) * 32 + lane) * 4));
     float mc, mr;
     bool want_js;
     if (A.mu[k]) {
@@ -1301,12 +1333,13 @@ __global__ void __launch_bounds__(NV > 8 ? 128 : 256, 2) tail_fwd_wpj_kernel(con
       mr = (k == 2) ? tz : ty;
       want_js = A.target && A.pixelwise && (A.loss || A.js[k]) && (k == 0 || is3d);
     }
+    if (WPP > 1) want_js = false;        // (the host only selects WPP > 1 when no JS term is requested)
     float m = 0.f;
     if (FROM_LOGITS) {
       m = -INFINITY;
 #pragma unroll
       for (int i = 0; i < NV; ++i) m = fmaxf(m, fmaxf(fmaxf(x[i].x, x[i].y), fmaxf(x[i].z, x[i].w)));
-      m = warp_max(m);
+      m = wpj_max<WPP>(m, red, warp);
     }
     const float m2 = m * L2E;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accx = 0.f;
@@ -1343,7 +1376,7 @@ __global__ void __launch_bounds__(NV > 8 ? 128 : 256, 2) tail_fwd_wpj_kernel(con
         x[i] = make_float4(v[0], v[1], v[2], v[3]);
       }
     }
-    acc0 = warp_sum(acc0); acc1 = warp_sum(acc1); acc2 = warp_sum(acc2);
+    acc0 = wpj_sum<WPP>(acc0, red, warp); acc1 = wpj_sum<WPP>(acc1, red, warp); acc2 = wpj_sum<WPP>(acc2, red, warp);
     float inv = 1.f, l2inv = 0.f, ea, eb;
     if (FROM_LOGITS) {
       inv = 1.0f / acc0;
@@ -1402,15 +1435,16 @@ __global__ void __launch_bounds__(NV > 8 ? 128 : 256, 2) tail_fwd_wpj_kernel(con
     }
     if (A.prob[k]) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(A.prob[k] + off + (i * 32 + lane) * 4) = x[i];
+      for (int i = 0; i < NV; ++i)
+        *reinterpret_cast<float4*>(A.prob[k] + off + ((sl * NV + i) * 32 + lane) * 4) = x[i];
     }
     pa[k] = ea; pb[k] = eb; pj[k] = js;
-    if (lane == 0) {
+    if (lane == 0 && sl == 0) {
       if (A.ab[k]) { A.ab[k][bj * 2 + 0] = ea; A.ab[k][bj * 2 + 1] = eb; }
       if (A.js[k]) A.js[k][bj] = js;
     }
   }
-  if (lane != 0) return;
+  if (lane != 0 || sl != 0) return;
   const float px = pa[0], py = pb[0], pz = 0.5f * (pa[1] + pb[2]);   // models/margipose_model.py:254-261
   if (A.coords) { A.coords[bj * 3 + 0] = px; A.coords[bj * 3 + 1] = py; A.coords[bj * 3 + 2] = pz; }
   if (A.loss && A.target) {
@@ -1634,10 +1668,17 @@ int launch_fwd(const FwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
     if (nv) {
       const int wpb = nv > 8 ? 4 : 8;
       const dim3 grid((BJ + wpb - 1) / wpb), block(32 * wpb);
-#define MP_FWDJ(NV) mp_launch(tail_fwd_wpj_kernel<NV, FROM_LOGITS>, grid, block, 0, st, A, BJ, wsh)
+#define MP_FWDJ(NV) mp_launch(tail_fwd_wpj_kernel<NV, FROM_LOGITS, 1>, grid, block, 0, st, A, BJ, wsh)
       if (nv == 1) MP_FWDJ(1); else if (nv == 2) MP_FWDJ(2); else if (nv == 4) MP_FWDJ(4); else if (nv == 8) MP_FWDJ(8);
       else if (nv == 16) MP_FWDJ(16); else MP_FWDJ(32);
 #undef MP_FWDJ
+      return MP_OK;
+    }
+    // larger planes without a JS term: 2 or 4 warps (one block) per plane, 32 float4 per lane
+    if (!with_js && wsh >= 0 && g_tail_wpj_max >= 32 && (HW == 2 * 32 * 128 || HW == 4 * 32 * 128)) {
+      const dim3 grid(BJ);
+      if (HW == 2 * 32 * 128) mp_launch(tail_fwd_wpj_kernel<32, FROM_LOGITS, 2>, grid, dim3(64), 0, st, A, BJ, wsh);
+      else mp_launch(tail_fwd_wpj_kernel<32, FROM_LOGITS, 4>, grid, dim3(128), 0, st, A, BJ, wsh);
       return MP_OK;
     }
   }
