@@ -18,7 +18,7 @@
 long long g_tail_fast = 1;   // tunable "tail_fast": 1 = the log2-domain kernels for row lengths dividing 128
 long long g_tail_wpj_max = 32;   // tunable "tail_wpj_max": largest plane (in float4 per lane) of the forward warp-per-joint kernel
 long long g_tail_cap = 4;    // tunable "tail_cap": float4 slots per lane the warp plan tries first (4 or 8)
-long long g_tail_wpj = 1;    // tunable "tail_wpj": 1 = warp-per-joint kernels for planes of at most 1024 elements
+long long g_tail_wpj = 2;    // tunable "tail_wpj": 1 = warp-per-joint kernels for planes of at most 1024 elements, 2 = also their multi-warp variants with the JS term / backward for larger planes
 long long g_tail_waves = 0;  // tunable "tail_ctas_per_sm": persistent CTAs per SM of the fast kernels (0 = one CTA per group)
 
 namespace {
@@ -960,6 +960,7 @@ __global__ void __launch_bounds__(512, 2) tail_fwd_fast_kernel(const FwdArgs A, 
           accx = fmaf(ev, v[j], accx);
           rowsum += ev;
           acc1 = fmaf(ev, cw[j], acc1);
+          v[j] = ev;
         }
         acc0 += rowsum;
         acc2 = fmaf(rowsum, centre(h0 + i * rpi, A.g.ch_step, A.g.ch_first), acc2);
@@ -1022,7 +1023,7 @@ __global__ void __launch_bounds__(512, 2) tail_fwd_fast_kernel(const FwdArgs A, 
         const float er = tab[W + h0 + i * rpi] * ginv;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (FROM_LOGITS) pv[j] = fast_ex2(pv[j] + l2inv);
+          if (FROM_LOGITS) pv[j] *= inv;
           else plp = fmaf(pv[j], fast_lg2(pv[j] + KL_EPS), plp);
           const float sq = fmaf(qc[j], er, pv[j]);                 // p + q
           slm = fmaf(sq, fast_lg2(fmaf(0.5f, sq, KL_EPS)), slm);
@@ -1265,37 +1266,60 @@ __global__ void __launch_bounds__(512, 2) tail_bwd_fast_kernel(const BwdArgs A, 
 // drops from ~800 instructions per warp (fast kernels above) to ~200.
 // WPP > 1 (softmax + expectations only, no JS term): WPP warps = one block share a plane of up to 16384 elements (128 x 128),
 // 32 float4 per lane each; their partial maxima / sums meet in 16 floats of shared memory (two block barriers per plane).
-template <int WPP>
-__device__ __forceinline__ float wpj_sum(float v, float* red, int warp) {
-  v = warp_sum(v);
-  if (WPP == 1) return v;
-  __syncthreads();                       // the previous use of `red` has been read by everyone
-  if ((threadIdx.x & 31) == 0) red[warp] = v;
-  __syncthreads();
-  float s = 0.f;
+// Block-wide sums / maximum of the WPP warps that share a plane: shuffle tree, lane 0 of every warp posts its N partial
+// values as one float4, ONE block barrier, every warp folds the WPP posts with log2(WPP) more shuffles.  Consecutive
+// reductions alternate between two shared-memory buffers (`phase`), so a buffer is rewritten only after a later barrier
+// has proved that everyone finished reading it.
+template <int WPP, int N>
+__device__ __forceinline__ void wpj_sum_n(float (&v)[N], float4* red, int& phase, int warp, int lane) {
+  static_assert(N <= 4, "one float4 per warp");
 #pragma unroll
-  for (int q = 0; q < WPP; ++q) s += red[q];
-  return s;
+  for (int n = 0; n < N; ++n) v[n] = warp_sum(v[n]);
+  if (WPP == 1) return;
+  float4* r = red + (phase & 1) * 16;
+  ++phase;
+  if (lane == 0) r[warp] = make_float4(v[0], N > 1 ? v[N > 1 ? 1 : 0] : 0.f, N > 2 ? v[N > 2 ? 2 : 0] : 0.f, N > 3 ? v[N > 3 ? 3 : 0] : 0.f);
+  __syncthreads();
+  float4 t = r[lane & (WPP - 1)];
+#pragma unroll
+  for (int o = WPP >> 1; o > 0; o >>= 1) {
+    t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
+    if (N > 1) t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+    if (N > 2) t.z += __shfl_xor_sync(0xffffffffu, t.z, o);
+    if (N > 3) t.w += __shfl_xor_sync(0xffffffffu, t.w, o);
+  }
+  v[0] = t.x;
+  if (N > 1) v[N > 1 ? 1 : 0] = t.y;
+  if (N > 2) v[N > 2 ? 2 : 0] = t.z;
+  if (N > 3) v[N > 3 ? 3 : 0] = t.w;
 }
 template <int WPP>
-__device__ __forceinline__ float wpj_max(float v, float* red, int warp) {
+__device__ __forceinline__ float wpj_sum(float v, float4* red, int& phase, int warp, int lane) {
+  float a[1] = {v};
+  wpj_sum_n<WPP, 1>(a, red, phase, warp, lane);
+  return a[0];
+}
+template <int WPP>
+__device__ __forceinline__ float wpj_max(float v, float4* red, int& phase, int warp, int lane) {
   v = warp_max(v);
   if (WPP == 1) return v;
+  float4* r = red + (phase & 1) * 16;
+  ++phase;
+  if (lane == 0) r[warp].x = v;
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[warp] = v;
-  __syncthreads();
-  float m = red[0];
+  float m = r[lane & (WPP - 1)].x;
 #pragma unroll
-  for (int q = 1; q < WPP; ++q) m = fmaxf(m, red[q]);
+  for (int o = WPP >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   return m;
 }
 
 template <int NV, bool FROM_LOGITS, int WPP>
-__global__ void __launch_bounds__(WPP > 1 ? 32 * WPP : (NV > 8 ? 128 : 256), 2)
+__global__ void __launch_bounds__(WPP > 1 ? 32 * WPP : (NV > 8 ? 128 : 256), (WPP > 1 && NV <= 16) ? (WPP >= 16 ? 1 : 16 / WPP) : 2)
 tail_fwd_wpj_kernel(const FwdArgs A, const int BJ, const int wshift) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float red[4];
+  __shared__ float4 red[WPP > 1 ? 32 : 1];
+  int phase = 0;
   const int W = A.g.W, H = A.g.H, HW = A.g.HW;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -1333,13 +1357,12 @@ tail_fwd_wpj_kernel(const FwdArgs A, const int BJ, const int wshift) {
       mr = (k == 2) ? tz : ty;
       want_js = A.target && A.pixelwise && (A.loss || A.js[k]) && (k == 0 || is3d);
     }
-    if (WPP > 1) want_js = false;        // (the host only selects WPP > 1 when no JS term is requested)
     float m = 0.f;
     if (FROM_LOGITS) {
       m = -INFINITY;
 #pragma unroll
       for (int i = 0; i < NV; ++i) m = fmaxf(m, fmaxf(fmaxf(x[i].x, x[i].y), fmaxf(x[i].z, x[i].w)));
-      m = wpj_max<WPP>(m, red, warp);
+      m = wpj_max<WPP>(m, red, phase, warp, lane);
     }
     const float m2 = m * L2E;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accx = 0.f;
@@ -1355,6 +1378,7 @@ tail_fwd_wpj_kernel(const FwdArgs A, const int BJ, const int wshift) {
           accx = fmaf(ev, v[j], accx);
           rowsum += ev;
           acc1 = fmaf(ev, cw[j], acc1);
+          v[j] = ev;
         }
         acc0 += rowsum;
         acc2 = fmaf(rowsum, centre(h0 + i * rpi, A.g.ch_step, A.g.ch_first), acc2);
@@ -1376,7 +1400,11 @@ tail_fwd_wpj_kernel(const FwdArgs A, const int BJ, const int wshift) {
         x[i] = make_float4(v[0], v[1], v[2], v[3]);
       }
     }
-    acc0 = wpj_sum<WPP>(acc0, red, warp); acc1 = wpj_sum<WPP>(acc1, red, warp); acc2 = wpj_sum<WPP>(acc2, red, warp);
+    {
+      float a3[3] = {acc0, acc1, acc2};
+      wpj_sum_n<WPP, 3>(a3, red, phase, warp, lane);
+      acc0 = a3[0]; acc1 = a3[1]; acc2 = a3[2];
+    }
     float inv = 1.f, l2inv = 0.f, ea, eb;
     if (FROM_LOGITS) {
       inv = 1.0f / acc0;
@@ -1407,8 +1435,12 @@ tail_fwd_wpj_kernel(const FwdArgs A, const int BJ, const int wshift) {
         sr += qri;
         ar = fmaf(qri, lg, ar);
       }
-      sc = warp_sum(sc) * col_mult; ac = warp_sum(ac) * col_mult;
-      sr = warp_sum(sr) * row_mult; ar = warp_sum(ar) * row_mult;
+      sc = warp_sum(sc) * col_mult; ac = warp_sum(ac) * col_mult;     // every warp holds whole rows: all columns
+      {
+        float r2[2] = {sr, ar};                                          // the rows are spread over the plane's warps
+        wpj_sum_n<WPP, 2>(r2, red, phase, warp, lane);
+        sr = r2[0] * row_mult; ar = r2[1] * row_mult;
+      }
       const float ginv = 1.0f / (sc * sr + KL_EPS);
       float slm = 0.f, plp = 0.f;
 #pragma unroll
@@ -1418,15 +1450,15 @@ tail_fwd_wpj_kernel(const FwdArgs A, const int BJ, const int wshift) {
         const float er = fast_ex2(__fmul_rn(__fmul_rn(dr, dr), A.g.kh) * L2E) * ginv;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (FROM_LOGITS) pv[j] = fast_ex2(pv[j] + l2inv);
+          if (FROM_LOGITS) pv[j] *= inv;
           else plp = fmaf(pv[j], fast_lg2(pv[j] + KL_EPS), plp);
           const float sq = fmaf(qc[j], er, pv[j]);
           slm = fmaf(sq, fast_lg2(fmaf(0.5f, sq, KL_EPS)), slm);
         }
         x[i] = make_float4(pv[0], pv[1], pv[2], pv[3]);
       }
-      float jsp = warp_sum(plp - slm);
-      if (FROM_LOGITS) jsp += fmaf(warp_sum(accx), inv, l2inv);        // sum p lg p
+      float jsp = wpj_sum<WPP>(FROM_LOGITS ? fmaf(accx, inv, plp - slm) : plp - slm, red, phase, warp, lane);
+      if (FROM_LOGITS) jsp += l2inv;                                   // sum p lg p = (sum e t) / (sum e) - lg2(sum e)
       jsp += fmaf(ginv, fmaf(ac, sr, sc * ar), log2f(ginv) * (sc * sr * ginv));   // sum q lg q (exponents are log2 already)
       js = 0.5f * jsp * LN2;
     } else if (FROM_LOGITS) {
@@ -1456,17 +1488,22 @@ tail_fwd_wpj_kernel(const FwdArgs A, const int BJ, const int wshift) {
   }
 }
 
-template <int NV, bool PROJECT>
-__global__ void __launch_bounds__(256, 2) tail_bwd_wpj_kernel(const BwdArgs A, const int BJ, const int wshift) {
+template <int NV, bool PROJECT, int WPP>
+__global__ void __launch_bounds__(WPP > 1 ? 32 * WPP : 256, WPP > 1 ? (WPP >= 16 ? 1 : 16 / WPP) : 2)
+tail_bwd_wpj_kernel(const BwdArgs A, const int BJ, const int wshift) {
   pdl_trigger();
   pdl_wait();
+  __shared__ float4 red[WPP > 1 ? 32 : 1];
+  int phase = 0;
   const int W = A.g.W, HW = A.g.HW;
   const int lane = threadIdx.x & 31;
-  const int bj = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5;
+  const int sl = WPP > 1 ? warp : 0;             // this warp's slice of the plane (WPP > 1: one (sample, joint) per block)
+  const int bj = WPP > 1 ? (int)blockIdx.x : blockIdx.x * (blockDim.x >> 5) + warp;
   if (bj >= BJ) return;
   const int w0 = (lane * 4) & (W - 1);
   const int rpi = 128 >> wshift;
-  const int h0 = (lane * 4) >> wshift;
+  const int h0 = ((sl * NV * 32 + lane) * 4) >> wshift;
   const float col_mult = (float)W * (1.0f / 128.0f), row_mult = 4.0f / (float)W;
   float cw[4];
 #pragma unroll
@@ -1489,8 +1526,8 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_wpj_kernel(const BwdArgs A, c
     float4 p[NV], d[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      p[i] = __ldg(reinterpret_cast<const float4*>(A.prob[k] + off + (i * 32 + lane) * 4));
-      d[i] = A.gup[k] ? __ldg(reinterpret_cast<const float4*>(A.gup[k] + off + (i * 32 + lane) * 4))
+      p[i] = __ldg(reinterpret_cast<const float4*>(A.prob[k] + off + ((sl * NV + i) * 32 + lane) * 4));
+      d[i] = A.gup[k] ? __ldg(reinterpret_cast<const float4*>(A.gup[k] + off + ((sl * NV + i) * 32 + lane) * 4))
                       : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float wjs, cc, cr, mc, mr;
@@ -1529,7 +1566,7 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_wpj_kernel(const BwdArgs A, c
         qr[i] = fast_ex2(__fmul_rn(__fmul_rn(dd, dd), A.g.kh) * L2E);
         sr += qr[i];
       }
-      ginv = 1.0f / (warp_sum(sc) * col_mult * (warp_sum(sr) * row_mult) + KL_EPS);
+      ginv = 1.0f / (warp_sum(sc) * col_mult * (wpj_sum<WPP>(sr, red, phase, warp, lane) * row_mult) + KL_EPS);
     }
     const float kjs = 0.5f * wjs * LN2, hjs = 0.5f * wjs;
     const float TINY = 2e-16f;
@@ -1568,7 +1605,7 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_wpj_kernel(const BwdArgs A, c
       d[i] = make_float4(dv[0], dv[1], dv[2], dv[3]);
     }
     if (PROJECT) {
-      part = warp_sum(part);
+      part = wpj_sum<WPP>(part, red, phase, warp, lane);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         d[i].x = p[i].x * (d[i].x - part); d[i].y = p[i].y * (d[i].y - part);
@@ -1576,7 +1613,7 @@ __global__ void __launch_bounds__(256, 2) tail_bwd_wpj_kernel(const BwdArgs A, c
       }
     }
 #pragma unroll
-    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(A.out[k] + off + (i * 32 + lane) * 4) = d[i];
+    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(A.out[k] + off + ((sl * NV + i) * 32 + lane) * 4) = d[i];
   }
 }
 
@@ -1674,12 +1711,29 @@ int launch_fwd(const FwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
 #undef MP_FWDJ
       return MP_OK;
     }
-    // larger planes without a JS term: 2 or 4 warps (one block) per plane, 32 float4 per lane
+    // larger planes: several warps (one block) per plane.  Without a JS term 2 or 4 warps of 32 float4 per lane; with it
+    // 8 float4 per lane (the JS pass needs the registers), i.e. 2 ... 16 warps for 2048 ... 16384 elements.
     if (!with_js && wsh >= 0 && g_tail_wpj_max >= 32 && (HW == 2 * 32 * 128 || HW == 4 * 32 * 128)) {
       const dim3 grid(BJ);
       if (HW == 2 * 32 * 128) mp_launch(tail_fwd_wpj_kernel<32, FROM_LOGITS, 2>, grid, dim3(64), 0, st, A, BJ, wsh);
       else mp_launch(tail_fwd_wpj_kernel<32, FROM_LOGITS, 4>, grid, dim3(128), 0, st, A, BJ, wsh);
       return MP_OK;
+    }
+    if (with_js && wsh >= 0 && g_tail_wpj >= 2 && HW % 1024 == 0) {
+      const int wpp = HW / 1024;
+      const dim3 grid(BJ), block(32 * wpp);
+#define MP_FWDM(WPP) mp_launch(tail_fwd_wpj_kernel<8, FROM_LOGITS, WPP>, grid, block, 0, st, A, BJ, wsh)
+      // 16 float4 per lane where the plane is large enough for two warps of them: fewer, longer-lived warps overlap their
+      // load / compute / store phases better (128 x 128: 0.81 of the HBM peak against 0.52 with 16 warps of 8 float4,
+      // 64 x 64: 0.83 against 0.71; tunable tail_wpj=3 selects the narrow variants)
+#define MP_FWDM16(WPP) mp_launch(tail_fwd_wpj_kernel<16, FROM_LOGITS, WPP>, grid, dim3(32 * WPP), 0, st, A, BJ, wsh)
+      const bool wide = g_tail_wpj != 3;
+      if (wpp == 2) { MP_FWDM(2); return MP_OK; }
+      if (wpp == 4) { if (wide) MP_FWDM16(2); else MP_FWDM(4); return MP_OK; }
+      if (wpp == 8) { if (wide) MP_FWDM16(4); else MP_FWDM(8); return MP_OK; }
+      if (wpp == 16) { if (wide) MP_FWDM16(8); else MP_FWDM(16); return MP_OK; }
+#undef MP_FWDM16
+#undef MP_FWDM
     }
   }
   if (vec4) {
@@ -1736,10 +1790,20 @@ int launch_bwd(const BwdArgs& A, int BJ, bool vec4, cudaStream_t st) {
     const int nv = wpj_slots(A.g.H, A.g.W, wsh, 8);   // backward holds p AND the gradient: 1024 elements per warp at most
     if (nv) {
       const dim3 grid((BJ + 7) / 8), block(256);
-#define MP_BWDJ(NV) mp_launch(tail_bwd_wpj_kernel<NV, PROJECT>, grid, block, 0, st, A, BJ, wsh)
+#define MP_BWDJ(NV) mp_launch(tail_bwd_wpj_kernel<NV, PROJECT, 1>, grid, block, 0, st, A, BJ, wsh)
       if (nv == 1) MP_BWDJ(1); else if (nv == 2) MP_BWDJ(2); else if (nv == 4) MP_BWDJ(4); else MP_BWDJ(8);
 #undef MP_BWDJ
       return MP_OK;
+    }
+    if (wsh >= 0 && g_tail_wpj >= 2 && HW % 1024 == 0) {   // larger planes: 2 ... 16 warps (one block) per plane
+      const int wpp = HW / 1024;
+      const dim3 grid(BJ), block(32 * wpp);
+#define MP_BWDM(WPP) mp_launch(tail_bwd_wpj_kernel<8, PROJECT, WPP>, grid, block, 0, st, A, BJ, wsh)
+      if (wpp == 2) { MP_BWDM(2); return MP_OK; }
+      if (wpp == 4) { MP_BWDM(4); return MP_OK; }
+      if (wpp == 8) { MP_BWDM(8); return MP_OK; }
+      if (wpp == 16) { MP_BWDM(16); return MP_OK; }
+#undef MP_BWDM
     }
   }
   if (vec4) {
