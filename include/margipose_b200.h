@@ -414,9 +414,13 @@ MP_API int mp_sgd_step_hp(float* param, const float* grad, float* momentum_buf, 
  *                   NHWC; default 1 (the backward kernels share SMs with the weight-gradient kernels, see csrc/bn.cu)
  *   "tail_fast"   : 1 (default) = mp_tail_fwd / mp_tail_bwd use the log2-domain kernels when the heatmap width divides 128;
  *                   0 = the general warp-sliced kernels
- *   "tail_wpj"    : 1 (default) = planes of at most 1024 elements (the model's 32 x 32 heatmaps) use the warp-per-joint
- *                   kernels (a whole plane in one warp's registers, no shared memory, no block barriers)
- *   "tail_ctas_per_sm": > 0 caps their grid at that many (persistent) CTAs per SM (default 0 = one CTA per (sample, joint) group) */
+ *   "tail_wpj"    : register-resident "warp per joint" kernels (no shared-memory staging) for planes whose row length is a
+ *                   power of two <= 128: 0 = off, 1 = planes of at most 1024 elements (the model's 32 x 32 heatmaps; 4096
+ *                   without a JS term) in one warp, 2 (default) = also larger planes (multiples of 1024 elements up to
+ *                   128 x 128) in 2 ... 16 warps, 3 = same with 8 instead of 16 float4 per lane in the forward (slower)
+ *   "tail_wpj_max": most float4 per lane of the one-warp forward kernel without a JS term (default 32 = 64 x 64 planes)
+ *   "tail_cap"    : float4 per lane the shared-memory (fast / warp) kernels plan for, 4 (default) or 8
+ *   "tail_ctas_per_sm": > 0 caps the grid of the shared-memory (fast) kernels at that many (persistent) CTAs per SM (default 0 = one CTA per (sample, joint) group) */
 MP_API int mp_set_tunable(const char* name, int64_t value);
 
 #ifdef __cplusplus
