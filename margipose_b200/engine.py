@@ -378,6 +378,9 @@ class Engine:
         # reductions get one replica per block, weight gradients run without split-K (tunable "deterministic")
         self.det = bool(getattr(model, 'deterministic', False)) or \
             os.environ.get('MARGIPOSE_B200_DETERMINISTIC', '0') == '1'
+        # BatchNorm coefficients from the conv epilogue's sums: by the conv's last CTA (True) or by the consuming mp_bn_fwd
+        # itself (False: no ticket / fence / finalise tail in the conv kernel)
+        self.conv_finalize = (not self.det) and os.environ.get('MARGIPOSE_B200_CONV_FINALIZE', '1') != '0'
         self.R = 32 if self.det else 1     # forward statistics
         self.RB = 32 if self.det else 4    # backward reductions: the blocks spread over RB copies of the sums
         n_stat = (self.R + 2 * self.RB) * self.L.bn_floats
@@ -645,7 +648,7 @@ class Engine:
             br.running_mean, br.running_var = bn.rm.data.data_ptr(), bn.rv.data.data_ptr()
             br.save_mean = vbase + 4 * bn.slot
             br.save_invstd = vbase + 4 * (bn.slot + bn.Cp)
-            if self.training and not self.det:      # finalised by the producing conv's last CTA
+            if self.training and self.conv_finalize:      # finalised by the producing conv's last CTA
                 br.scale = self.affine.data_ptr() + 4 * bn.slot
                 br.shift = self.affine.data_ptr() + 4 * (bn.slot + bn.Cp)
             if self.training:
@@ -683,6 +686,7 @@ class Engine:
         stats = fin = None
         if self.training and bn is not None and not self.det:
             stats = self.stats_of(bn)
+        if stats is not None and self.conv_finalize:
             branch = BnBranch()
             probe = self.bn_args(bn, y)
             ctypes.memmove(ctypes.addressof(branch), ctypes.addressof(probe.a), ctypes.sizeof(BnBranch))
