@@ -169,6 +169,39 @@ __device__ __forceinline__ void affine(const mp_bn_args& A, const mp_bn_branch& 
   }
 }
 
+// Saved statistics + running buffers of one BatchNorm (one thread row of one block per launch).  Every load is issued
+// before the first store: interleaved read-modify-writes form a chain of dependent L2 / DRAM round trips that holds
+// this thread row's share of the streaming loop back by several microseconds.
+__device__ __noinline__ void bookkeeping(const mp_bn_args& A, const mp_bn_branch& br, int c0) {
+  if (br.scale && A.training) return;     // the producing conv already did it
+  float mean[8], invstd[8], var[8];
+  channel_stats8(A, br, c0, false, mean, invstd, var);
+  const bool run = A.training && br.running_mean;
+  float rm[8], rv[8], bias[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    const bool ok = run && c < A.C;
+    rm[i] = ok ? br.running_mean[c] : 0.f;
+    rv[i] = ok ? br.running_var[c] : 0.f;
+    bias[i] = (ok && br.conv_bias) ? br.conv_bias[c] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    if (c >= A.C) continue;
+    if (br.save_mean) {
+      br.save_mean[c] = mean[i];
+      br.save_invstd[c] = invstd[i];
+    }
+    if (run) {
+      const float unbiased = A.M > 1 ? var[i] * ((float)A.M / (float)(A.M - 1)) : var[i];
+      br.running_mean[c] = (1.f - A.momentum) * rm[i] + A.momentum * (mean[i] + bias[i]);
+      br.running_var[c] = (1.f - A.momentum) * rv[i] + A.momentum * unbiased;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------- forward
 template <bool SPLIT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) bn_fwd_kernel(const __grid_constant__ BnGroup GRP) {
@@ -182,26 +215,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bn_fwd_kernel(const __grid_constan
   if (has_b) affine(A, A.b, c0, false, sb, hb);
 
   if (blockIdx.x == 0 && threadIdx.y == 0) {   // bookkeeping: saved statistics + running buffers
-    for (int which = 0; which < (has_b ? 2 : 1); ++which) {
-      const mp_bn_branch& br = which ? A.b : A.a;
-      if (br.scale && A.training) continue;     // the producing conv already did it
-      float mean[8], invstd[8], var[8];
-      channel_stats8(A, br, c0, false, mean, invstd, var);
-      for (int i = 0; i < 8; ++i) {
-        const int c = c0 + i;
-        if (c >= A.C) continue;
-        if (br.save_mean) {
-          br.save_mean[c] = mean[i];
-          br.save_invstd[c] = invstd[i];
-        }
-        if (A.training && br.running_mean) {
-          const float unbiased = A.M > 1 ? var[i] * ((float)A.M / (float)(A.M - 1)) : var[i];
-          const float bias = br.conv_bias ? br.conv_bias[c] : 0.f;
-          br.running_mean[c] = (1.f - A.momentum) * br.running_mean[c] + A.momentum * (mean[i] + bias);
-          br.running_var[c] = (1.f - A.momentum) * br.running_var[c] + A.momentum * unbiased;
-        }
-      }
-    }
+    bookkeeping(A, A.a, c0);
+    if (has_b) bookkeeping(A, A.b, c0);
   }
 
   const long long ppb = (long long)blockDim.y * U;
@@ -443,21 +458,33 @@ __device__ __forceinline__ void bwd_coefs(const mp_bn_args& A, const mp_bn_branc
   rsum8(A.sums + (2 * which + 1) * A.Cp, c0, A.stat_replicas, 4 * A.Cp, s2v);
   load8f(br.save_mean, c0, meanv);      // (Cp)-sized buffers: vector loads, all in flight together
   load8f(br.save_invstd, c0, invv);
+  float gv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) gv[i] = (c0 + i < A.C) ? __ldg(br.gamma + c0 + i) : 0.f;   // (C-sized parameter: guarded scalar loads, no stores in between)
+  float dg[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = c0 + i;
-    scale[i] = kb[i] = kc[i] = 0.f;
+    scale[i] = kb[i] = kc[i] = dg[i] = 0.f;
     if (c >= A.C) continue;
     const float mean = meanv[i], invstd = invv[i];
     const float s1 = s1v[i], s2 = s2v[i];
     const float dgamma = invstd * (s2 - mean * s1);     // sum dz * x^
-    const float sc = br.gamma[c] * invstd;
+    const float sc = gv[i] * invstd;
     scale[i] = sc;
     kb[i] = -sc * dgamma * inv_m * invstd;
     kc[i] = -sc * s1 * inv_m - kb[i] * mean;
-    if (write_param_grads) {
-      if (br.dbeta) br.dbeta[c] += s1;
-      if (br.dgamma) br.dgamma[c] += dgamma;
+    dg[i] = dgamma;
+  }
+  if (write_param_grads) {
+    // One thread per channel and launch adds to the parameter gradients, so the sum is still deterministic; the
+    // result-less atomics (RED) cost no load latency -- a read-modify-write chain here (16 dependent L2 / DRAM round
+    // trips) held this thread row's share of the streaming loop back by ~10 us per launch.
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (c0 + i >= A.C) continue;
+      if (br.dbeta) atomicAdd(br.dbeta + c0 + i, s1v[i]);
+      if (br.dgamma) atomicAdd(br.dgamma + c0 + i, dg[i]);
     }
   }
 }
@@ -650,26 +677,8 @@ __global__ void __launch_bounds__(MAXT, 2) bn_fwd_tma_kernel(const __grid_consta
   affine(A, A.a, c0, false, sa, ha);
   if (has_b) affine(A, A.b, c0, false, sb, hb);
   if (blockIdx.x == 0 && threadIdx.y == 0) {   // bookkeeping: saved statistics + running buffers
-    for (int which = 0; which < (has_b ? 2 : 1); ++which) {
-      const mp_bn_branch& br = which ? A.b : A.a;
-      if (br.scale && A.training) continue;     // the producing conv already did it
-      float mean[8], invstd[8], var[8];
-      channel_stats8(A, br, c0, false, mean, invstd, var);
-      for (int i = 0; i < 8; ++i) {
-        const int c = c0 + i;
-        if (c >= A.C) continue;
-        if (br.save_mean) {
-          br.save_mean[c] = mean[i];
-          br.save_invstd[c] = invstd[i];
-        }
-        if (A.training && br.running_mean) {
-          const float unbiased = A.M > 1 ? var[i] * ((float)A.M / (float)(A.M - 1)) : var[i];
-          const float bias = br.conv_bias ? br.conv_bias[c] : 0.f;
-          br.running_mean[c] = (1.f - A.momentum) * br.running_mean[c] + A.momentum * (mean[i] + bias);
-          br.running_var[c] = (1.f - A.momentum) * br.running_var[c] + A.momentum * unbiased;
-        }
-      }
-    }
+    bookkeeping(A, A.a, c0);
+    if (has_b) bookkeeping(A, A.b, c0);
   }
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(A.out);
   for (long long t = R.t_lo; t < R.t_hi; ++t) {
