@@ -478,18 +478,22 @@ igemm_kernel(const __grid_constant__ IgemmMaps TM, const __grid_constant__ Igemm
           for (int c = et; c < P.fin_Cp; c += EPI_THREADS) {
             float scale = 0.f, shift = 0.f;
             if (c < P.fin_C) {
-              const float mean = __ldcg(Q.stat_sum + c) * inv_m;
-              const float var = fmaxf(__ldcg(Q.stat_sq + c) * inv_m - mean * mean, 0.f);
+              // every load before the first store: one L2 / DRAM round trip on the launch's serial tail instead of two
+              const float s1 = __ldcg(Q.stat_sum + c), s2 = __ldcg(Q.stat_sq + c);
+              const float gamma = Q.fin_gamma[c], beta = Q.fin_beta[c];
+              const float rm = Q.fin_rmean ? Q.fin_rmean[c] : 0.f, rv = Q.fin_rmean ? Q.fin_rvar[c] : 0.f;
+              const float bias = Q.fin_bias ? Q.fin_bias[c] : 0.f;
+              const float mean = s1 * inv_m;
+              const float var = fmaxf(s2 * inv_m - mean * mean, 0.f);
               const float invstd = rsqrtf(var + P.fin_eps);
-              scale = Q.fin_gamma[c] * invstd;
-              shift = fmaf(-mean, scale, Q.fin_beta[c]);
+              scale = gamma * invstd;
+              shift = fmaf(-mean, scale, beta);
               Q.fin_smean[c] = mean;
               Q.fin_sinvstd[c] = invstd;
               if (Q.fin_rmean) {
                 const float unbiased = P.fin_count > 1 ? var * ((float)P.fin_count / (float)(P.fin_count - 1)) : var;
-                const float bias = Q.fin_bias ? Q.fin_bias[c] : 0.f;
-                Q.fin_rmean[c] = (1.f - P.fin_momentum) * Q.fin_rmean[c] + P.fin_momentum * (mean + bias);
-                Q.fin_rvar[c] = (1.f - P.fin_momentum) * Q.fin_rvar[c] + P.fin_momentum * unbiased;
+                Q.fin_rmean[c] = (1.f - P.fin_momentum) * rm + P.fin_momentum * (mean + bias);
+                Q.fin_rvar[c] = (1.f - P.fin_momentum) * rv + P.fin_momentum * unbiased;
               }
             }
             Q.fin_scale[c] = scale;

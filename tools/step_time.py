@@ -13,7 +13,10 @@ for kv in sys.argv[1:]:
     assert lib().mp_set_tunable(k.encode(), int(v)) == 0, kv
 B = int(os.environ.get('BATCH', '32'))
 torch.manual_seed(0)
-model = create_model(bench.DESC).cuda().train()
+model = create_model(bench.DESC)
+if os.environ.get('PRECISION'):
+    model.set_precision(os.environ['PRECISION'])
+model = model.cuda().train()
 x = torch.randn(B, 3, 256, 256, device='cuda')
 model(x)
 eng = model.engine_for(B, 256, 256, True)
@@ -34,6 +37,7 @@ def time_graph(segs, reps=5):
 
 
 f, b = time_graph(eng.fwd), time_graph(eng.bwd)
-cls = {n: eng.time_kernel_class(n)[1] for n in ('mp_conv_igemm', 'mp_conv_wgrad')}
-print('%-60s fwd %6.2f  bwd %6.2f  sum %6.2f ms | serial igemm %.2f wgrad %.2f' % (
-    ' '.join(sys.argv[1:]) or '(defaults)', f, b, f + b, cls['mp_conv_igemm'], cls['mp_conv_wgrad']))
+cls = {n: eng.time_kernel_class(n)[1] for n in ('mp_conv_igemm', 'mp_conv_wgrad', 'mp_bn_fwd', 'mp_bn_bwd_reduce', 'mp_bn_bwd_apply')}
+print('%-40s fwd %6.2f  bwd %6.2f  sum %6.2f ms | serial igemm %.2f wgrad %.2f bn %.2f / %.2f / %.2f' % (
+    ' '.join(sys.argv[1:]) or '(defaults)', f, b, f + b, cls['mp_conv_igemm'], cls['mp_conv_wgrad'], cls['mp_bn_fwd'],
+    cls['mp_bn_bwd_reduce'], cls['mp_bn_bwd_apply']))
