@@ -10,8 +10,9 @@ backward (+ one gradient all-reduce when N > 1) + SGD-momentum update, synthetic
 seeded random-init weights (no network for datasets / checkpoints).
 
   value : steps run from device-resident inputs (CUDA events, max over ranks)
-  e2e   : the same step through the public API (margipose_b200.train.TrainStep.__call__) fed from
-          pinned HOST buffers each step, loss read back to the host each step
+  e2e   : the same step through the public API (margipose_b200.train.TrainStep.submit, the call behind
+          TrainStep.__call__) fed from pinned HOST buffers each step, every step's loss read back to the host
+          (step i's loss is waited for after step i + 1 has been queued)
   roofline : the tcgen05 implicit-GEMM conv kernel (mp_conv_igemm: the grouped fprop + dgrad launches
           of one step, each alone on the GPU, replayed from a CUDA graph), algorithmic FLOPs / CUDA-event
           time per launch vs the measured sustained bf16 peak
@@ -486,18 +487,24 @@ def run_b200(args):
     # takes driver locks that delay launches, which the per-step synchronisation of the end-to-end loop below exposes
     clocks = sampler.stop() if rank == 0 else None
 
-    # end to end: pinned host inputs every step, loss read back every step.  As a prefetching loader would, the copy of
-    # batch i + 1 is started (TrainStep.__call__(..., prefetch=next batch): copy stream, staging slot) once step i has been
-    # queued and before its loss is waited for; every step's inputs still cross PCIe inside the timed region.
+    # end to end: pinned host inputs every step, every step's loss read back.  As a prefetching loader would, the copy of
+    # batch i + 1 is started (TrainStep.submit(..., prefetch=next batch): copy stream, staging slot) once step i has been
+    # queued; as an asynchronous logger would, step i's loss (4 bytes into pinned host memory, queued behind the step) is
+    # waited for after step i + 1 has been queued, so the GPU does not idle while the host turns around.  Every step's
+    # inputs cross PCIe and every step's loss is read on the host inside the timed region.
     for i in range(2):
         step(*host_sets[i % len(host_sets)])
     barrier()
     t0 = time.perf_counter()
-    last = None
+    last = pending = None
     step.prefetch(*host_sets[0])
     for i in range(K):
         nxt = host_sets[(i + 1) % len(host_sets)] if i + 1 < K else None
-        last = step(*host_sets[i % len(host_sets)], prefetch=nxt)
+        queued = step.submit(*host_sets[i % len(host_sets)], prefetch=nxt)
+        if pending is not None:
+            last = pending.item()
+        pending = queued
+    last = pending.item()
     torch.cuda.synchronize(dev)
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
@@ -578,7 +585,7 @@ def run_b200(args):
             'inference': infer, 'precise_mode': precise,
             'e2e': {'value': B * world * K / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d,
                     'd2h_bytes_per_step': d2h, 'last_loss': last,
-                    'note': 'TrainStep.__call__ per step; the next batch is announced with TrainStep.prefetch (pinned '
+                    'note': 'TrainStep.submit per step (the call behind TrainStep.__call__), loss of step i read after step i + 1 is queued; the next batch is announced with TrainStep.prefetch (pinned '
                             'host -> staging slot on a copy stream), so its PCIe copy overlaps the running step'},
             'gpu_launches': n_launches, 'clocks': clocks}
     print(json.dumps(line))

@@ -41,6 +41,20 @@ def forward_loss(model, out_var, target_var, mask_var, valid_depth):
     return K.average_loss(losses, mask_var)
 
 
+class PendingLoss:
+    """Loss of a step queued with `TrainStep.submit`: a pinned host scalar the GPU writes when the step is done."""
+
+    def __init__(self, host, event):
+        self.host, self.event = host, event
+
+    def done(self):
+        return self.event.query()
+
+    def item(self):
+        self.event.synchronize()
+        return self.host.item()
+
+
 class TrainStep:
     def __init__(self, model, optimizer, batch, height=256, width=256, use_graph=True, warmup=3,
                  fused_loss=True, overlap_allreduce=True):
@@ -81,6 +95,8 @@ class TrainStep:
         self._slots = []
         self._staged = {}          # id(images tensor) -> slot index
         self._next_slot = 0
+        self._loss_ring = []       # pinned host scalars + events of the steps whose loss has not been read yet
+        self._n_submitted = 0
         # backward program slices [lo, hi) and the flat-gradient ranges that are final after each
         self._pieces = parallel.bucket_plan(self.eng.bwd_marks, self.eng.L.stage_ranges,
                                             model._bank.flat_grad.numel())
@@ -261,19 +277,34 @@ class TrainStep:
         slot['free'].record(cur)
         return True
 
-    def __call__(self, images, targets, mask=None, valid_depth=None, prefetch=None):
-        """Copies one batch in (pinned host tensors copy asynchronously; a batch announced with `prefetch` is
-        already on the device), runs the step and returns the loss as a Python float (a 4-byte device-to-host
-        read, like train_3d.py:167).
-        valid_depth: optional per-sample flags, 1 = 3D loss, 0 = 2D loss (bin/train_3d.py:126-142).
-        prefetch: the NEXT batch as a tuple (images, targets[, mask[, valid_depth]]): its host -> device copy is
-        started after this step's launches have been queued and before its loss is waited for."""
+    def submit(self, images, targets, mask=None, valid_depth=None, prefetch=None):
+        """Queues one step and returns a `PendingLoss` without waiting for the GPU: the batch is copied in (pinned host
+        tensors copy asynchronously; a batch announced with `prefetch` is already on the device), the step's launches
+        and a 4-byte device-to-host copy of its loss are queued, then the NEXT batch's host -> device copy is started
+        (`prefetch`: a tuple (images, targets[, mask[, valid_depth]])).  `PendingLoss.item()` waits for that step only,
+        so a loop that reads step i's loss after submitting step i + 1 never leaves the GPU idle while the host turns
+        around.  Up to four steps may be pending."""
         if not self._take_staged(images):
             self.load(images, targets, mask, valid_depth)
         self.run()
+        if not self._loss_ring:
+            self._loss_ring = [PendingLoss(torch.zeros(1, dtype=torch.float32).pin_memory(), torch.cuda.Event())
+                               for _ in range(4)]
+        pending = self._loss_ring[self._n_submitted % len(self._loss_ring)]
+        self._n_submitted += 1
+        pending.host.copy_(self.loss.reshape(1), non_blocking=True)
+        pending.event.record(torch.cuda.current_stream(self.device))
         if prefetch is not None:
             self.prefetch(*prefetch)
-        return self.loss.item()
+        return pending
+
+    def __call__(self, images, targets, mask=None, valid_depth=None, prefetch=None):
+        """One step, returning its loss as a Python float (a 4-byte device-to-host read, like train_3d.py:167):
+        `submit(...).item()`.
+        valid_depth: optional per-sample flags, 1 = 3D loss, 0 = 2D loss (bin/train_3d.py:126-142).
+        prefetch: the NEXT batch as a tuple (images, targets[, mask[, valid_depth]]): its host -> device copy is
+        started after this step's launches have been queued and before its loss is waited for."""
+        return self.submit(images, targets, mask, valid_depth, prefetch).item()
 
     def launches_per_step(self):
         """Kernel launches of OUR library in one step (for bench.py's gpu_launches)."""

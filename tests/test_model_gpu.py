@@ -606,6 +606,45 @@ def test_train_step_prefetch_is_equivalent_to_direct_loading():
     assert run(True) == run(False)
 
 
+def test_train_step_submit_pipeline_returns_the_same_losses():
+    """TrainStep.submit queues a step and hands back a PendingLoss; reading step i's loss after step i + 1 has been
+    queued (what bench.py's end-to-end loop does) must give the losses of the plain `loss = step(batch)` loop
+    (deterministic mode: bit-identical)."""
+    from margipose_b200 import utils
+    from margipose_b200.models import create_model
+    from margipose_b200.optim import FlatSGD
+    from margipose_b200.train import TrainStep
+    desc = {'type': 'margipose', 'version': '6.0.1', 'settings': dict(n_stages=1, feature_extractor='resnet18')}
+    torch.manual_seed(171)
+    state = create_model(desc).state_dict()
+    batches = [tuple(t.pin_memory() for t in model_inputs(180 + i, 2)) for i in range(3)]
+
+    def run(pipelined):
+        utils.init_algorithms(deterministic=True)
+        try:
+            model = create_model(desc)
+        finally:
+            utils.init_algorithms(deterministic=False)
+        model.load_state_dict(state)
+        model = model.cuda().train()
+        step = TrainStep(model, FlatSGD(model, lr=1e-2, momentum=0.9), batch=2, warmup=1)
+        if not pipelined:
+            return [step(*batches[i % 3]) for i in range(7)]
+        losses, pending = [], None
+        step.prefetch(*batches[0])
+        for i in range(7):
+            queued = step.submit(*batches[i % 3], prefetch=batches[(i + 1) % 3] if i + 1 < 7 else None)
+            if pending is not None:
+                losses.append(pending.item())
+            pending = queued
+        assert isinstance(pending.done(), bool)
+        losses.append(pending.item())
+        return losses
+
+    a, b = run(True), run(False)
+    assert len(a) == 7 and a == b
+
+
 def test_forward_loss_mixed_2d_3d_batches_match_the_reference_loop():
     """bin/train_3d.py:126-142: samples with valid_depth == 1 get the 3D loss, the others the 2D loss; the reference
     stacks them in a per-sample Python loop.  `train.forward_loss` (flag inside the fused tail kernels) and
