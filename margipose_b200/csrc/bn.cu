@@ -127,18 +127,35 @@ __device__ __forceinline__ void channel_stats8(const mp_bn_args& A, const mp_bn_
     }
     return;
   }
+  // (every load below is issued before the first use: a guarded load followed by its use, eight times over, is a chain
+  // of eight dependent L2 / DRAM round trips in front of the block's streaming loop -- tools/bn_scale.py from_sums)
+  if (from_saved) {   // Cp-sized buffers: two 128-bit loads each
+    const float4 m0 = __ldg(reinterpret_cast<const float4*>(br.save_mean + c0)), m1 = __ldg(reinterpret_cast<const float4*>(br.save_mean + c0) + 1);
+    const float4 i0 = __ldg(reinterpret_cast<const float4*>(br.save_invstd + c0)), i1 = __ldg(reinterpret_cast<const float4*>(br.save_invstd + c0) + 1);
+    mean[0] = m0.x; mean[1] = m0.y; mean[2] = m0.z; mean[3] = m0.w; mean[4] = m1.x; mean[5] = m1.y; mean[6] = m1.z; mean[7] = m1.w;
+    invstd[0] = i0.x; invstd[1] = i0.y; invstd[2] = i0.z; invstd[3] = i0.w;
+    invstd[4] = i1.x; invstd[5] = i1.y; invstd[6] = i1.z; invstd[7] = i1.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      var[i] = 0.f;
+      if (c0 + i >= A.C) mean[i] = invstd[i] = 0.f;
+    }
+    return;
+  }
+  float rm[8], rv[8], cb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {   // C-sized module buffers: predicated scalar loads, all in flight together
+    const bool ok = c0 + i < A.C;
+    rm[i] = ok ? br.running_mean[c0 + i] : 0.f;
+    rv[i] = ok ? br.running_var[c0 + i] : 1.f;
+    cb[i] = (ok && br.conv_bias) ? br.conv_bias[c0 + i] : 0.f;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int c = c0 + i;
-    mean[i] = invstd[i] = var[i] = 0.f;
-    if (c >= A.C) continue;
-    if (from_saved) {
-      mean[i] = br.save_mean[c];
-      invstd[i] = br.save_invstd[c];
-    } else {
-      mean[i] = br.running_mean[c] - (br.conv_bias ? br.conv_bias[c] : 0.f);
-      invstd[i] = rsqrtf(br.running_var[c] + A.eps);
-    }
+    const bool ok = c0 + i < A.C;
+    mean[i] = ok ? rm[i] - cb[i] : 0.f;
+    invstd[i] = ok ? rsqrtf(rv[i] + A.eps) : 0.f;
+    var[i] = 0.f;
   }
 }
 
@@ -155,52 +172,90 @@ __device__ __forceinline__ void affine(const mp_bn_args& A, const mp_bn_branch& 
     load8f(br.shift, c0, shift);
     return;
   }
+  float gv[8], bv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {   // C-sized parameters: predicated loads, issued before anything waits on the statistics
+    const bool ok = c0 + i < A.C;
+    gv[i] = ok ? br.gamma[c0 + i] : 0.f;
+    bv[i] = ok ? br.beta[c0 + i] : 0.f;
+  }
   float mean[8], invstd[8], var[8];
   channel_stats8(A, br, c0, from_saved, mean, invstd, var);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int c = c0 + i;
-    scale[i] = 0.f;
-    shift[i] = 0.f;
-    if (c < A.C) {
-      scale[i] = br.gamma[c] * invstd[i];
-      shift[i] = fmaf(-mean[i], scale[i], br.beta[c]);
-    }
+    scale[i] = gv[i] * invstd[i];                 // zero beyond C
+    shift[i] = fmaf(-mean[i], scale[i], bv[i]);
   }
 }
 
-// Saved statistics + running buffers of one BatchNorm (one thread row of one block per launch).  Every load is issued
-// before the first store: interleaved read-modify-writes form a chain of dependent L2 / DRAM round trips that holds
-// this thread row's share of the streaming loop back by several microseconds.
-__device__ __noinline__ void bookkeeping(const mp_bn_args& A, const mp_bn_branch& br, int c0) {
-  if (br.scale && A.training) return;     // the producing conv already did it
-  float mean[8], invstd[8], var[8];
-  channel_stats8(A, br, c0, false, mean, invstd, var);
-  const bool run = A.training && br.running_mean;
-  float rm[8], rv[8], bias[8];
+// Saved statistics + running buffers of one BatchNorm (one thread row of one block per launch).  A real function call
+// with the branch's pointers passed BY VALUE: inlined into the kernels it costs them hundreds of bytes of spills, and
+// through a reference to the __grid_constant__ argument struct every field access is a generic load of parameter space.
+// Every load is issued before the first store (interleaved read-modify-writes form a chain of dependent round trips).
+struct BookArgs {
+  const float* sum; const float* sq; const float* conv_bias;
+  float* running_mean; float* running_var; float* save_mean; float* save_invstd;
+  long long M, stat_stride;
+  int C, stat_replicas, training;
+  float momentum, eps;
+};
+__device__ __noinline__ void bookkeeping_call(const BookArgs B, const int c0) {
+  float mean[8], invstd[8], var[8], rm[8], rv[8], bias[8];
+  const bool run = B.training && B.running_mean;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int c = c0 + i;
-    const bool ok = run && c < A.C;
-    rm[i] = ok ? br.running_mean[c] : 0.f;
-    rv[i] = ok ? br.running_var[c] : 0.f;
-    bias[i] = (ok && br.conv_bias) ? br.conv_bias[c] : 0.f;
+    const bool ok = c0 + i < B.C && (run || !B.training);
+    rm[i] = ok ? B.running_mean[c0 + i] : 0.f;
+    rv[i] = ok ? B.running_var[c0 + i] : 1.f;
+    bias[i] = (ok && B.conv_bias) ? B.conv_bias[c0 + i] : 0.f;
+  }
+  if (B.training) {
+    float s1[8], s2[8];
+    rsum8(B.sum, c0, B.stat_replicas, B.stat_stride, s1);
+    rsum8(B.sq, c0, B.stat_replicas, B.stat_stride, s2);
+    const float inv_m = 1.0f / (float)B.M;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mean[i] = s1[i] * inv_m;
+      var[i] = fmaxf(s2[i] * inv_m - mean[i] * mean[i], 0.f);
+      invstd[i] = rsqrtf(var[i] + B.eps);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mean[i] = rm[i] - bias[i];
+      invstd[i] = rsqrtf(rv[i] + B.eps);
+      var[i] = 0.f;
+    }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = c0 + i;
-    if (c >= A.C) continue;
-    if (br.save_mean) {
-      br.save_mean[c] = mean[i];
-      br.save_invstd[c] = invstd[i];
+    if (c >= B.C) continue;
+    if (B.save_mean) {
+      B.save_mean[c] = mean[i];
+      B.save_invstd[c] = invstd[i];
     }
     if (run) {
-      const float unbiased = A.M > 1 ? var[i] * ((float)A.M / (float)(A.M - 1)) : var[i];
-      br.running_mean[c] = (1.f - A.momentum) * rm[i] + A.momentum * (mean[i] + bias[i]);
-      br.running_var[c] = (1.f - A.momentum) * rv[i] + A.momentum * unbiased;
+      const float unbiased = B.M > 1 ? var[i] * ((float)B.M / (float)(B.M - 1)) : var[i];
+      B.running_mean[c] = (1.f - B.momentum) * rm[i] + B.momentum * (mean[i] + bias[i]);
+      B.running_var[c] = (1.f - B.momentum) * rv[i] + B.momentum * unbiased;
     }
   }
 }
+// (A and br are accessed statically by the caller: constant-bank reads)
+#define MP_BN_BOOKKEEPING(A, br, c0)                                                                              \
+  do {                                                                                                            \
+    if (!((br).scale && (A).training)) {   /* otherwise the producing conv already did it */                      \
+      BookArgs B__;                                                                                               \
+      B__.sum = (br).sum; B__.sq = (br).sq; B__.conv_bias = (br).conv_bias;                                       \
+      B__.running_mean = (br).running_mean; B__.running_var = (br).running_var;                                   \
+      B__.save_mean = (br).save_mean; B__.save_invstd = (br).save_invstd;                                         \
+      B__.M = (A).M; B__.stat_stride = (A).stat_stride; B__.C = (A).C; B__.stat_replicas = (A).stat_replicas;     \
+      B__.training = (A).training; B__.momentum = (A).momentum; B__.eps = (A).eps;                                \
+      bookkeeping_call(B__, c0);                                                                                  \
+    }                                                                                                             \
+  } while (0)
 
 // ------------------------------------------------------------------------------------- forward
 template <bool SPLIT, int MINB>
@@ -215,8 +270,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bn_fwd_kernel(const __grid_constan
   if (has_b) affine(A, A.b, c0, false, sb, hb);
 
   if (blockIdx.x == 0 && threadIdx.y == 0) {   // bookkeeping: saved statistics + running buffers
-    bookkeeping(A, A.a, c0);
-    if (has_b) bookkeeping(A, A.b, c0);
+    MP_BN_BOOKKEEPING(A, A.a, c0);
+    if (has_b) MP_BN_BOOKKEEPING(A, A.b, c0);
   }
 
   const long long ppb = (long long)blockDim.y * U;
@@ -677,8 +732,8 @@ __global__ void __launch_bounds__(MAXT, 2) bn_fwd_tma_kernel(const __grid_consta
   affine(A, A.a, c0, false, sa, ha);
   if (has_b) affine(A, A.b, c0, false, sb, hb);
   if (blockIdx.x == 0 && threadIdx.y == 0) {   // bookkeeping: saved statistics + running buffers
-    bookkeeping(A, A.a, c0);
-    if (has_b) bookkeeping(A, A.b, c0);
+    MP_BN_BOOKKEEPING(A, A.a, c0);
+    if (has_b) MP_BN_BOOKKEEPING(A, A.b, c0);
   }
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(A.out);
   for (long long t = R.t_lo; t < R.t_hi; ++t) {
