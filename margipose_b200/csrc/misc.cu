@@ -440,71 +440,69 @@ __global__ void __launch_bounds__(256) combiner_bwd_kernel(const __nv_bfloat16* 
 }
 
 // -------------------------------------------------------------------------------- stem im2col
-// patches[n, ho, wo, (r*7+s)*3 + c] = x[n, c, 2*ho + r - 3, 2*wo + s - 3]; 192 columns per row.
-__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
-                                   int W, long long lo_delta) {
+// patches[n, ho, wo, (r*7+s)*3 + c] = x[n, c, 2*ho + r - 3, 2*wo + s - 3]; 192 columns per row (147 real).  From the fp32
+// NCHW image, or from a uint8 NHWC image (what an image decoder produces) with the input step of the reference fused in:
+// to_tensor (/255) and ImageNet normalisation (x - mean) / std (data_specs.py:6-13,38-39); padding taps are zeros of the
+// NORMALISED tensor, as the conv's zero padding sees them.
+// A block owns STEM_TW consecutive output pixels of one output row, stages the 7 x (2 * STEM_TW + 5) x 3 input window it needs
+// in shared memory with coalesced reads (normalised, zero outside the image), and writes the pixels' 192-column patch rows
+// -- one contiguous run of STEM_TW * 384 bytes -- with fully coalesced 16-byte stores.  (A thread per (pixel, 8 columns) that
+// gathers straight from global memory stores 16 bytes per 384-byte row and lane: 187 us instead of 124 us per step.)
+constexpr int STEM_TW = 32, STEM_WW = 2 * STEM_TW + 5;
+template <bool U8>
+__global__ void __launch_bounds__(192) stem_im2col_tiled_kernel(const void* __restrict__ xin, __nv_bfloat16* __restrict__ out,
+                                                                int N, int H, int W, float3 scale, float3 shift,
+                                                                long long lo_delta) {
   pdl_trigger();
   pdl_wait();
+  __shared__ float win[3][7][STEM_WW + 3];
   const int Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)N * Ho * Wo * 24;   // 24 groups of 8 columns
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  // consecutive threads = consecutive output columns of one 8-column group: the image reads of a warp are
-  // one stride-2 run per (tap, channel) instead of 24 scattered runs per pixel
-  const int wo = (int)(i % Wo);
-  long long t = i / Wo;
-  const int g = (int)(t % 24); t /= 24;
-  const int ho = (int)(t % Ho);
-  const int n = (int)(t / Ho);
-  float v[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = g * 8 + j;
-    float val = 0.f;
-    if (k < 147) {
-      const int tap = k / 3, c = k - tap * 3;
-      const int r = tap / 7, s = tap - r * 7;
-      const int h = 2 * ho + r - 3, w = 2 * wo + s - 3;
-      if (h >= 0 && h < H && w >= 0 && w < W) val = __ldg(x + (((long long)n * 3 + c) * H + h) * W + w);
+  const int tiles_w = (Wo + STEM_TW - 1) / STEM_TW;
+  const int tw = blockIdx.x % tiles_w;
+  const int ho = (blockIdx.x / tiles_w) % Ho;
+  const int n = blockIdx.x / (tiles_w * Ho);
+  const int wo0 = tw * STEM_TW, w_first = 2 * wo0 - 3, h_first = 2 * ho - 3;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < 3 * 7 * STEM_WW; i += blockDim.x) {
+    int c, r, col;
+    if (U8) {   // NHWC bytes: channel fastest
+      c = i % 3; col = (i / 3) % STEM_WW; r = i / (3 * STEM_WW);
+    } else {    // NCHW floats: column fastest
+      col = i % STEM_WW; r = (i / STEM_WW) % 7; c = i / (7 * STEM_WW);
     }
-    v[j] = val;
-  }
-  mp_st8(out + (((long long)n * Ho + ho) * Wo + wo) * 192 + g * 8, lo_delta, v);
-}
-
-// Same gather from a uint8 NHWC image (what an image decoder produces) with the input step of the reference fused
-// in: to_tensor (/255) and ImageNet normalisation (x - mean) / std (data_specs.py:6-13,38-39).  Padding taps are
-// zeros of the NORMALISED tensor, as the conv's zero padding sees them.
-__global__ void stem_im2col_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
-                                      int W, float3 scale, float3 shift, long long lo_delta) {
-  pdl_trigger();
-  pdl_wait();
-  const int Ho = H / 2, Wo = W / 2;
-  const long long total = (long long)N * Ho * Wo * 24;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int wo = (int)(i % Wo);
-  long long t = i / Wo;
-  const int g = (int)(t % 24); t /= 24;
-  const int ho = (int)(t % Ho);
-  const int n = (int)(t / Ho);
-  float v[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = g * 8 + j;
+    const int h = h_first + r, w = w_first + col;
     float val = 0.f;
-    if (k < 147) {
-      const int tap = k / 3, c = k - tap * 3;
-      const int r = tap / 7, s = tap - r * 7;
-      const int h = 2 * ho + r - 3, w = 2 * wo + s - 3;
-      if (h >= 0 && h < H && w >= 0 && w < W) {
-        const float px = (float)__ldg(x + (((long long)n * H + h) * W + w) * 3 + c);
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      if (U8) {
+        const float px = (float)__ldg(reinterpret_cast<const uint8_t*>(xin) + (((long long)n * H + h) * W + w) * 3 + c);
         val = fmaf(px, c == 0 ? scale.x : (c == 1 ? scale.y : scale.z), c == 0 ? shift.x : (c == 1 ? shift.y : shift.z));
+      } else {
+        val = __ldg(reinterpret_cast<const float*>(xin) + (((long long)n * 3 + c) * H + h) * W + w);
       }
     }
-    v[j] = val;
+    win[c][r][col] = val;
   }
-  mp_st8(out + (((long long)n * Ho + ho) * Wo + wo) * 192 + g * 8, lo_delta, v);
+  __syncthreads();
+  // 192 threads = 8 pixels x 24 column groups per pass: a thread keeps ITS column group, so the window offsets of its
+  // eight columns are computed once; consecutive threads store consecutive 16-byte pieces of the row
+  __nv_bfloat16* row = out + (((long long)n * Ho + ho) * Wo + wo0) * 192;
+  const int g = threadIdx.x % 24, p0 = threadIdx.x / 24;
+  const float* wf = &win[0][0][0];
+  int offs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = g * 8 + j;
+    const int tap = k / 3, c = k - tap * 3;
+    const int r = tap / 7, sx = tap - r * 7;
+    offs[j] = k < 147 ? (c * 7 + r) * (STEM_WW + 3) + sx : -1;
+  }
+  for (int px = p0; px < STEM_TW; px += 8) {
+    if (wo0 + px >= Wo) break;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = offs[j] >= 0 ? wf[offs[j] + 2 * px] : 0.f;
+    mp_st8(row + (long long)(px * 24 + g) * 8, lo_delta, v);
+  }
 }
 
 // -------------------------------------------------------------------------------------- add_n
@@ -715,9 +713,11 @@ int mp_combiner_bwd(const void* dout, const float* const p[3], const float* w, f
 int mp_stem_im2col(const float* x, void* patches, int N, int H, int W, int64_t lo_delta, void* stream) {
   MP_CHECK_DELTA("mp_stem_im2col");
   MP_CHECK_ARG(x && patches && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "mp_stem_im2col: bad arguments");
-  const long long total = (long long)N * (H / 2) * (W / 2) * 24;
-  MP_CUDA(mp_launch(stem_im2col_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
-      x, (__nv_bfloat16*)patches, N, H, W, (long long)lo_delta));
+  const long long blocks = (long long)N * (H / 2) * ((W / 2 + STEM_TW - 1) / STEM_TW);
+  MP_CHECK_ARG(blocks <= 0x7fffffffLL, "mp_stem_im2col: too many tiles");
+  MP_CUDA(mp_launch(stem_im2col_tiled_kernel<false>, dim3((unsigned)blocks), dim3(192), 0, (cudaStream_t)stream,
+      (const void*)x, (__nv_bfloat16*)patches, N, H, W, make_float3(1.f, 1.f, 1.f), make_float3(0.f, 0.f, 0.f),
+      (long long)lo_delta));
   MP_CHECK_LAUNCH("mp_stem_im2col");
   return MP_OK;
 }
@@ -728,12 +728,13 @@ int mp_stem_im2col_u8(const uint8_t* x, void* patches, const float mean[3], cons
   MP_CHECK_ARG(x && patches && mean && stddev && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0,
                "mp_stem_im2col_u8: bad arguments");
   MP_CHECK_ARG(stddev[0] > 0.f && stddev[1] > 0.f && stddev[2] > 0.f, "mp_stem_im2col_u8: stddev must be positive");
-  const long long total = (long long)N * (H / 2) * (W / 2) * 24;
   // (p / 255 - mean) / std = p * scale + shift
   const float3 scale = make_float3(1.f / (255.f * stddev[0]), 1.f / (255.f * stddev[1]), 1.f / (255.f * stddev[2]));
   const float3 shift = make_float3(-mean[0] / stddev[0], -mean[1] / stddev[1], -mean[2] / stddev[2]);
-  MP_CUDA(mp_launch(stem_im2col_u8_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
-      x, (__nv_bfloat16*)patches, N, H, W, scale, shift, (long long)lo_delta));
+  const long long blocks = (long long)N * (H / 2) * ((W / 2 + STEM_TW - 1) / STEM_TW);
+  MP_CHECK_ARG(blocks <= 0x7fffffffLL, "mp_stem_im2col_u8: too many tiles");
+  MP_CUDA(mp_launch(stem_im2col_tiled_kernel<true>, dim3((unsigned)blocks), dim3(192), 0, (cudaStream_t)stream,
+      (const void*)x, (__nv_bfloat16*)patches, N, H, W, scale, shift, (long long)lo_delta));
   MP_CHECK_LAUNCH("mp_stem_im2col_u8");
   return MP_OK;
 }
