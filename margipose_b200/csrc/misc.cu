@@ -52,26 +52,54 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
   const long long total = (long long)N * Ho * Wo * G;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int g = (int)(i % G);
-  long long t = i / G;
-  const int wo = (int)(t % Wo); t /= Wo;
-  const int ho = (int)(t % Ho);
-  const int n = (int)(t / Ho);
+  // (32-bit index arithmetic: the launcher checks total < 2^31; 64-bit divisions by run-time values cost ~100 instructions each)
+  const unsigned iu = (unsigned)i;
+  const int g = (int)(iu % (unsigned)G);
+  unsigned t = iu / (unsigned)G;
+  const int wo = (int)(t % (unsigned)Wo); t /= (unsigned)Wo;
+  const int ho = (int)(t % (unsigned)Ho);
+  const int n = (int)(t / (unsigned)Ho);
   float best[8];
   int arg[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
-  for (int r = 0; r < 3; ++r) {
-    const int h = 2 * ho + r - 1;
-    if (h < 0 || h >= H) continue;
-    for (int s = 0; s < 3; ++s) {
-      const int w = 2 * wo + s - 1;
-      if (w < 0 || w >= W) continue;
+  if (lo_delta == 0) {
+    // all nine window loads are issued before the first comparison (a guarded load followed by its use, nine times over,
+    // is a chain of nine dependent memory round trips)
+    uint4 raw[9];
+    bool ok[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int h = 2 * ho + r - 1, w = 2 * wo + s - 1;
+        ok[r * 3 + s] = h >= 0 && h < H && w >= 0 && w < W;
+        raw[r * 3 + s] = ok[r * 3 + s] ? __ldg(reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + g * 8))
+                                       : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+#pragma unroll
+    for (int t9 = 0; t9 < 9; ++t9) {
+      if (!ok[t9]) continue;
       float v[8];
-      mp_ld8(x + (((long long)n * H + h) * W + w) * C + g * 8, lo_delta, v);
+      unpack8(raw[t9], v);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (v[j] > best[j] || v[j] != v[j]) { best[j] = v[j]; arg[j] = r * 3 + s; }
+        if (v[j] > best[j] || v[j] != v[j]) { best[j] = v[j]; arg[j] = t9; }
+    }
+  } else {
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * ho + r - 1;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int w = 2 * wo + s - 1;
+        if (w < 0 || w >= W) continue;
+        float v[8];
+        mp_ld8(x + (((long long)n * H + h) * W + w) * C + g * 8, lo_delta, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v[j] > best[j] || v[j] != v[j]) { best[j] = v[j]; arg[j] = r * 3 + s; }
+      }
     }
   }
   const long long o = (((long long)n * Ho + ho) * Wo + wo) * C + g * 8;
@@ -90,31 +118,40 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const u
   const long long total = (long long)N * H * W * G;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int g = (int)(i % G);
-  long long t = i / G;
-  const int w = (int)(t % W); t /= W;
-  const int h = (int)(t % H);
-  const int n = (int)(t / H);
+  const unsigned iu = (unsigned)i;   // (32-bit index arithmetic, see maxpool_fwd_kernel)
+  const int g = (int)(iu % (unsigned)G);
+  unsigned t = iu / (unsigned)G;
+  const int w = (int)(t % (unsigned)W); t /= (unsigned)W;
+  const int h = (int)(t % (unsigned)H);
+  const int n = (int)(t / (unsigned)H);
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  // output windows (ho, wo) that contain (h, w): 2*ho + r - 1 == h
-  for (int r = 0; r < 3; ++r) {
-    const int hh = h + 1 - r;
-    if (hh < 0 || (hh & 1) || hh / 2 >= Ho) continue;
-    for (int s = 0; s < 3; ++s) {
-      const int ww = w + 1 - s;
-      if (ww < 0 || (ww & 1) || ww / 2 >= Wo) continue;
-      const long long o = (((long long)n * Ho + hh / 2) * Wo + ww / 2) * C + g * 8;
-      const uint2 a = __ldg(reinterpret_cast<const uint2*>(idx + o));
-      float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + o)), v);
-      const int tap = r * 3 + s;
+  // output windows (ho, wo) that contain (h, w): 2*ho + r - 1 == h, i.e. r = 1 for even h, r in {0, 2} for odd h (same for
+  // columns): at most four candidates, all loaded before the first one is used
+  const int rr[2] = {(h & 1) ? 0 : 1, (h & 1) ? 2 : -1};
+  const int ss[2] = {(w & 1) ? 0 : 1, (w & 1) ? 2 : -1};
+  uint2 ia[4];
+  uint4 va[4];
+  int tapv[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int aj = ((j < 4 ? a.x : a.y) >> ((j & 3) * 8)) & 0xff;
-        if (aj == tap) acc[j] += v[j];
-      }
+  for (int q = 0; q < 4; ++q) {
+    const int r = rr[q >> 1], sx = ss[q & 1];
+    const int hh = h + 1 - r, ww = w + 1 - sx;
+    const bool in = r >= 0 && sx >= 0 && hh >= 0 && ww >= 0 && (hh >> 1) < Ho && (ww >> 1) < Wo;
+    tapv[q] = in ? r * 3 + sx : -1;
+    const long long o = in ? (((long long)n * Ho + (hh >> 1)) * Wo + (ww >> 1)) * C + g * 8 : 0;
+    ia[q] = in ? __ldg(reinterpret_cast<const uint2*>(idx + o)) : make_uint2(0xffffffffu, 0xffffffffu);
+    va[q] = in ? __ldg(reinterpret_cast<const uint4*>(dy + o)) : make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float v[8];
+    unpack8(va[q], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int aj = (int)(((j < 4 ? ia[q].x : ia[q].y) >> ((j & 3) * 8)) & 0xff);
+      if (aj == tapv[q]) acc[j] += v[j];
     }
   }
   *reinterpret_cast<uint4*>(dx + (((long long)n * H + h) * W + w) * C + g * 8) = pack8(acc);
@@ -130,11 +167,12 @@ __global__ void axis_permute_kernel(const __nv_bfloat16* __restrict__ in, __nv_b
   const long long total = (long long)N * S * S * Cp;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int ch = (int)(i % Cp);
-  long long t = i / Cp;
-  const int col = (int)(t % S); t /= S;
-  const int row = (int)(t % S);
-  const int n = (int)(t / S);
+  const unsigned iu = (unsigned)i;   // (32-bit index arithmetic, see maxpool_fwd_kernel)
+  const int ch = (int)(iu % (unsigned)Cp);
+  unsigned t = iu / (unsigned)Cp;
+  const int col = (int)(t % (unsigned)S); t /= (unsigned)S;
+  const int row = (int)(t % (unsigned)S);
+  const int n = (int)(t / (unsigned)S);
   __nv_bfloat16 v = __float2bfloat16(0.f);
   if (ch < C) {
     const int g = ch / S, k = ch - g * S;
@@ -622,6 +660,7 @@ int mp_maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, in
   MP_CHECK_ARG(x && y && idx && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0,
                "mp_maxpool_fwd: bad arguments");
   const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  MP_CHECK_ARG(total < (1LL << 31), "mp_maxpool_fwd: tensor too large (32-bit element index)");
   MP_CUDA(mp_launch(maxpool_fwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)x, (__nv_bfloat16*)y, idx, N, H, W, C, (long long)lo_delta));
   MP_CHECK_LAUNCH("mp_maxpool_fwd");
@@ -631,6 +670,7 @@ int mp_maxpool_fwd(const void* x, void* y, uint8_t* idx, int N, int H, int W, in
 int mp_maxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int N, int H, int W, int C, void* stream) {
   MP_CHECK_ARG(dy && dx && idx && N > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "mp_maxpool_bwd: bad arguments");
   const long long total = (long long)N * H * W * (C / 8);
+  MP_CHECK_ARG(total < (1LL << 31), "mp_maxpool_bwd: tensor too large (32-bit element index)");
   MP_CUDA(mp_launch(maxpool_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)dy, idx, (__nv_bfloat16*)dx, N, H, W, C));
   MP_CHECK_LAUNCH("mp_maxpool_bwd");
@@ -641,6 +681,7 @@ int mp_axis_permute(const void* in, void* out, int mode, int N, int S, int C, in
   MP_CHECK_ARG(in && out && in != out && (mode == 1 || mode == 2) && N > 0 && S > 0 && C % S == 0 && Cp >= C,
                "mp_axis_permute: bad arguments (the spatial size must divide the channel count)");
   const long long total = (long long)N * S * S * Cp;
+  MP_CHECK_ARG(total < (1LL << 31), "mp_axis_permute: tensor too large (32-bit element index)");
   MP_CUDA(mp_launch(axis_permute_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const __nv_bfloat16*)in, (__nv_bfloat16*)out, mode, N, S, C, Cp));
   MP_CHECK_LAUNCH("mp_axis_permute");
