@@ -1264,8 +1264,10 @@ __global__ void __launch_bounds__(512, 2) tail_bwd_fast_kernel(const BwdArgs A, 
 // every reduction is a shuffle tree, and the separable Gaussian's column / row factors are evaluated directly by the
 // lanes that need them (4 columns + NV rows per lane) instead of going through a table.  The per-plane fixed cost
 // drops from ~800 instructions per warp (fast kernels above) to ~200.
-// WPP > 1 (softmax + expectations only, no JS term): WPP warps = one block share a plane of up to 16384 elements (128 x 128),
-// 32 float4 per lane each; their partial maxima / sums meet in 16 floats of shared memory (two block barriers per plane).
+// WPP > 1 (planes above one warp's registers, up to 128 x 128): WPP warps = one block share a (sample, joint), each holds
+// NV float4 per lane of the plane (forward: 32 without a JS term, 16 with it; backward: 8, it holds p and the gradient); their
+// partial maxima / sums meet in shared memory (one block barrier per reduction, below).
+//
 // Block-wide sums / maximum of the WPP warps that share a plane: shuffle tree, lane 0 of every warp posts its N partial
 // values as one float4, ONE block barrier, every warp folds the WPP posts with log2(WPP) more shuffles.  Consecutive
 // reductions alternate between two shared-memory buffers (`phase`), so a buffer is rewritten only after a later barrier
