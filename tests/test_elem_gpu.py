@@ -181,18 +181,36 @@ def test_combiner_forward_backward():
     torch.testing.assert_close(dw.cpu(), wt.grad.reshape(C, 3 * J), rtol=1e-3, atol=1e-5)
 
 
-def test_stem_im2col_conv_equals_7x7_stride2():
+@pytest.mark.parametrize('h,w', [(64, 64), (48, 80), (24, 16)])
+def test_stem_im2col_conv_equals_7x7_stride2(h, w):
+    """The stem gather (a block per 32 output pixels of a row; ragged last tile, images narrower than a tile) followed by
+    the 1x1 GEMM is the 7x7 stride-2 convolution (margipose_model.py:130); the uint8 NHWC variant with /255 and the
+    ImageNet normalisation fused gives the same patches as the fp32 path fed the normalised image."""
     from margipose_b200 import ops, convops as C
+    from margipose_b200._lib import lib, check, stream_ptr
+    import ctypes
     gen = torch.Generator().manual_seed(5)
-    x = torch.randn(2, 3, 64, 64, generator=gen)
+    x = torch.randn(2, 3, h, w, generator=gen)
     wt = _bf(torch.randn(64, 3, 7, 7, generator=gen) / 147 ** 0.5)
     want = F.conv2d(_bf(x), wt, None, 2, 3)
     patches = ops.stem_im2col(x.cuda())
+    assert patches[..., 147:].abs().max().item() == 0
     g = C.ConvGeom(147, 64, 1)
     master = wt.permute(0, 2, 3, 1).reshape(64, 1, 147).contiguous().cuda()
-    out = torch.zeros(2, 32, 32, 64, dtype=torch.bfloat16, device='cuda')
+    out = torch.zeros(2, h // 2, w // 2, 64, dtype=torch.bfloat16, device='cuda')
     C.conv_forward(g, patches, C.pack_fwd(g, master), out)
     torch.testing.assert_close(_nchw(out, 64), want, rtol=1e-2, atol=2e-2)
+    # uint8 NHWC input
+    img = torch.randint(0, 256, (2, h, w, 3), generator=gen, dtype=torch.uint8)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    xn = ((img.float() / 255 - torch.tensor(mean)) / torch.tensor(std)).permute(0, 3, 1, 2).contiguous()
+    p8 = torch.empty_like(patches)
+    dev = torch.device('cuda')
+    imgc = img.cuda()
+    check(lib().mp_stem_im2col_u8(imgc.data_ptr(), p8.data_ptr(), (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std),
+                                  2, h, w, 0, stream_ptr(dev)), 'mp_stem_im2col_u8')
+    torch.cuda.synchronize()
+    torch.testing.assert_close(p8.float(), ops.stem_im2col(xn.cuda()).float(), rtol=1e-2, atol=1e-2)
 
 
 def test_add_and_sgd():
