@@ -92,7 +92,7 @@ def test_fused_tail_vs_golden(case, from_logits):
             torch.testing.assert_close(g3[k].cpu(), case['grad3'][k], **GTOL)
 
 
-@pytest.mark.parametrize('shape', [(4, 17, 32, 32), (2, 17, 48, 48), (2, 3, 128, 128), (2, 3, 64, 128),
+@pytest.mark.parametrize('shape', [(4, 17, 32, 32), (2, 17, 48, 48), (2, 3, 128, 128), (2, 3, 64, 128), (2, 5, 64, 64), (1, 2, 32, 64),
                                    (2, 4, 20, 30), (3, 2, 7, 9)])
 def test_fused_tail_mixed_2d_3d_and_upstream_grads_vs_oracle(shape):
     """Mixed valid_depth batches (bin/train_3d.py:126-142), upstream heatmap gradients (what the
