@@ -1105,7 +1105,7 @@ int mp_bn_bwd_reduce_grouped(const mp_bn_args* args, int n, void* stream) {
   int rc = make_group(args, n, "mp_bn_bwd_reduce", true, &g);
   if (rc != MP_OK) return rc;
   dim3 grid, block;
-  int cap = n > 1 ? 2 * 148 / n : 148;
+  int cap = 2 * 148 / n;   // two resident blocks per SM (one block per SM reads at ~3 TB/s, tools/bn_scale.py)
   // deterministic mode: one block per replica of the sums, so no two blocks ever add into the same address
   if (mp_deterministic() && cap > args->stat_replicas) cap = args->stat_replicas;
   launch_dims(args, &grid, &block, U, cap);
