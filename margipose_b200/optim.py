@@ -38,6 +38,12 @@ class FlatSGD(torch.optim.Optimizer):
         # scheduler wrote -- including the "first step initialises the momentum buffer" flag.
         self._hyper_host = torch.zeros(8).pin_memory()
         self._hyper = torch.zeros(8, device=device)
+        # The mirror is read by the GPU when the queued copy executes, not when it is queued: with steps in flight
+        # (TrainStep.submit) a scheduler's next value must not reach the mirror before the previous step's copy has
+        # run.  _hyper_copied marks the end of the last queued step; refresh_hyper() waits for it before it writes
+        # CHANGED values (unchanged hyperparameters never wait).
+        self._hyper_last = None
+        self._hyper_copied = torch.cuda.Event()
 
     def add_param_group(self, param_group):
         if getattr(self, 'param_groups', None):
@@ -49,9 +55,23 @@ class FlatSGD(torch.optim.Optimizer):
         """Host side only: publish the current param_groups hyperparameters to the pinned mirror (call before
         replaying a CUDA graph that contains step(); step() itself does it when run eagerly)."""
         g = self.param_groups[0]
+        new = (float(g['lr']), float(g['momentum']), float(g['dampening']), float(g['weight_decay']),
+               float(self.grad_scale), 1.0 if self._steps == 0 else 0.0)
+        if new == self._hyper_last:
+            return
+        if not torch.cuda.is_current_stream_capturing():
+            # no-op unless a step that reads the old values is still queued.  (While a step is being captured nothing
+            # may synchronise -- and nothing is queued: TrainStep._capture synchronises the device first.)
+            self._hyper_copied.synchronize()
         h = self._hyper_host
-        h[0], h[1], h[2], h[3], h[4] = g['lr'], g['momentum'], g['dampening'], g['weight_decay'], self.grad_scale
-        h[5] = 1.0 if self._steps == 0 else 0.0
+        for i, v in enumerate(new):
+            h[i] = v
+        self._hyper_last = new
+
+    def _mark_hyper_copied(self):
+        """Behind a queued step (eager or replayed): everything that reads the pinned mirror is in front of this."""
+        if not torch.cuda.is_current_stream_capturing():
+            self._hyper_copied.record(torch.cuda.current_stream(self._hyper.device))
 
     def zero_grad(self, set_to_none=False):
         self.bank.flat_grad.zero_()
@@ -76,6 +96,7 @@ class FlatSGD(torch.optim.Optimizer):
         """Host bookkeeping for a step replayed from a CUDA graph (step() itself did not run)."""
         self._steps += 1
         self.model.mark_params_dirty()
+        self._mark_hyper_copied()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -94,4 +115,5 @@ class FlatSGD(torch.optim.Optimizer):
                      grad_scale=self.grad_scale, hyper=self._hyper)
         self._steps += 1
         self.model.mark_params_dirty()
+        self._mark_hyper_copied()
         return loss

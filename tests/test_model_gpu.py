@@ -306,6 +306,45 @@ def test_train_step_cuda_graph_follows_lr_schedule():
     assert not torch.equal(before, flat)
 
 
+def test_schedule_values_do_not_overtake_queued_steps():
+    """`TrainStep.submit` queues steps without waiting for them; the optimiser's hyperparameters travel through a
+    pinned host mirror that the GPU reads when the queued copy executes.  A scheduler that writes the NEXT step's
+    learning rate right after `submit` must not change the rate of the step that is still in flight: step A runs
+    with lr = 0 (parameters frozen) although lr is raised, and step B queued, before A has executed."""
+    from margipose_b200.models import create_model
+    from margipose_b200.optim import FlatSGD
+    from margipose_b200.train import TrainStep
+    desc = {'type': 'margipose', 'version': '6.0.1',
+            'settings': dict(n_stages=1, feature_extractor='resnet18')}
+    torch.manual_seed(7)
+    model = create_model(desc).cuda().train()
+    opt = FlatSGD(model, lr=1e-2, momentum=0.0)
+    step = TrainStep(model, opt, batch=2, warmup=1)
+    x, target, mask = model_inputs(8, 2)
+    x, target, mask = x.pin_memory(), target.pin_memory(), mask.pin_memory()
+    for _ in range(3):
+        step(x, target, mask)
+    assert step._graphs is not None
+    flat = model._bank.flat
+    for mode in ('graph', 'eager'):
+        if mode == 'eager':
+            step._graphs, step.use_graph = None, False
+        opt.param_groups[0]['lr'] = 0.0
+        torch.cuda.synchronize()
+        before = flat.clone()
+        # keep the GPU busy so that the host is certainly ahead of it when the rate is raised
+        busy = torch.randn(4096, 4096, device='cuda')
+        for _ in range(20):
+            busy = busy @ busy * 1e-3
+        step.submit(x, target, mask)                 # step A, lr = 0
+        mid = flat.clone()                           # stream-ordered: after A, before B
+        opt.param_groups[0]['lr'] = 1e-2
+        step.submit(x, target, mask).item()          # step B, lr = 1e-2
+        torch.cuda.synchronize()
+        assert torch.equal(before, mid), '%s: the in-flight step picked up the next step\'s learning rate' % mode
+        assert not torch.equal(mid, flat), '%s: the raised learning rate did not reach the next step' % mode
+
+
 def test_full_size_properties_of_the_bench_workload():
     """BASELINE.json configs[1] at full size (4-stage ResNet-34, 256x256, 17 joints, batch 32): the grouped /
     two-accumulator / CTA-pair conv paths that small batches never select, checked through size-independent
