@@ -41,6 +41,36 @@ def forward_loss(model, out_var, target_var, mask_var, valid_depth):
     return K.average_loss(losses, mask_var)
 
 
+def learning_schedule(model, optim_algorithm, lr, max_iters=None, lr_milestones=(), lr_gamma=0.1, sgd=None):
+    """The optimiser / schedule selection of bin/train_3d.py:338-347 (+ train_helpers.py:57-77) on the flat optimiser:
+    returns an object with `.optimizer` and, depending on the algorithm, `.batch_step()` (call per batch) or
+    `.step()` (call per epoch), which is how `do_training_pass` (:145-156) drives it.
+
+      '1cycle'     SGD(lr=0) under the 1-cycle learning-rate / momentum schedule over `max_iters` batches (momentum 0.9)
+      'sgd_simple' plain SGD, no schedule
+      'sgd'        SGD, learning rate multiplied by `lr_gamma` at the epochs in `lr_milestones`
+      'nesterov'   the same with Nesterov momentum 0.8
+    RMSprop (the reference's third milestone algorithm) has no flat kernel here and is rejected.
+    `sgd`: optimiser factory `sgd(model, lr=..., momentum=..., nesterov=...)`, default `FlatSGD`."""
+    from collections import namedtuple
+    from .hyperparam_scheduler import make_1cycle
+    if sgd is None:
+        from .optim import FlatSGD as sgd
+    if optim_algorithm == '1cycle':
+        if not max_iters:
+            raise ValueError("'1cycle' needs max_iters = epochs * batches per epoch")
+        return make_1cycle(sgd(model, lr=0), max_iters, lr_max=lr, momentum=0.9)
+    if optim_algorithm == 'sgd_simple':
+        return namedtuple('DummyScheduler', 'optimizer')(optimizer=sgd(model, lr=lr, momentum=0))
+    if optim_algorithm == 'sgd':
+        optimiser = sgd(model, lr=lr)
+    elif optim_algorithm == 'nesterov':
+        optimiser = sgd(model, lr=lr, momentum=0.8, nesterov=True)
+    else:
+        raise Exception('unrecognised optimisation algorithm: ' + optim_algorithm)
+    return torch.optim.lr_scheduler.MultiStepLR(optimiser, milestones=list(lr_milestones), gamma=lr_gamma)
+
+
 class PendingLoss:
     """Loss of a step queued with `TrainStep.submit`: a pinned host scalar the GPU writes when the step is done."""
 
