@@ -159,3 +159,33 @@ def test_engine_zips_the_three_column_programs_into_grouped_launches():
     assert first.flops == 3.0 and not getattr(first, 'aux', False)
     # the grouped argument array is contiguous memory of the C struct (what mp_*_grouped expects)
     assert ctypes.sizeof(first.args) == 3 * ctypes.sizeof(IgemmArgs)
+
+
+def test_reference_checkpoint_loads_on_cpu_without_unpickling_code(tmp_path):
+    """A checkpoint in the reference's wire format (bin/train_3d.py:374-382), written from the oracle -- whose module
+    tree has the reference's key names -- with a torch.optim.SGD state as the reference saves it, loads through
+    `load_model` (models/__init__.py:30-34) under `weights_only=True`: every tensor arrives under the same key.
+    A file that needs arbitrary unpickling is refused unless the caller opts in."""
+    import pickle
+    from margipose_b200.models import load_model
+    d = desc(n_stages=2)
+    torch.manual_seed(3)
+    om = M.create_oracle(d)
+    opt = torch.optim.SGD(om.parameters(), lr=0.1, momentum=0.9)
+    path = str(tmp_path / 'model-latest.pth')
+    torch.save({'state_dict': om.state_dict(), 'model_desc': d, 'train_datasets': ['mpi3d-train', 'mpii-train'],
+                'optimizer': opt.state_dict(), 'epoch': 7}, path)
+    model = load_model(path)
+    want, got = om.state_dict(), model.state_dict()
+    assert list(want.keys()) == list(got.keys())
+    for k in want:
+        assert torch.equal(want[k], got[k]), k
+    assert model.inner.n_stages == 2 and not any(p.is_cuda for p in model.parameters())
+
+    class Evil:
+        def __reduce__(self):
+            return (print, ('code ran during unpickling',))
+    bad = str(tmp_path / 'bad.pth')
+    torch.save({'state_dict': om.state_dict(), 'model_desc': d, 'extra': Evil()}, bad)
+    with pytest.raises(pickle.UnpicklingError):
+        load_model(bad)
