@@ -189,3 +189,34 @@ def test_reference_checkpoint_loads_on_cpu_without_unpickling_code(tmp_path):
     torch.save({'state_dict': om.state_dict(), 'model_desc': d, 'extra': Evil()}, bad)
     with pytest.raises(pickle.UnpicklingError):
         load_model(bad)
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/src/margipose/data_specs.py'), reason='reference tree not present')
+def test_image_specs_convert_is_the_references_bit_for_bit():
+    """bin/infer_single.py:62-66 goes through `model.data_specs.input_specs.convert / unconvert`
+    (data_specs.py:6-42): same tensors, same image back; `convert_uint8` + the CUDA path's arithmetic
+    ((x / 255 - mean) / stddev, csrc/misc.cu stem gather) is the same map."""
+    import importlib.util
+    import numpy as np
+    import PIL.Image
+    from margipose_b200.data_specs import ImageSpecs
+    spec = importlib.util.spec_from_file_location('_ref_data_specs', '/root/reference/src/margipose/data_specs.py')
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(5)
+    img = PIL.Image.fromarray(rng.integers(0, 256, (48, 64, 3), dtype=np.uint8), 'RGB')
+    for mean, std in [(ImageSpecs.IMAGENET_MEAN, ImageSpecs.IMAGENET_STDDEV), (None, None)]:
+        ours, theirs = ImageSpecs(256, mean, std), ref.ImageSpecs(256, mean, std)
+        a, b = ours.convert(img), theirs.convert(img)
+        assert a.dtype == torch.float32 and a.shape == (3, 48, 64) and torch.equal(a, b)
+        assert np.array_equal(np.array(ours.unconvert(a)), np.array(theirs.unconvert(b)))
+        assert torch.equal(a, b), 'unconvert must not modify its argument'
+    u8 = ImageSpecs(256, ImageSpecs.IMAGENET_MEAN, ImageSpecs.IMAGENET_STDDEV).convert_uint8(img)
+    assert u8.dtype == torch.uint8 and u8.shape == (48, 64, 3)
+    mean, std = torch.tensor(ImageSpecs.IMAGENET_MEAN), torch.tensor(ImageSpecs.IMAGENET_STDDEV)
+    fused = ((u8.float() / 255 - mean) / std).permute(2, 0, 1)
+    host = ImageSpecs(256, ImageSpecs.IMAGENET_MEAN, ImageSpecs.IMAGENET_STDDEV).convert(img)
+    torch.testing.assert_close(fused, host, rtol=0, atol=1e-6)
+    # greyscale input is promoted to RGB, as torchvision's to_tensor would not do silently: the model needs 3 channels
+    grey = PIL.Image.fromarray(rng.integers(0, 256, (8, 8), dtype=np.uint8), 'L')
+    assert ImageSpecs(256).convert(grey).shape == (3, 8, 8)
